@@ -1,0 +1,188 @@
+/*
+ * tfrt_b200.h -- C ABI of libtfrt_b200.so: the B200 (sm_100a) implementation of the tfrt
+ * ray-trace hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (ecpoppenheimer/TensorFlowRayTrace) is pure Python and has no FFI; its extension
+ * seams for this path are Python call sites.  Every entry point below names the reference
+ * interface it replaces (path:line under the reference tree).  INTEGRATION.md shows the ctypes
+ * stub a tfrt maintainer would add at each seam.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - All work is enqueued on the given stream (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no allocation: the caller owns every buffer, including workspaces.
+ *   - Return value 0 = success; nonzero = error, message in tfrt_last_error() (thread local).
+ *   - Rays are structure-of-arrays fp32, "slot" indexed: slot i is source ray i for the whole
+ *     trace (rays never split: StandardReaction emits exactly one child per active ray,
+ *     tfrt/operation.py:305-307), so per-ray history is addressed by (iteration, slot).
+ *   - Triangles are the merged boundary set in the reference's order optical -> stop -> target
+ *     (tfrt/engine.py:1015-1018); categories OPTICAL=0, STOP=1, TARGET=2 (tfrt/engine.py:14-16).
+ *   - Outputs for rays without a valid hit are unspecified, as in the reference
+ *     (tfrt/engine.py:1110-1114); no entry point ever writes NaN for miss / parallel / TIR.
+ */
+#ifndef TFRT_B200_H
+#define TFRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFRT_B200_ABI_VERSION 1
+
+/* ray status after one projection (tfrt/engine.py:2063-2111) */
+#define TFRT_STATUS_ACTIVE 0   /* hit an OPTICAL boundary: reacts and continues */
+#define TFRT_STATUS_STOPPED 1  /* hit a STOP boundary */
+#define TFRT_STATUS_FINISHED 2 /* hit a TARGET boundary */
+#define TFRT_STATUS_DEAD 3     /* no valid intersection */
+
+/* material kinds: refractive index n(lambda[nm]) (tfrt/materials.py:25-104) */
+#define TFRT_MAT_CONSTANT 0  /* n = c[0]                                  (build_constant_material,
+                                vacuum: c0=1, reflective: c0=0) */
+#define TFRT_MAT_SELLMEIER 1 /* n = sqrt(1 + sum_k c[2k] x^2/(x^2 - c[2k+1])), k<3
+                                (crown_glass, flint_glass, fused_silica, polycarbonate) */
+#define TFRT_MAT_LAURENT 2   /* n = sqrt(c0 + c1 x^2 + c2 x^4 + c3 x^-2 + c4 x^-4 + c5 x^-6 + c6 x^-8)
+                                (acrylic) */
+#define TFRT_MAT_POLY 3      /* n = c0 + c1 x^2 + c2 x^-2                 (soda_lime) */
+
+typedef struct {
+    int32_t kind;
+    int32_t _pad;
+    double c[7];
+} TfrtMaterial;
+
+const char *tfrt_last_error(void);
+int tfrt_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  vertices -> triangle fields.
+ * Replaces TriangleBoundaryBase.update_fields_from_vertices (tfrt/boundaries.py:890-923):
+ * gathers the three corners of every face and computes the unit face normal
+ * normalize((p2-p1) x (p3-p2)).  faces is (F,3) int32 (no pyvista "3" prefix column).
+ * tri_out[9] are the xp,yp,zp,x1,y1,z1,x2,y2,z2 field arrays (F each); norm_out is (F,3).
+ */
+int tfrt_faces_forward(const float *vertices, const int32_t *faces, int32_t n_faces,
+                       float *const tri_out[9], float *norm_out, void *stream);
+
+/* VJP of tfrt_faces_forward.  g_tri[9] / g_norm are cotangents of the outputs (any may be NULL);
+ * update_map is the optional (F,3) uint8 vertex_update_map (0 => tf.stop_gradient on that corner,
+ * tfrt/boundaries.py:900-913).  g_vertices (V,3) fp32 is OVERWRITTEN (zeroed, then accumulated). */
+int tfrt_faces_backward(const float *vertices, const int32_t *faces, const uint8_t *update_map,
+                        int32_t n_faces, int32_t n_vertices, const float *const g_tri[9],
+                        const float *g_norm, float *g_vertices, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Triangle tile packing for the intersection kernel (no reference equivalent: the reference
+ * re-derives edge vectors for all M x N pairs, tfrt/geometry.py:286-298).
+ * tfrt_packed_floats(T) floats of workspace; size_eps is OpticalSystemBase.size_epsilion
+ * (tfrt/engine.py:177-179), folded into the packed plane offsets.
+ */
+size_t tfrt_packed_floats(int32_t n_tri);
+int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps, float *packed,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * b1  intersection seam.
+ * Replaces OpticalSystem3D._intersection (tfrt/engine.py:1102-1166), i.e.
+ * geometry.line_triangle_intersect (tfrt/geometry.py:191-320) + validity pruning + nearest
+ * hit (argmin over triangles, lowest index on ties) + gather.
+ * ray[6] = x_start,y_start,z_start,x_end,y_end,z_end (N each).  Outputs (N each): x,y,z, valid,
+ * ray_u, trig_u, trig_v, gather_trig (gather_ray is arange(N) in the reference and is omitted).
+ * `hit_ws` is N uint64 of workspace.
+ */
+int tfrt_intersect3d(const float *const ray[6], int32_t n_rays, const float *const tri[9],
+                     const float *packed, int32_t n_tri, float intersect_eps, float size_eps,
+                     float ray_start_eps, uint64_t *hit_ws, float *x, float *y, float *z,
+                     uint8_t *valid, float *ray_u, float *trig_u, float *trig_v,
+                     int32_t *gather_trig, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * b4  whole-loop seam: OpticalEngine.ray_trace (tfrt/engine.py:2311-2330) with
+ * process_projection_3D (:1988-2191), single_pass (:2193-2302) and StandardReaction.main
+ * (tfrt/operation.py:255-307) + geometry.snells_law_3D (tfrt/geometry.py:671-753) fused.
+ */
+typedef struct {
+    int32_t n_rays;         /* N source rays */
+    int32_t n_tri;          /* T merged triangles */
+    int32_t n_optical;      /* the first n_optical triangles are OPTICAL */
+    int32_t max_iterations; /* K */
+    float intersect_eps;    /* OpticalSystemBase.intersect_epsilion  tfrt/engine.py:177 */
+    float size_eps;         /* .size_epsilion (must equal the value used for `packed`) */
+    float ray_start_eps;    /* .ray_start_epsilion */
+    float new_ray_length;   /* OpticalEngine.new_ray_length  tfrt/engine.py:1228 */
+    int32_t index_mode;     /* 1: StandardReaction("index") mat_in/mat_out + materials table;
+                               0: ("value") per-triangle n_in / n_out */
+    int32_t n_materials;
+
+    const float *src[7];    /* x_start,y_start,z_start,x_end,y_end,z_end,wavelength; N each */
+    const float *tri[9];    /* xp,yp,zp,x1,y1,z1,x2,y2,z2; T each */
+    const float *norm;      /* (T,3) */
+    const int32_t *category; /* T */
+    const int32_t *mat_in;  /* n_optical (index mode) */
+    const int32_t *mat_out;
+    const float *n_in;      /* n_optical (value mode) */
+    const float *n_out;
+    const TfrtMaterial *materials; /* n_materials, device */
+    const float *packed;    /* tfrt_pack_triangles output */
+
+    /* workspace + history ("tape"), all caller-allocated */
+    float *cur[6];          /* N each: working ray state (start, end) per slot */
+    uint64_t *hit;          /* N */
+    float *tape_f;          /* K*9*N : per iteration Sx,Sy,Sz,Px,Py,Pz,ray_u,trig_u,trig_v */
+    int32_t *tape_tri;      /* K*N : merged triangle index of the hit (-1: none) */
+    uint8_t *tape_status;   /* K*N : TFRT_STATUS_*; 255 = slot not live at that iteration */
+    int32_t *tape_outpos;   /* K*N : position of the slot in its category list at that iteration */
+    int32_t *live;          /* (K+1)*N : live[k] = slots entering iteration k, ascending */
+    int32_t *cat_ids[3];    /* N each: slots that STOPPED / FINISHED / DIED, iteration-major */
+    int32_t *block_counts;  /* 8*ceil(N/256) */
+    int32_t *counters;      /* (K+1)*4: [k][0]=live entering k, [k][1..3]=cumulative
+                               stopped/finished/dead before k */
+} TfrtTrace3DArgs;
+
+int tfrt_trace3d_forward(const TfrtTrace3DArgs *args, void *stream);
+
+/* Materialise one history set in the reference's order (concat over iterations of the
+ * order-preserving masks, tfrt/engine.py:2074-2111, :1379-1399).
+ * which: 0 active, 1 stopped, 2 finished, 3 dead.  `counters_host` is the (K+1)*4 counters
+ * array copied to the host.  out[6] = x_start..z_end (total each), out_slot = source slot of
+ * every output ray (for inherited fields, tfrt/engine.py:2242-2257), out_iter = iteration.
+ * dead_ray_length < 0 => unchanged (tfrt/engine.py:2036-2046).  Returns the total through
+ * *n_out (host). */
+int tfrt_history_count(const TfrtTrace3DArgs *args, const int32_t *counters_host, int which,
+                       int64_t *n_out);
+int tfrt_materialize3d(const TfrtTrace3DArgs *args, const int32_t *counters_host, int which,
+                       float dead_ray_length, float *const out[6], int32_t *out_slot,
+                       int32_t *out_iter, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * b5  gradient seam: tape.gradient(error, parameters) (tfrt/optimizer.py:216-220) restricted to
+ * the trace: cotangents of the materialised history -> cotangents of triangle fields / norm /
+ * source rays.  g_hist[which][6] are cotangents of the arrays produced by tfrt_materialize3d
+ * (NULL where absent).  g_tri (T,9)+g_norm (T,3) are accumulated in fp64 into g_acc (T*12
+ * doubles, zeroed by the call), then written to fp32 g_tri_out[9] (T each) and g_norm_out (T,3).
+ * g_src[6] (N each, may be NULL) receives d/d(source start,end).
+ */
+typedef struct {
+    const float *g_hist[4][6];
+    double *g_acc;            /* T*12 */
+    float *g_ray_ws;          /* 6*N workspace (per-slot running cotangent of the live ray) */
+    float *g_tri_out[9];
+    float *g_norm_out;
+    float *g_src[6];
+    float dead_ray_length;    /* value used when materialising dead rays; < 0 => unchanged */
+} TfrtTrace3DBwdArgs;
+
+int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_host,
+                          const TfrtTrace3DBwdArgs *bwd, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helpers (roofline denominators): run an FFMA-only loop on every SM and return the
+ * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2). */
+int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFRT_B200_H */

@@ -1,0 +1,124 @@
+"""
+ctypes binding of libtfrt_b200.so (the C ABI declared in include/tfrt_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if it cannot be
+loaded, or a call fails, a RuntimeError is raised.  Calling a compute entry point without a
+CUDA device raises as well (the library returns a CUDA error).
+"""
+
+import ctypes
+import os
+
+from . import _build
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_void_p = ctypes.c_void_p
+
+
+class TfrtMaterial(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("_pad", ctypes.c_int32), ("c", ctypes.c_double * 7)]
+
+
+class TfrtTrace3DArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_rays", ctypes.c_int32),
+        ("n_tri", ctypes.c_int32),
+        ("n_optical", ctypes.c_int32),
+        ("max_iterations", ctypes.c_int32),
+        ("intersect_eps", ctypes.c_float),
+        ("size_eps", ctypes.c_float),
+        ("ray_start_eps", ctypes.c_float),
+        ("new_ray_length", ctypes.c_float),
+        ("index_mode", ctypes.c_int32),
+        ("n_materials", ctypes.c_int32),
+        ("src", c_void_p * 7),
+        ("tri", c_void_p * 9),
+        ("norm", c_void_p),
+        ("category", c_void_p),
+        ("mat_in", c_void_p),
+        ("mat_out", c_void_p),
+        ("n_in", c_void_p),
+        ("n_out", c_void_p),
+        ("materials", c_void_p),
+        ("packed", c_void_p),
+        ("cur", c_void_p * 6),
+        ("hit", c_void_p),
+        ("tape_f", c_void_p),
+        ("tape_tri", c_void_p),
+        ("tape_status", c_void_p),
+        ("tape_outpos", c_void_p),
+        ("live", c_void_p),
+        ("cat_ids", c_void_p * 3),
+        ("block_counts", c_void_p),
+        ("counters", c_void_p),
+    ]
+
+
+class TfrtTrace3DBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("g_hist", (c_void_p * 6) * 4),
+        ("g_acc", c_void_p),
+        ("g_ray_ws", c_void_p),
+        ("g_tri_out", c_void_p * 9),
+        ("g_norm_out", c_void_p),
+        ("g_src", c_void_p * 6),
+        ("dead_ray_length", ctypes.c_float),
+    ]
+
+
+# every symbol include/tfrt_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "tfrt_last_error", "tfrt_abi_version",
+    "tfrt_faces_forward", "tfrt_faces_backward",
+    "tfrt_packed_floats", "tfrt_pack_triangles",
+    "tfrt_intersect3d",
+    "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
+    "tfrt_trace3d_backward",
+    "tfrt_fp32_peak",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if needed) libtfrt_b200.so; raises RuntimeError on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB_PATH):
+        _build.build()
+    try:
+        lib = ctypes.CDLL(_build.LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise RuntimeError(f"tensorflowraytrace_b200: cannot load {_build.LIB_PATH}: {e}") from e
+    lib.tfrt_last_error.restype = ctypes.c_char_p
+    lib.tfrt_abi_version.restype = ctypes.c_int
+    lib.tfrt_packed_floats.restype = ctypes.c_size_t
+    lib.tfrt_packed_floats.argtypes = [ctypes.c_int32]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().tfrt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as c_void_p."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors, n):
+    arr = (c_void_p * n)()
+    for i in range(n):
+        t = tensors[i] if i < len(tensors) else None
+        arr[i] = 0 if t is None else t.data_ptr()
+    return arr

@@ -1,0 +1,89 @@
+// abi.cu -- error plumbing, version, and the fp32 peak micro-benchmarks (roofline denominators).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tfrt_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *tfrt_last_error(void) { return g_err; }
+extern "C" int tfrt_abi_version(void) { return TFRT_B200_ABI_VERSION; }
+
+namespace {
+
+// 8 independent accumulator chains per thread, register-only: measures the FMA pipe.
+__global__ void __launch_bounds__(256) k_ffma_scalar(int iters, float seed, float *sink) {
+    float a[8], b = seed, c = seed * 0.5f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;   // never true; keeps the loop alive
+}
+
+__global__ void __launch_bounds__(256) k_ffma_packed(int iters, float seed, float *sink) {
+    float2 a[8], b = make_float2(seed, seed * 1.5f), c = make_float2(seed * 0.5f, seed * 0.25f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(seed + i, seed - i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], b, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream) {
+    TFRT_REQUIRE(flops_per_s && iters > 0, "tfrt_fp32_peak: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    TFRT_CHECK_CUDA(cudaGetDevice(&dev));
+    TFRT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *sink = nullptr;
+    TFRT_CHECK_CUDA(cudaMalloc(&sink, sizeof(float)));
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    TFRT_CHECK_CUDA(cudaEventCreate(&e0));
+    TFRT_CHECK_CUDA(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition is the warm-up
+        TFRT_CHECK_CUDA(cudaEventRecord(e0, st));
+        if (packed)
+            k_ffma_packed<<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
+        else
+            k_ffma_scalar<<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
+        TFRT_CHECK_CUDA(cudaEventRecord(e1, st));
+        TFRT_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        TFRT_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    const double fmas = (double)blocks * threads * (double)iters * 64.0 * (packed ? 2.0 : 1.0);
+    *flops_per_s = 2.0 * fmas / (best_ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

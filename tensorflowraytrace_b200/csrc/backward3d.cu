@@ -1,0 +1,307 @@
+// backward3d.cu -- K2: reverse pass of the trace loop (the tf.GradientTape of
+// tfrt/optimizer.py:216-220 restricted to OpticalEngine.ray_trace).
+//
+// The forward tape holds, per (iteration k, slot): ray start S, projected end P (hit H or the
+// unchanged end for a miss), ray_u t, barycentrics (u, v), hit triangle, status and the slot's
+// position in the output list it was appended to.  argmin / masks / barycentric comparisons carry
+// no gradient in the reference, so the VJP is O(rays x iterations): walk k = K-1 .. 0 and apply,
+// per live ray, the closed forms (derived in DESIGN.md, checked against float64 autograd of the
+// oracle in tests/):
+//
+//   reaction (ACTIVE only, tfrt/geometry.py:715-753), new ray (S', E') = (H, H + L w):
+//       g_w = L g_E' ;  g_H = g_S' + g_E' (+ history cotangent on H)
+//       refract: c = sgn(nu) sqrt(r) - eta nu, c' = sgn(nu) eta^2 nu / sqrt(r) - eta
+//                g_n^ = c g_w + (g_w.n^) c' u^ ;  g_u^ = eta g_w + (g_w.n^) c' n^
+//       reflect: g_u^ = g_w - 2 (g_w.n^) n^ ;    g_n^ = -2 [nu g_w + (g_w.n^) u^]
+//       normalisations: g_x = (g_y^ - (g_y^.y^) y^) / |x|   for x = H - S and x = norm
+//   hit point (tfrt/geometry.py:286-318), H = S + t D on the plane of (A, B, C), m = e1 x e2:
+//       kappa = (g_H.D)/(m.D) ; g_A = (1-u-v) kappa m ; g_B = u kappa m ; g_C = v kappa m
+//       g_S += (1-t)(g_H - kappa m) ;  g_E = t (g_H - kappa m)
+//
+// Triangle cotangents are accumulated in fp64 with warp-aggregated atomics (lanes that hit the
+// same triangle are combined first), then rounded once to fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBwdThreads = 256;
+
+struct BwdParams {
+    int n_rays, k, is_last, index_mode;
+    int n_live;
+    int active_offset;          // position of this iteration's first ray in the active history
+    double new_ray_length, dead_ray_length;
+    const int32_t *live;        // live[k]
+    const float *tape_f;        // tape_f + k*9*N
+    const int32_t *tape_tri;
+    const uint8_t *tape_status;
+    const int32_t *tape_outpos;
+    const float *g_hist[4][6];
+    const float *tri[9];
+    const float *norm;
+    const float *src_wavelength;
+    const int32_t *mat_in, *mat_out;
+    const float *n_in, *n_out;
+    const TfrtMaterial *materials;
+    float *g_ray[6];            // running cotangent of the ray entering iteration k+1 / k
+    double *g_acc;              // T*12
+    float *g_src[6];            // written at k == 0 when non-null
+};
+
+// Sum `vals[12]` over the lanes of `peers` (lanes sharing one triangle) into the group's lowest
+// lane.  Groups are tiny for incoherent rays, so a rank-by-rank gather is enough.
+__device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double vals[12],
+                                                bool &is_leader) {
+    const int n = __popc(peers);
+    int maxn = n;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, off));
+    const int leader = __ffs(peers) - 1;
+    is_leader = (lane == leader);
+    for (int step = 1; step < maxn; ++step) {
+        const unsigned src = __fns(peers, 0, step + 1);   // lane of the peer with rank `step`
+        const int src_lane = (src == 0xffffffffu) ? lane : (int)src;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const double other = __shfl_sync(0xffffffffu, vals[c], src_lane);
+            if (is_leader && step < n) vals[c] += other;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
+    const int p = blockIdx.x * kBwdThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const size_t N = (size_t)P.n_rays;
+    bool contributes = false;
+    int tri = -1;
+    double acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc[c] = 0.0;
+
+    if (p < P.n_live) {
+        const int slot = P.live[p];
+        const int status = P.tape_status[slot];
+        tri = P.tape_tri[slot];
+        const float *tf = P.tape_f;
+        const double S[3] = {tf[0 * N + slot], tf[1 * N + slot], tf[2 * N + slot]};
+        const double Pt[3] = {tf[3 * N + slot], tf[4 * N + slot], tf[5 * N + slot]};
+        const double t = tf[6 * N + slot], u = tf[7 * N + slot], v = tf[8 * N + slot];
+
+        // cotangent of this iteration's history record (start, projected end)
+        double ghS[3] = {0, 0, 0}, ghP[3] = {0, 0, 0};
+        {
+            const int pos = P.tape_outpos[slot] + (status == TFRT_STATUS_ACTIVE ? P.active_offset : 0);
+            const float *const *g = P.g_hist[status];
+            for (int c = 0; c < 3; ++c) {
+                if (g[c]) ghS[c] = g[c][pos];
+                if (g[3 + c]) ghP[c] = g[3 + c][pos];
+            }
+        }
+        double gS[3], gE[3];
+        if (status == TFRT_STATUS_DEAD) {
+            // ray unchanged (optionally rescaled: end' = S + L (E - S), tfrt/engine.py:2036-2046)
+            const double L = P.dead_ray_length;
+            for (int c = 0; c < 3; ++c) {
+                if (L >= 0.0) {
+                    gS[c] = ghS[c] + (1.0 - L) * ghP[c];
+                    gE[c] = L * ghP[c];
+                } else {
+                    gS[c] = ghS[c];
+                    gE[c] = ghP[c];
+                }
+            }
+        } else {
+            double A[3], B[3], C[3];
+            for (int c = 0; c < 3; ++c) {
+                A[c] = P.tri[c][tri];
+                B[c] = P.tri[3 + c][tri];
+                C[c] = P.tri[6 + c][tri];
+            }
+            double gH[3] = {ghP[0], ghP[1], ghP[2]};
+            double gSd[3] = {ghS[0], ghS[1], ghS[2]};
+            if (status == TFRT_STATUS_ACTIVE) {
+                double gSn[3], gEn[3];
+                for (int c = 0; c < 3; ++c) {
+                    gSn[c] = P.is_last ? 0.0 : (double)P.g_ray[c][slot];
+                    gEn[c] = P.is_last ? 0.0 : (double)P.g_ray[3 + c][slot];
+                }
+                double gw[3];
+                for (int c = 0; c < 3; ++c) {
+                    gw[c] = P.new_ray_length * gEn[c];
+                    gH[c] += gSn[c] + gEn[c];
+                }
+                // recompute the reaction's intermediates (same formulas as the forward kernel)
+                double d[3] = {Pt[0] - S[0], Pt[1] - S[1], Pt[2] - S[2]};
+                const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                const double dinv = rsqrt(fmax(d2, 1e-12));
+                const double uh[3] = {d[0] * dinv, d[1] * dinv, d[2] * dinv};
+                const double nr[3] = {P.norm[3 * tri], P.norm[3 * tri + 1], P.norm[3 * tri + 2]};
+                const double n2 = nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2];
+                const double ninv = rsqrt(fmax(n2, 1e-12));
+                const double nh[3] = {nr[0] * ninv, nr[1] * ninv, nr[2] * ninv};
+                const double nu = nh[0] * uh[0] + nh[1] * uh[1] + nh[2] * uh[2];
+                double n_in, n_out;
+                if (P.index_mode) {
+                    const double wl = P.src_wavelength[slot];
+                    n_in = tfrt_material_n(P.materials[P.mat_in[tri]], wl);
+                    n_out = tfrt_material_n(P.materials[P.mat_out[tri]], wl);
+                } else {
+                    n_in = P.n_in[tri];
+                    n_out = P.n_out[tri];
+                }
+                const bool in_safe = n_in != 0.0, out_safe = n_out != 0.0;
+                const double nis = in_safe ? n_in : 1.0, nos = out_safe ? n_out : 1.0;
+                const double eta = (nu > 0.0) ? (out_safe ? nis / nos : 0.0)
+                                              : (in_safe ? nos / nis : 0.0);
+                const double r = 1.0 - eta * eta + eta * eta * nu * nu;
+                const double gwn = gw[0] * nh[0] + gw[1] * nh[1] + gw[2] * nh[2];
+                double g_uh[3], g_nh[3];
+                if (r < 0.0 || n_in == 0.0) {
+                    for (int c = 0; c < 3; ++c) {
+                        g_uh[c] = gw[c] - 2.0 * gwn * nh[c];
+                        g_nh[c] = -2.0 * (nu * gw[c] + gwn * uh[c]);
+                    }
+                } else {
+                    const double sgn = (nu > 0.0) ? 1.0 : ((nu < 0.0) ? -1.0 : 0.0);
+                    const double sq = sqrt(r);
+                    const double cc = sgn * sq - eta * nu;
+                    const double cp = (sq > 0.0 ? sgn * eta * eta * nu / sq : 0.0) - eta;
+                    for (int c = 0; c < 3; ++c) {
+                        g_nh[c] = cc * gw[c] + gwn * cp * uh[c];
+                        g_uh[c] = eta * gw[c] + gwn * cp * nh[c];
+                    }
+                }
+                // through the two normalisations (x * rsqrt(max(|x|^2, 1e-12)))
+                if (d2 > 1e-12) {
+                    const double dot = g_uh[0] * uh[0] + g_uh[1] * uh[1] + g_uh[2] * uh[2];
+                    for (int c = 0; c < 3; ++c) {
+                        const double gd = (g_uh[c] - dot * uh[c]) * dinv;
+                        gH[c] += gd;
+                        gSd[c] -= gd;
+                    }
+                } else {
+                    for (int c = 0; c < 3; ++c) {
+                        gH[c] += g_uh[c] * dinv;
+                        gSd[c] -= g_uh[c] * dinv;
+                    }
+                }
+                {
+                    const double dot = g_nh[0] * nh[0] + g_nh[1] * nh[1] + g_nh[2] * nh[2];
+                    for (int c = 0; c < 3; ++c)
+                        acc[9 + c] = (n2 > 1e-12) ? (g_nh[c] - dot * nh[c]) * ninv : g_nh[c] * ninv;
+                }
+            }
+            // hit-point block
+            const double e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+            const double e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+            const double m[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                                 e1[0] * e2[1] - e1[1] * e2[0]};
+            // D is only needed up to scale: use H - S (t > 0 for a valid hit)
+            const double D[3] = {Pt[0] - S[0], Pt[1] - S[1], Pt[2] - S[2]};
+            const double mD = m[0] * D[0] + m[1] * D[1] + m[2] * D[2];
+            const double gD = gH[0] * D[0] + gH[1] * D[1] + gH[2] * D[2];
+            const double kappa = (mD != 0.0) ? gD / mD : 0.0;
+            const double b0 = 1.0 - u - v;
+            for (int c = 0; c < 3; ++c) {
+                const double km = kappa * m[c];
+                acc[c] = b0 * km;
+                acc[3 + c] = u * km;
+                acc[6 + c] = v * km;
+                const double proj = gH[c] - km;
+                gS[c] = gSd[c] + (1.0 - t) * proj;
+                gE[c] = t * proj;
+            }
+            contributes = true;
+        }
+        for (int c = 0; c < 3; ++c) {
+            P.g_ray[c][slot] = (float)gS[c];
+            P.g_ray[3 + c][slot] = (float)gE[c];
+            if (P.k == 0 && P.g_src[c]) {
+                P.g_src[c][slot] = (float)gS[c];
+                P.g_src[3 + c][slot] = (float)gE[c];
+            }
+        }
+    }
+
+    // warp-aggregated fp64 atomics into the per-triangle accumulators
+    const unsigned active = __ballot_sync(0xffffffffu, contributes);
+    if (active == 0) return;
+    const int key = contributes ? tri : -1 - lane;   // non-contributors never match anybody
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    bool is_leader = false;
+    aggregate_peers(peers, lane, acc, is_leader);
+    if (contributes && is_leader) {
+        double *dst = P.g_acc + (size_t)tri * 12;
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+            if (acc[c] != 0.0) atomicAdd(dst + c, acc[c]);
+    }
+}
+
+__global__ void k_finish_tri_grads(const double *__restrict__ g_acc, int n_tri, float *o0,
+                                   float *o1, float *o2, float *o3, float *o4, float *o5,
+                                   float *o6, float *o7, float *o8, float *g_norm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tri) return;
+    const double *g = g_acc + (size_t)i * 12;
+    o0[i] = (float)g[0]; o1[i] = (float)g[1]; o2[i] = (float)g[2];
+    o3[i] = (float)g[3]; o4[i] = (float)g[4]; o5[i] = (float)g[5];
+    o6[i] = (float)g[6]; o7[i] = (float)g[7]; o8[i] = (float)g[8];
+    g_norm[3 * i] = (float)g[9]; g_norm[3 * i + 1] = (float)g[10]; g_norm[3 * i + 2] = (float)g[11];
+}
+
+}  // namespace
+
+extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch,
+                                     const TfrtTrace3DBwdArgs *b, void *stream) {
+    TFRT_REQUIRE(a && ch && b, "tfrt_trace3d_backward: null argument");
+    TFRT_REQUIRE(b->g_acc && b->g_ray_ws && b->g_norm_out, "tfrt_trace3d_backward: null workspace");
+    for (int c = 0; c < 9; ++c)
+        TFRT_REQUIRE(b->g_tri_out[c], "tfrt_trace3d_backward: null g_tri_out[%d]", c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = a->n_rays, K = a->max_iterations, T = a->n_tri;
+    TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_acc, 0, sizeof(double) * 12 * (size_t)T, st));
+    if (N > 0) {
+        TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_ray_ws, 0, sizeof(float) * 6 * (size_t)N, st));
+        for (int c = 0; c < 6; ++c)
+            if (b->g_src[c]) TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_src[c], 0, sizeof(float) * N, st));
+    }
+    // active-history offsets per iteration
+    long long active_before = 0;
+    for (int k = 0; k < K; ++k) active_before += ch[(k + 1) * 4 + 0];
+    for (int k = K - 1; k >= 0; --k) {
+        active_before -= ch[(k + 1) * 4 + 0];
+        const int n_live = ch[k * 4 + 0];
+        if (n_live <= 0) continue;
+        BwdParams P;
+        P.n_rays = N; P.k = k; P.is_last = (k == K - 1); P.index_mode = a->index_mode;
+        P.n_live = n_live;
+        P.active_offset = (int)active_before;
+        P.new_ray_length = a->new_ray_length;
+        P.dead_ray_length = b->dead_ray_length;
+        P.live = a->live + (size_t)k * N;
+        P.tape_f = a->tape_f + (size_t)k * 9 * N;
+        P.tape_tri = a->tape_tri + (size_t)k * N;
+        P.tape_status = a->tape_status + (size_t)k * N;
+        P.tape_outpos = a->tape_outpos + (size_t)k * N;
+        for (int w = 0; w < 4; ++w)
+            for (int c = 0; c < 6; ++c) P.g_hist[w][c] = b->g_hist[w][c];
+        for (int c = 0; c < 9; ++c) P.tri[c] = a->tri[c];
+        P.norm = a->norm; P.src_wavelength = a->src[6];
+        P.mat_in = a->mat_in; P.mat_out = a->mat_out; P.n_in = a->n_in; P.n_out = a->n_out;
+        P.materials = a->materials;
+        for (int c = 0; c < 6; ++c) {
+            P.g_ray[c] = b->g_ray_ws + (size_t)c * N;
+            P.g_src[c] = b->g_src[c];
+        }
+        P.g_acc = b->g_acc;
+        k_backward3d<<<tfrt_div_up(n_live, kBwdThreads), kBwdThreads, 0, st>>>(P);
+    }
+    k_finish_tri_grads<<<tfrt_div_up(T, 256), 256, 0, st>>>(
+        b->g_acc, T, b->g_tri_out[0], b->g_tri_out[1], b->g_tri_out[2], b->g_tri_out[3],
+        b->g_tri_out[4], b->g_tri_out[5], b->g_tri_out[6], b->g_tri_out[7], b->g_tri_out[8],
+        b->g_norm_out);
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

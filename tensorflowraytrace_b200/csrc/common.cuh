@@ -1,0 +1,127 @@
+// common.cuh -- shared device helpers for libtfrt_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tfrt_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libtfrt_b200 is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+
+void tfrt_set_error(const char *fmt, ...);
+
+#define TFRT_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            tfrt_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                           __LINE__);                                                          \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define TFRT_REQUIRE(cond, ...)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            tfrt_set_error(__VA_ARGS__);                                                       \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// packed triangle layout
+//
+// One triangle = 24 floats = six float4, each coefficient stored twice so that a broadcast
+// LDS.128 yields two ready-made f32x2 operands for the two rays a thread processes together:
+//   q0 = (nx, nx, ny, ny)   q1 = (nz, nz, d , d )      plane:   det = n.D, t' = d - n.O
+//   q2 = (ax, ax, ay, ay)   q3 = (az, az, ad, ad)      u-plane: u = a.P + ad   (+size_eps)
+//   q4 = (bx, bx, by, by)   q5 = (bz, bz, bd, bd)      v-plane: v = b.P + bd   (+size_eps)
+// with n = e1 x e2 (un-normalised, so |det| is the reference's |denominator|,
+// tfrt/geometry.py:300), d = n.A, a = (e2 x n)/|n|^2, b = (n x e1)/|n|^2.
+#define TFRT_TRI_FLOATS 24
+#define TFRT_TILE_TRIS 128                      // triangles per shared-memory stage
+#define TFRT_TILE_BYTES (TFRT_TILE_TRIS * TFRT_TRI_FLOATS * 4)
+
+#define TFRT_NOHIT_KEY 0x7f800000u              // +inf bits: "no valid hit yet"
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA 1-D) PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// refractive index n(lambda) in fp64 (tfrt/materials.py:25-104)
+
+__device__ __forceinline__ double tfrt_material_n(const TfrtMaterial &m, double x) {
+    const double x2 = x * x;
+    switch (m.kind) {
+    case TFRT_MAT_SELLMEIER: {
+        double s = 1.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += m.c[2 * k] * x2 / (x2 - m.c[2 * k + 1]);
+        return sqrt(s);
+    }
+    case TFRT_MAT_LAURENT: {
+        const double i2 = 1.0 / x2;
+        const double i4 = i2 * i2;
+        return sqrt(m.c[0] + m.c[1] * x2 + m.c[2] * x2 * x2 + m.c[3] * i2 + m.c[4] * i4 +
+                    m.c[5] * i4 * i2 + m.c[6] * i4 * i4);
+    }
+    case TFRT_MAT_POLY:
+        return m.c[0] + m.c[1] * x2 + m.c[2] / x2;
+    default:
+        return m.c[0];
+    }
+}

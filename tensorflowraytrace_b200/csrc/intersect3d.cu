@@ -1,0 +1,278 @@
+// intersect3d.cu -- K1a: brute-force nearest ray x triangle hit (sm_100a).
+//
+// Replaces the dense (M,N) evaluation of geometry.line_triangle_intersect
+// (tfrt/geometry.py:191-320) + pruning + argmin of OpticalSystem3D._intersection
+// (tfrt/engine.py:1138-1148).  Every live ray is tested against every triangle.
+//
+// Design
+//  * a thread owns 2*R2 rays kept in registers as R2 f32x2 pairs (origin, direction);
+//  * triangles stream through shared memory in tiles of TFRT_TILE_TRIS, copied by one elected
+//    thread with cp.async.bulk (TMA 1-D) into a 3-stage mbarrier ring;
+//  * per (ray, triangle) the precomputed-plane test costs 18 fp32 ops issued as 9 FFMA2/FADD2
+//    (two rays per instruction) + 1 MUFU.RCP + 4 integer ops:
+//        det = n.D            t' = d - n.O           t = t'/det   (origin pre-shifted by
+//        P   = O + t D        u  = a.P + ad          v = b.P + bd  ray_start_eps so t>=0 <=> valid)
+//        w   = (1+3 eps) - u - v
+//    valid & nearer  <=>  (bits(t) | signbit(u|v|w))  <  best   as unsigned integers;
+//  * the running best is (key, triangle index); ascending scan + strict '<' gives the lowest
+//    index on exact ties (the behaviour of argmin in the reference's CPU kernels);
+//  * optional split of the triangle range over blockIdx.y, merged with a 64-bit atomicMin on
+//    (key << 32 | index) -- same tie rule -- so small ray counts still fill 148 SMs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kStages = 3;
+
+struct __align__(16) IntersectSmem {
+    float4 tile[kStages][TFRT_TILE_TRIS * 6];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+template <int R2>
+__global__ void __launch_bounds__(kThreads)
+k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
+              const float *__restrict__ sz, const float *__restrict__ ex,
+              const float *__restrict__ ey, const float *__restrict__ ez,
+              const int32_t *__restrict__ live, const int32_t *__restrict__ n_live_ptr,
+              int n_live_static, const float4 *__restrict__ packed, int n_tiles,
+              int tiles_per_split, float intersect_eps, float ray_start_eps, float w_one,
+              unsigned long long *__restrict__ hit, int use_atomic) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    IntersectSmem &sm = *reinterpret_cast<IntersectSmem *>(smem_raw);
+
+    const int n_live = n_live_ptr ? *n_live_ptr : n_live_static;
+    const int rays_per_cta = kThreads * 2 * R2;
+    const int base = blockIdx.x * rays_per_cta;
+    if (base >= n_live) return;
+
+    const int tile_begin = blockIdx.y * tiles_per_split;
+    const int tile_end = min(n_tiles, tile_begin + tiles_per_split);
+    const int my_tiles = tile_end - tile_begin;
+    if (my_tiles <= 0) return;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer prologue: fill the ring
+    if (tid == 0) {
+        const int pre = min(kStages, my_tiles);
+        for (int s = 0; s < pre; ++s) {
+            mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
+            bulk_g2s(sm.tile[s], packed + (size_t)(tile_begin + s) * TFRT_TILE_TRIS * 6,
+                     TFRT_TILE_BYTES, &sm.full[s]);
+        }
+    }
+
+    // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
+    float2 Ox[R2], Oy[R2], Oz[R2], Dx[R2], Dy[R2], Dz[R2];
+    uint32_t best[2 * R2];
+    int32_t bidx[2 * R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+        float o[2][3], d[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = base + (2 * r + h) * kThreads + tid;
+            if (p < n_live) {
+                const int slot = live ? live[p] : p;
+                const float ax = sx[slot], ay = sy[slot], az = sz[slot];
+                d[h][0] = ex[slot] - ax;
+                d[h][1] = ey[slot] - ay;
+                d[h][2] = ez[slot] - az;
+                // shift the origin by ray_start_eps along the ray: t_shifted >= 0 <=> ray_u >= eps
+                o[h][0] = fmaf(ray_start_eps, d[h][0], ax);
+                o[h][1] = fmaf(ray_start_eps, d[h][1], ay);
+                o[h][2] = fmaf(ray_start_eps, d[h][2], az);
+            } else {  // padding lane: zero direction => det == 0 => never a hit
+                o[h][0] = o[h][1] = o[h][2] = 0.f;
+                d[h][0] = d[h][1] = d[h][2] = 0.f;
+            }
+            best[2 * r + h] = TFRT_NOHIT_KEY;
+            bidx[2 * r + h] = 0;
+        }
+        Ox[r] = f2(o[0][0], o[1][0]); Oy[r] = f2(o[0][1], o[1][1]); Oz[r] = f2(o[0][2], o[1][2]);
+        Dx[r] = f2(d[0][0], d[1][0]); Dy[r] = f2(d[0][1], d[1][1]); Dz[r] = f2(d[0][2], d[1][2]);
+    }
+
+    const float2 one2 = f2(w_one, w_one);   // 1 + 3*size_eps (eps is folded into ad, bd)
+
+    for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % kStages;
+        const uint32_t parity = (uint32_t)((it / kStages) & 1);
+        mbar_wait(&sm.full[s], parity);
+        const float4 *__restrict__ tile = sm.tile[s];
+        const int tri0 = (tile_begin + it) * TFRT_TILE_TRIS;
+
+#pragma unroll 2
+        for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
+            const float4 q0 = tile[j * 6 + 0];
+            const float4 q1 = tile[j * 6 + 1];
+            const float4 q2 = tile[j * 6 + 2];
+            const float4 q3 = tile[j * 6 + 3];
+            const float4 q4 = tile[j * 6 + 4];
+            const float4 q5 = tile[j * 6 + 5];
+            const float2 nx = f2(q0.x, q0.y), ny = f2(q0.z, q0.w), nz = f2(q1.x, q1.y),
+                         nd = f2(q1.z, q1.w);
+            const float2 ax = f2(q2.x, q2.y), ay = f2(q2.z, q2.w), az = f2(q3.x, q3.y),
+                         ad = f2(q3.z, q3.w);
+            const float2 bx = f2(q4.x, q4.y), by = f2(q4.z, q4.w), bz = f2(q5.x, q5.y),
+                         bd = f2(q5.z, q5.w);
+            const int tri = tri0 + j;
+            uint32_t key[2 * R2];
+            bool cand = false;
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                float2 det = __fmul2_rn(nx, Dx[r]);
+                det = __ffma2_rn(ny, Dy[r], det);
+                det = __ffma2_rn(nz, Dz[r], det);
+                float2 tq = __ffma2_rn(neg2(nx), Ox[r], nd);
+                tq = __ffma2_rn(neg2(ny), Oy[r], tq);
+                tq = __ffma2_rn(neg2(nz), Oz[r], tq);
+                float2 inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
+                const float2 t = __fmul2_rn(tq, inv);
+                const float2 px = __ffma2_rn(t, Dx[r], Ox[r]);
+                const float2 py = __ffma2_rn(t, Dy[r], Oy[r]);
+                const float2 pz = __ffma2_rn(t, Dz[r], Oz[r]);
+                float2 u = __ffma2_rn(ax, px, ad);
+                u = __ffma2_rn(ay, py, u);
+                u = __ffma2_rn(az, pz, u);
+                float2 v = __ffma2_rn(bx, px, bd);
+                v = __ffma2_rn(by, py, v);
+                v = __ffma2_rn(bz, pz, v);
+                float2 w = __fadd2_rn(one2, neg2(u));
+                w = __fadd2_rn(w, neg2(v));
+                // sign bit of (u|v|w) set <=> outside the (inflated) triangle; fold into the key
+                key[2 * r] = __float_as_uint(t.x) |
+                             ((__float_as_uint(u.x) | __float_as_uint(v.x) |
+                               __float_as_uint(w.x)) & 0x80000000u);
+                key[2 * r + 1] = __float_as_uint(t.y) |
+                                 ((__float_as_uint(u.y) | __float_as_uint(v.y) |
+                                   __float_as_uint(w.y)) & 0x80000000u);
+                cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
+            }
+            // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so the
+            // common case pays one vote instead of predicated selects per test.
+            if (__any_sync(0xffffffffu, cand)) {
+#pragma unroll
+                for (int r = 0; r < R2; ++r) {
+                    // |det| >= intersect_eps is the reference's safe-denominator validity
+                    // (tfrt/geometry.py:306); det is re-derived here to keep it out of the
+                    // common path's live registers.
+                    float2 det = __fmul2_rn(nx, Dx[r]);
+                    det = __ffma2_rn(ny, Dy[r], det);
+                    det = __ffma2_rn(nz, Dz[r], det);
+                    if (key[2 * r] < best[2 * r] && fabsf(det.x) >= intersect_eps) {
+                        best[2 * r] = key[2 * r];
+                        bidx[2 * r] = tri;
+                    }
+                    if (key[2 * r + 1] < best[2 * r + 1] && fabsf(det.y) >= intersect_eps) {
+                        best[2 * r + 1] = key[2 * r + 1];
+                        bidx[2 * r + 1] = tri;
+                    }
+                }
+            }
+        }
+
+        // release the stage; the producer refills it with tile it + kStages
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+        if (tid == 0 && it + kStages < my_tiles) {
+            mbar_wait(&sm.empty[s], parity);
+            mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
+            bulk_g2s(sm.tile[s],
+                     packed + (size_t)(tile_begin + it + kStages) * TFRT_TILE_TRIS * 6,
+                     TFRT_TILE_BYTES, &sm.full[s]);
+        }
+        (void)warp;
+    }
+
+    // ---- epilogue: (key, index) per live position
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = base + (2 * r + h) * kThreads + tid;
+            if (p < n_live) {
+                const unsigned long long packed_hit =
+                    ((unsigned long long)best[2 * r + h] << 32) | (uint32_t)bidx[2 * r + h];
+                if (use_atomic)
+                    atomicMin(&hit[p], packed_hit);
+                else
+                    hit[p] = packed_hit;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// host launcher -------------------------------------------------------------------------------
+// n_upper: upper bound of the live count (grid size); the kernel reads the exact count from
+// n_live_ptr when given.
+int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
+                            const int32_t *n_live_ptr, int n_upper, const float *packed,
+                            int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
+                            uint64_t *hit, cudaStream_t stream) {
+    if (n_upper <= 0 || n_tri <= 0) return 0;
+    const int n_tiles = tfrt_div_up(n_tri, TFRT_TILE_TRIS);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        TFRT_CHECK_CUDA(cudaGetDevice(&dev));
+        TFRT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // rays per thread: 8 when that still yields >= 2 waves of CTAs, else 4, else 2
+    int r2 = 4;
+    const long long want = 2LL * num_sms * 4;   // ~4 resident CTAs per SM, two waves
+    while (r2 > 1 && tfrt_div_up(n_upper, kThreads * 2 * r2) < want) r2 >>= 1;
+    const int ray_blocks = tfrt_div_up(n_upper, kThreads * 2 * r2);
+    int splits = 1;
+    if (ray_blocks < want) { long long sp = (want + ray_blocks - 1) / ray_blocks; splits = (int)(sp < n_tiles ? sp : n_tiles); }
+    const int tiles_per_split = tfrt_div_up(n_tiles, splits);
+    splits = tfrt_div_up(n_tiles, tiles_per_split);
+    const int use_atomic = splits > 1;
+    if (use_atomic)
+        TFRT_CHECK_CUDA(cudaMemsetAsync(hit, 0xff, (size_t)n_upper * sizeof(uint64_t), stream));
+
+    const size_t smem = sizeof(IntersectSmem);
+    dim3 grid(ray_blocks, splits), block(kThreads);
+#define TFRT_LAUNCH(R2)                                                                         \
+    do {                                                                                        \
+        static bool attr_set = false;                                                           \
+        if (!attr_set) {                                                                        \
+            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_intersect3d<R2>,                             \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                 (int)smem));                                   \
+            attr_set = true;                                                                    \
+        }                                                                                       \
+        k_intersect3d<R2><<<grid, block, smem, stream>>>(                                       \
+            ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,          \
+            reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, intersect_eps,  \
+            ray_start_eps, 1.0f + 3.0f * size_eps, reinterpret_cast<unsigned long long *>(hit),       \
+            use_atomic);            \
+    } while (0)
+    if (r2 == 4) TFRT_LAUNCH(4);
+    else if (r2 == 2) TFRT_LAUNCH(2);
+    else TFRT_LAUNCH(1);
+#undef TFRT_LAUNCH
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,174 @@
+// pack.cu -- triangle precompute: per-triangle plane coefficients for the intersection kernel,
+// and K3 (vertices -> triangle fields, and its VJP).
+#include "common.cuh"
+
+namespace {
+
+// One thread per (padded) triangle: writes the 24-float record described in common.cuh.
+__global__ void k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
+                                 const float *__restrict__ zp, const float *__restrict__ x1,
+                                 const float *__restrict__ y1, const float *__restrict__ z1,
+                                 const float *__restrict__ x2, const float *__restrict__ y2,
+                                 const float *__restrict__ z2, int n_tri, int n_padded,
+                                 float size_eps, float4 *__restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    // never-hit record: det == 0 and t' = -1  =>  t = -inf (sign bit set)
+    float n[3] = {0.f, 0.f, 0.f}, d = -1.f, a[3] = {0.f, 0.f, 0.f}, ad = 0.f, b[3] = {0.f, 0.f, 0.f},
+          bd = 0.f;
+    if (i < n_tri) {
+        const double A[3] = {xp[i], yp[i], zp[i]};
+        const double e1[3] = {x1[i] - A[0], y1[i] - A[1], z1[i] - A[2]};
+        const double e2[3] = {x2[i] - A[0], y2[i] - A[1], z2[i] - A[2]};
+        const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                             e1[0] * e2[1] - e1[1] * e2[0]};
+        const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+        if (nn > 0.0 && isfinite(nn)) {
+            const double inv = 1.0 / nn;
+            // a = (e2 x N)/|N|^2 : u = a.(P-A);  b = (N x e1)/|N|^2 : v = b.(P-A)
+            const double av[3] = {(e2[1] * N[2] - e2[2] * N[1]) * inv,
+                                  (e2[2] * N[0] - e2[0] * N[2]) * inv,
+                                  (e2[0] * N[1] - e2[1] * N[0]) * inv};
+            const double bv[3] = {(N[1] * e1[2] - N[2] * e1[1]) * inv,
+                                  (N[2] * e1[0] - N[0] * e1[2]) * inv,
+                                  (N[0] * e1[1] - N[1] * e1[0]) * inv};
+            for (int k = 0; k < 3; ++k) {
+                n[k] = (float)N[k];
+                a[k] = (float)av[k];
+                b[k] = (float)bv[k];
+            }
+            d = (float)(N[0] * A[0] + N[1] * A[1] + N[2] * A[2]);
+            ad = (float)(-(av[0] * A[0] + av[1] * A[1] + av[2] * A[2]) + (double)size_eps);
+            bd = (float)(-(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + (double)size_eps);
+        }
+    }
+    float4 *o = packed + (size_t)i * 6;
+    o[0] = make_float4(n[0], n[0], n[1], n[1]);
+    o[1] = make_float4(n[2], n[2], d, d);
+    o[2] = make_float4(a[0], a[0], a[1], a[1]);
+    o[3] = make_float4(a[2], a[2], ad, ad);
+    o[4] = make_float4(b[0], b[0], b[1], b[1]);
+    o[5] = make_float4(b[2], b[2], bd, bd);
+}
+
+// K3 forward: gather face corners, unit normal normalize((p2-p1) x (p3-p2))
+// (tfrt/boundaries.py:890-923).
+__global__ void k_faces_forward(const float *__restrict__ vertices,
+                                const int32_t *__restrict__ faces, int n_faces, float *xp,
+                                float *yp, float *zp, float *x1, float *y1, float *z1, float *x2,
+                                float *y2, float *z2, float *norm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_faces) return;
+    const int i0 = faces[3 * i], i1 = faces[3 * i + 1], i2 = faces[3 * i + 2];
+    const float p0[3] = {vertices[3 * i0], vertices[3 * i0 + 1], vertices[3 * i0 + 2]};
+    const float p1[3] = {vertices[3 * i1], vertices[3 * i1 + 1], vertices[3 * i1 + 2]};
+    const float p2[3] = {vertices[3 * i2], vertices[3 * i2 + 1], vertices[3 * i2 + 2]};
+    xp[i] = p0[0]; yp[i] = p0[1]; zp[i] = p0[2];
+    x1[i] = p1[0]; y1[i] = p1[1]; z1[i] = p1[2];
+    x2[i] = p2[0]; y2[i] = p2[1]; z2[i] = p2[2];
+    const double ux = (double)p1[0] - p0[0], uy = (double)p1[1] - p0[1], uz = (double)p1[2] - p0[2];
+    const double vx = (double)p2[0] - p1[0], vy = (double)p2[1] - p1[1], vz = (double)p2[2] - p1[2];
+    const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+    const double inv = 1.0 / sqrt(cx * cx + cy * cy + cz * cz);
+    norm[3 * i] = (float)(cx * inv);
+    norm[3 * i + 1] = (float)(cy * inv);
+    norm[3 * i + 2] = (float)(cz * inv);
+}
+
+// K3 backward: cotangents of (xp..z2, norm) -> cotangents of vertices (scatter-add).
+//   norm = c/|c|, c = (p1-p0) x (p2-p1)
+//   g_c  = (g_n - (g_n.n) n)/|c| ;  with u = p1-p0, v = p2-p1:  g_u = v x g_c, g_v = g_c x u
+//   g_p0 -= g_u ; g_p1 += g_u - g_v ; g_p2 += g_v
+// update_map[f][k] == 0 blocks the gradient of corner k of face f (tf.stop_gradient,
+// tfrt/boundaries.py:900-913).
+__global__ void k_faces_backward(const float *__restrict__ vertices,
+                                 const int32_t *__restrict__ faces,
+                                 const uint8_t *__restrict__ update_map, int n_faces,
+                                 const float *g_xp, const float *g_yp, const float *g_zp,
+                                 const float *g_x1, const float *g_y1, const float *g_z1,
+                                 const float *g_x2, const float *g_y2, const float *g_z2,
+                                 const float *g_norm, float *__restrict__ g_vertices) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_faces) return;
+    const int idx[3] = {faces[3 * i], faces[3 * i + 1], faces[3 * i + 2]};
+    double g[3][3];
+    g[0][0] = g_xp ? g_xp[i] : 0.0; g[0][1] = g_yp ? g_yp[i] : 0.0; g[0][2] = g_zp ? g_zp[i] : 0.0;
+    g[1][0] = g_x1 ? g_x1[i] : 0.0; g[1][1] = g_y1 ? g_y1[i] : 0.0; g[1][2] = g_z1 ? g_z1[i] : 0.0;
+    g[2][0] = g_x2 ? g_x2[i] : 0.0; g[2][1] = g_y2 ? g_y2[i] : 0.0; g[2][2] = g_z2 ? g_z2[i] : 0.0;
+    if (g_norm) {
+        double p[3][3];
+        for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < 3; ++c) p[k][c] = vertices[3 * idx[k] + c];
+        const double u[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+        const double v[3] = {p[2][0] - p[1][0], p[2][1] - p[1][1], p[2][2] - p[1][2]};
+        const double c[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2],
+                             u[0] * v[1] - u[1] * v[0]};
+        const double len = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        const double n[3] = {c[0] / len, c[1] / len, c[2] / len};
+        const double gn[3] = {g_norm[3 * i], g_norm[3 * i + 1], g_norm[3 * i + 2]};
+        const double dot = gn[0] * n[0] + gn[1] * n[1] + gn[2] * n[2];
+        const double gc[3] = {(gn[0] - dot * n[0]) / len, (gn[1] - dot * n[1]) / len,
+                              (gn[2] - dot * n[2]) / len};
+        const double gu[3] = {v[1] * gc[2] - v[2] * gc[1], v[2] * gc[0] - v[0] * gc[2],
+                              v[0] * gc[1] - v[1] * gc[0]};
+        const double gv[3] = {gc[1] * u[2] - gc[2] * u[1], gc[2] * u[0] - gc[0] * u[2],
+                              gc[0] * u[1] - gc[1] * u[0]};
+        for (int cdim = 0; cdim < 3; ++cdim) {
+            g[0][cdim] -= gu[cdim];
+            g[1][cdim] += gu[cdim] - gv[cdim];
+            g[2][cdim] += gv[cdim];
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        if (update_map && !update_map[3 * i + k]) continue;
+        for (int c = 0; c < 3; ++c) {
+            const float val = (float)g[k][c];
+            if (val != 0.f) atomicAdd(&g_vertices[3 * idx[k] + c], val);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t tfrt_packed_floats(int32_t n_tri) {
+    const size_t tiles = (size_t)tfrt_div_up(n_tri > 0 ? n_tri : 1, TFRT_TILE_TRIS);
+    return tiles * TFRT_TILE_TRIS * TFRT_TRI_FLOATS;
+}
+
+extern "C" int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps,
+                                   float *packed, void *stream) {
+    TFRT_REQUIRE(n_tri >= 0 && packed, "tfrt_pack_triangles: bad arguments");
+    if (n_tri == 0) return 0;
+    const int n_padded = tfrt_div_up(n_tri, TFRT_TILE_TRIS) * TFRT_TILE_TRIS;
+    k_pack_triangles<<<tfrt_div_up(n_padded, 128), 128, 0, (cudaStream_t)stream>>>(
+        tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], n_tri, n_padded,
+        size_eps, reinterpret_cast<float4 *>(packed));
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tfrt_faces_forward(const float *vertices, const int32_t *faces, int32_t n_faces,
+                                  float *const tri_out[9], float *norm_out, void *stream) {
+    TFRT_REQUIRE(vertices && faces && norm_out, "tfrt_faces_forward: null pointer");
+    if (n_faces <= 0) return 0;
+    k_faces_forward<<<tfrt_div_up(n_faces, 128), 128, 0, (cudaStream_t)stream>>>(
+        vertices, faces, n_faces, tri_out[0], tri_out[1], tri_out[2], tri_out[3], tri_out[4],
+        tri_out[5], tri_out[6], tri_out[7], tri_out[8], norm_out);
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tfrt_faces_backward(const float *vertices, const int32_t *faces,
+                                   const uint8_t *update_map, int32_t n_faces, int32_t n_vertices,
+                                   const float *const g_tri[9], const float *g_norm,
+                                   float *g_vertices, void *stream) {
+    TFRT_REQUIRE(vertices && faces && g_vertices, "tfrt_faces_backward: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    TFRT_CHECK_CUDA(cudaMemsetAsync(g_vertices, 0, sizeof(float) * 3 * (size_t)n_vertices, st));
+    if (n_faces <= 0) return 0;
+    k_faces_backward<<<tfrt_div_up(n_faces, 128), 128, 0, st>>>(
+        vertices, faces, update_map, n_faces, g_tri[0], g_tri[1], g_tri[2], g_tri[3], g_tri[4],
+        g_tri[5], g_tri[6], g_tri[7], g_tri[8], g_norm, g_vertices);
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

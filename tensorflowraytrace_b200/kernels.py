@@ -1,0 +1,256 @@
+"""
+Thin Python launchers over the C ABI (include/tfrt_b200.h).  Tensors are torch CUDA tensors used
+purely as device memory; all arithmetic happens in libtfrt_b200.so on the current CUDA stream.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs, check, ptr, ptr_array
+
+TRI_FIELDS = ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")
+RAY_FIELDS = ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")
+HISTORY = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "tensorflowraytrace_b200: kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.to(torch.float32).contiguous()
+
+
+def fp32_peak(packed=1, iters=4096):
+    """Measured fp32 FMA throughput (FLOP/s) of the current device: the roofline denominator."""
+    out = ctypes.c_double(0.0)
+    check(_lib.load().tfrt_fp32_peak(int(packed), int(iters), ctypes.byref(out), _stream()),
+          "tfrt_fp32_peak")
+    return out.value
+
+
+def faces_forward(vertices, faces):
+    """K3 forward.  vertices (V,3) f32 cuda, faces (F,3) int32 cuda -> (tri (9,F), norm (F,3))."""
+    _require_cuda(vertices, faces)
+    vertices = _f32(vertices)
+    F = faces.shape[0]
+    tri = torch.empty((9, F), dtype=torch.float32, device=vertices.device)
+    norm = torch.empty((F, 3), dtype=torch.float32, device=vertices.device)
+    check(_lib.load().tfrt_faces_forward(ptr(vertices), ptr(faces), F,
+                                         ptr_array([tri[i] for i in range(9)], 9), ptr(norm),
+                                         _stream()), "tfrt_faces_forward")
+    return tri, norm
+
+
+def faces_backward(vertices, faces, update_map, g_tri, g_norm):
+    """K3 backward -> g_vertices (V,3) f32."""
+    _require_cuda(vertices, faces)
+    vertices = _f32(vertices)
+    V, F = vertices.shape[0], faces.shape[0]
+    g_vertices = torch.empty((V, 3), dtype=torch.float32, device=vertices.device)
+    g_list = [None] * 9 if g_tri is None else [_f32(g_tri[i]) for i in range(9)]
+    g_norm = None if g_norm is None else _f32(g_norm)
+    check(_lib.load().tfrt_faces_backward(ptr(vertices), ptr(faces), ptr(update_map), F, V,
+                                          ptr_array(g_list, 9), ptr(g_norm), ptr(g_vertices),
+                                          _stream()), "tfrt_faces_backward")
+    return g_vertices
+
+
+def pack_triangles(tri, size_eps):
+    """tri: (9,T) f32 cuda (rows xp..z2) -> packed plane coefficients for the intersect kernel."""
+    _require_cuda(tri)
+    tri = _f32(tri)
+    T = tri.shape[1]
+    lib = _lib.load()
+    packed = torch.empty((lib.tfrt_packed_floats(T),), dtype=torch.float32, device=tri.device)
+    check(lib.tfrt_pack_triangles(ptr_array([tri[i] for i in range(9)], 9), T,
+                                  ctypes.c_float(size_eps), ptr(packed), _stream()),
+          "tfrt_pack_triangles")
+    return packed
+
+
+def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps):
+    """b1 seam: nearest valid hit per ray.  rays (6,N) f32, tri (9,T) f32.  Returns a dict with the
+    reference's field names (tfrt/engine.py:1026-1043, without `norm`)."""
+    _require_cuda(rays, tri, packed)
+    rays, tri = _f32(rays), _f32(tri)
+    N, T = rays.shape[1], tri.shape[1]
+    dev = rays.device
+    hit = torch.empty((max(N, 1),), dtype=torch.int64, device=dev)
+    out = {k: torch.empty((N,), dtype=torch.float32, device=dev)
+           for k in ("x", "y", "z", "ray_u", "trig_u", "trig_v")}
+    valid = torch.empty((N,), dtype=torch.uint8, device=dev)
+    gather_trig = torch.empty((N,), dtype=torch.int32, device=dev)
+    check(_lib.load().tfrt_intersect3d(
+        ptr_array([rays[i] for i in range(6)], 6), N, ptr_array([tri[i] for i in range(9)], 9),
+        ptr(packed), T, ctypes.c_float(intersect_eps), ctypes.c_float(size_eps),
+        ctypes.c_float(ray_start_eps), ptr(hit), ptr(out["x"]), ptr(out["y"]), ptr(out["z"]),
+        ptr(valid), ptr(out["ray_u"]), ptr(out["trig_u"]), ptr(out["trig_v"]), ptr(gather_trig),
+        _stream()), "tfrt_intersect3d")
+    out["valid"] = valid.bool()
+    out["gather_trig"] = gather_trig.long()
+    out["gather_ray"] = torch.arange(N, device=dev)
+    return out
+
+
+def material_table(descriptors, device):
+    """descriptors: list of (kind, [coefficients]) -> device byte tensor of TfrtMaterial."""
+    arr = (TfrtMaterial * max(len(descriptors), 1))()
+    for i, (kind, coef) in enumerate(descriptors):
+        arr[i].kind = int(kind)
+        for j in range(7):
+            arr[i].c[j] = float(coef[j]) if j < len(coef) else 0.0
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
+class Trace3D:
+    """One whole-loop trace (b4 seam): owns the tape / workspace and exposes the histories."""
+
+    def __init__(self, src, tri, norm, category, n_optical, max_iterations, *, packed=None,
+                 mat_in=None, mat_out=None, n_in=None, n_out=None, materials=None, n_materials=0,
+                 intersect_eps=1e-10, size_eps=1e-10, ray_start_eps=1e-10, new_ray_length=1.0):
+        _require_cuda(src, tri, norm, category)
+        self.src = _f32(src)          # (7,N): x_start..z_end, wavelength
+        self.tri = _f32(tri)          # (9,T)
+        self.norm = _f32(norm)        # (T,3)
+        self.category = category.to(torch.int32).contiguous()
+        dev = self.src.device
+        N, T, K = self.src.shape[1], self.tri.shape[1], int(max_iterations)
+        self.N, self.T, self.K = N, T, K
+        self.size_eps = float(size_eps)
+        self.packed = packed if packed is not None else pack_triangles(self.tri, size_eps)
+        self.index_mode = 1 if materials is not None else 0
+        self.mat_in = None if mat_in is None else mat_in.to(torch.int32).contiguous()
+        self.mat_out = None if mat_out is None else mat_out.to(torch.int32).contiguous()
+        self.n_in = None if n_in is None else _f32(n_in)
+        self.n_out = None if n_out is None else _f32(n_out)
+        self.materials = materials
+        n1 = max(N, 1)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.cur = torch.empty((6, n1), dtype=torch.float32, device=dev)
+        self.hit = torch.empty((n1,), dtype=torch.int64, device=dev)
+        self.tape_f = torch.empty((K, 9, n1), dtype=torch.float32, device=dev)
+        self.tape_tri = torch.empty((K, n1), **i32)
+        self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
+        self.tape_outpos = torch.empty((K, n1), **i32)
+        self.live = torch.empty((K + 1, n1), **i32)
+        self.cat_ids = torch.empty((3, n1), **i32)
+        self.block_counts = torch.empty((8 * ((n1 + 255) // 256),), **i32)
+        self.counters = torch.empty(((K + 1) * 4,), **i32)
+        self._counters_host = None
+
+        a = TfrtTrace3DArgs()
+        a.n_rays, a.n_tri, a.n_optical, a.max_iterations = N, T, int(n_optical), K
+        a.intersect_eps, a.size_eps = float(intersect_eps), float(size_eps)
+        a.ray_start_eps, a.new_ray_length = float(ray_start_eps), float(new_ray_length)
+        a.index_mode, a.n_materials = self.index_mode, int(n_materials)
+        for i in range(7):
+            a.src[i] = self.src[i].data_ptr()
+        for i in range(9):
+            a.tri[i] = self.tri[i].data_ptr()
+        a.norm, a.category = self.norm.data_ptr(), self.category.data_ptr()
+        a.mat_in = 0 if self.mat_in is None else self.mat_in.data_ptr()
+        a.mat_out = 0 if self.mat_out is None else self.mat_out.data_ptr()
+        a.n_in = 0 if self.n_in is None else self.n_in.data_ptr()
+        a.n_out = 0 if self.n_out is None else self.n_out.data_ptr()
+        a.materials = 0 if materials is None else materials.data_ptr()
+        a.packed = self.packed.data_ptr()
+        for i in range(6):
+            a.cur[i] = self.cur[i].data_ptr()
+        a.hit, a.tape_f = self.hit.data_ptr(), self.tape_f.data_ptr()
+        a.tape_tri, a.tape_status = self.tape_tri.data_ptr(), self.tape_status.data_ptr()
+        a.tape_outpos, a.live = self.tape_outpos.data_ptr(), self.live.data_ptr()
+        for i in range(3):
+            a.cat_ids[i] = self.cat_ids[i].data_ptr()
+        a.block_counts, a.counters = self.block_counts.data_ptr(), self.counters.data_ptr()
+        self.args = a
+
+    def forward(self):
+        """Enqueue the whole trace loop (asynchronous)."""
+        self._counters_host = None
+        check(_lib.load().tfrt_trace3d_forward(ctypes.byref(self.args), _stream()),
+              "tfrt_trace3d_forward")
+        return self
+
+    @property
+    def counters_host(self):
+        """(K+1, 4) int32 on the host: one small D2H copy, the only sync of a trace."""
+        if self._counters_host is None:
+            self._counters_host = self.counters.cpu().numpy().reshape(self.K + 1, 4).copy()
+        return self._counters_host
+
+    def live_counts(self):
+        """Live rays entering each executed iteration (for the tests/s metric)."""
+        return [int(c) for c in self.counters_host[: self.K, 0]]
+
+    def history_count(self, which):
+        w = HISTORY[which] if isinstance(which, str) else int(which)
+        ch = self.counters_host
+        if w == 0:
+            return int(ch[1:, 0].sum())
+        return int(ch[self.K, w])
+
+    def history(self, which, dead_ray_length=None):
+        """Materialise one ray set in the reference's order.  Returns (rays (6,n) f32,
+        slot (n,) int32 source index, iteration (n,) int32)."""
+        w = HISTORY[which] if isinstance(which, str) else int(which)
+        n = self.history_count(w)
+        dev = self.src.device
+        rays = torch.empty((6, n), dtype=torch.float32, device=dev)
+        slot = torch.empty((n,), dtype=torch.int32, device=dev)
+        it = torch.empty((n,), dtype=torch.int32, device=dev)
+        if n:
+            ch = np.ascontiguousarray(self.counters_host.reshape(-1))
+            drl = -1.0 if dead_ray_length is None else float(dead_ray_length)
+            check(_lib.load().tfrt_materialize3d(
+                ctypes.byref(self.args), ch.ctypes.data_as(ctypes.c_void_p), w,
+                ctypes.c_float(drl), ptr_array([rays[i] for i in range(6)], 6), ptr(slot),
+                ptr(it), _stream()), "tfrt_materialize3d")
+        return rays, slot, it
+
+    def backward(self, g_hist, want_src_grad=False, dead_ray_length=None):
+        """b5 seam.  g_hist: dict which -> (6,n) f32 cotangents of `history(which)` rays (or
+        None).  Returns (g_tri (9,T), g_norm (T,3), g_src (6,N) or None)."""
+        dev = self.src.device
+        b = TfrtTrace3DBwdArgs()
+        keep = []
+        for name, w in HISTORY.items():
+            g = g_hist.get(name)
+            if g is None:
+                continue
+            g = _f32(g)
+            if g.shape != (6, self.history_count(w)):
+                raise ValueError(f"cotangent of {name} rays has shape {tuple(g.shape)}")
+            keep.append(g)
+            for i in range(6):
+                b.g_hist[w][i] = g[i].data_ptr()
+        g_acc = torch.empty((self.T * 12,), dtype=torch.float64, device=dev)
+        g_ray_ws = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev)
+        g_tri = torch.empty((9, self.T), dtype=torch.float32, device=dev)
+        g_norm = torch.empty((self.T, 3), dtype=torch.float32, device=dev)
+        g_src = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev) if want_src_grad else None
+        b.dead_ray_length = -1.0 if dead_ray_length is None else float(dead_ray_length)
+        b.g_acc, b.g_ray_ws = g_acc.data_ptr(), g_ray_ws.data_ptr()
+        for i in range(9):
+            b.g_tri_out[i] = g_tri[i].data_ptr()
+        b.g_norm_out = g_norm.data_ptr()
+        if g_src is not None:
+            for i in range(6):
+                b.g_src[i] = g_src[i].data_ptr()
+        ch = np.ascontiguousarray(self.counters_host.reshape(-1))
+        check(_lib.load().tfrt_trace3d_backward(
+            ctypes.byref(self.args), ch.ctypes.data_as(ctypes.c_void_p), ctypes.byref(b),
+            _stream()), "tfrt_trace3d_backward")
+        del keep
+        return g_tri, g_norm, (None if g_src is None else g_src[:, : self.N])

@@ -1,0 +1,210 @@
+"""
+Deterministic synthetic scenes for the five BASELINE.json configs (NumPy float64).
+
+A scene is plain data (dicts of NumPy arrays) so that the CUDA path, the float64 oracle and
+the benchmark all consume bit-identical inputs.  The recipes follow the reference's own
+scripts and distributions (cited per function); see SURVEY.md section 8(d) for the table.
+
+Scene layout
+------------
+scene["sources"]    : dict field -> (N,) or (N, k) float64   (x_start..z_end, wavelength, rank)
+scene["surfaces"]   : list of parametric optical surfaces, each a dict with
+                      zero_points (V,3), vectors (V,3), parameters (V,), faces (F,3) int64,
+                      mat_in, mat_out (int)
+scene["targets"]    : list of static meshes {vertices (V,3), faces (F,3)}
+scene["stops"]      : list of static meshes
+scene["materials"]  : list of material names (tensorflowraytrace_b200.materials)
+scene["max_iterations"], scene["name"], scene["goal_scale"]
+"""
+
+import math
+
+import numpy as np
+
+from . import mesh_tools
+
+# wavelength constants, nm (reference: tfrt/drawing.py:53-60)
+RED, ORANGE, YELLOW, GREEN, BLUE, PURPLE = 680.0, 620.0, 575.0, 510.0, 450.0, 400.0
+RAINBOW_6 = (RED, ORANGE, YELLOW, GREEN, BLUE, PURPLE)
+
+GOLDEN = math.pi * (1.0 + 5.0 ** 0.5)
+
+
+# ----------------------------------------------------------------------------- distributions
+
+def static_uniform_sphere(angular_size, count):
+    """Golden-spiral unit vectors around +x (tfrt/distributions.py:1726-1747)."""
+    indices = np.arange(count, dtype=np.float64) + 0.5
+    phi = np.arccos(np.linspace(1.0, math.cos(angular_size), count))
+    theta = np.mod(GOLDEN * indices, 2.0 * math.pi)
+    return np.stack([np.cos(phi), np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta)], axis=1)
+
+
+def random_uniform_sphere(angular_size, count, rng):
+    """Uniform-on-cap unit vectors around +x (tfrt/distributions.py:1756-1774)."""
+    phi = np.arccos(rng.uniform(math.cos(angular_size), 1.0, count))
+    theta = np.mod(GOLDEN * rng.uniform(0.0, 1.0, count), 2.0 * math.pi)
+    return np.stack([np.cos(phi), np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta)], axis=1)
+
+
+def random_lambertian_sphere(angular_size, count, rng):
+    """Lambertian unit vectors around +x (tfrt/distributions.py:1815-1850)."""
+    phi = np.arccos(np.sqrt(rng.uniform(math.cos(angular_size) ** 2, 1.0, count)))
+    theta = np.mod(GOLDEN * rng.uniform(0.0, 1.0, count), 2.0 * math.pi)
+    return np.stack([np.cos(phi), np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta)], axis=1)
+
+
+def random_uniform_square(size, count, rng):
+    """(count, 2) points in [-size, size]^2 and their rank = point / size
+    (tfrt/distributions.py:1361-1392)."""
+    pts = np.stack([rng.uniform(-size, size, count), rng.uniform(-size, size, count)], axis=1)
+    return pts, pts / size
+
+
+def make_rays(starts, directions, wavelengths, ray_length=1.0, extra=None):
+    """Field dict of a source: end = start + ray_length * direction
+    (tfrt/sources.py:598-603 for a point source; :820-866 for an angular source)."""
+    starts = np.broadcast_to(np.asarray(starts, dtype=np.float64), directions.shape)
+    ends = starts + ray_length * directions
+    out = {
+        "x_start": np.ascontiguousarray(starts[:, 0]),
+        "y_start": np.ascontiguousarray(starts[:, 1]),
+        "z_start": np.ascontiguousarray(starts[:, 2]),
+        "x_end": np.ascontiguousarray(ends[:, 0]),
+        "y_end": np.ascontiguousarray(ends[:, 1]),
+        "z_end": np.ascontiguousarray(ends[:, 2]),
+        "wavelength": np.ascontiguousarray(
+            np.broadcast_to(np.asarray(wavelengths, dtype=np.float64), (directions.shape[0],))),
+    }
+    if extra:
+        out.update(extra)
+    return out
+
+
+# ----------------------------------------------------------------------------- boundaries
+
+def _to_yz_plane(points, x0):
+    """Map mesh-plane coordinates (a, b, 0) -> (x0, a, b): a cyclic permutation, so face
+    orientation is preserved and a +z mesh normal becomes +x (the role of
+    `zero_points.rotate_y(90)` in dev/simple_3d_optimize.py:62-63)."""
+    return np.stack([np.full(points.shape[0], x0), points[:, 0], points[:, 1]], axis=1)
+
+
+def lens_surfaces(step_count, radius=1.0, thickness=0.2, curvature_radius=2.6):
+    """Two hexagonal parametric surfaces forming a biconvex acrylic lens, pattern of
+    dev/simple_3d_optimize.py:69-81: vectors from FromVectorVG((1,0,0)); first surface norm
+    flipped (faces toward -x), second toward +x; mat_in=1 (lens), mat_out=0 (vacuum)."""
+    pts, faces = mesh_tools.hexagonal_mesh(radius, step_count)
+    sag = mesh_tools.circular_cap_sag(pts, curvature_radius)
+    sag_max = curvature_radius - math.sqrt(curvature_radius ** 2 - radius ** 2)
+    vectors = np.tile(np.array([[1.0, 0.0, 0.0]]), (pts.shape[0], 1))
+    front = {
+        "zero_points": _to_yz_plane(pts, 0.0),
+        "vectors": vectors.copy(),
+        "parameters": sag - sag_max,
+        "faces": np.ascontiguousarray(faces[:, ::-1]),   # flipped norm: points to -x
+        "mat_in": 1, "mat_out": 0,
+    }
+    back = {
+        "zero_points": _to_yz_plane(pts, thickness),
+        "vectors": vectors.copy(),
+        "parameters": sag_max - sag,
+        "faces": faces.copy(),
+        "mat_in": 1, "mat_out": 0,
+    }
+    return [front, back]
+
+
+def static_mesh(points, faces):
+    return {"vertices": np.asarray(points, dtype=np.float64), "faces": np.asarray(faces, dtype=np.int64)}
+
+
+# ----------------------------------------------------------------------------- configs
+
+def config2(ray_count=65536, step_count=13):
+    """3D point source through a 2k-triangle lens, forward only (SURVEY.md 8(d) cfg 2)."""
+    dirs = static_uniform_sphere(math.pi / 8.0, ray_count)
+    sources = make_rays((-1.0, 0.0, 0.0), dirs, YELLOW)
+    tv, tf_ = mesh_tools.plane_mesh((8.0, 0.0, 0.0), 50.0, axis=0)
+    return {
+        "name": f"cfg2_point_source_{ray_count}rays_hex{step_count}",
+        "dimension": 3,
+        "sources": sources,
+        "surfaces": lens_surfaces(step_count),
+        "targets": [static_mesh(tv, tf_)],
+        "stops": [],
+        "materials": ["vacuum", "acrylic"],
+        "max_iterations": 3,
+    }
+
+
+def lens_optimize_config(ray_count, step_count, seed=1234, name="cfg3"):
+    """Imaging-lens optimisation scene (dev/simple_3d_optimize.py:22-89, 128-140):
+    undense angular source at x=-4, lens at x=0..0.2, target at x=8, per-ray goal
+    = -(magnification * object_size) * rank."""
+    rng = np.random.default_rng(seed)
+    source_distance, magnification, object_size = 4.0, 2.0, 0.2
+    base, rank = random_uniform_square(object_size, ray_count, rng)
+    dirs = random_uniform_sphere(math.pi / 16.0, ray_count, rng)
+    starts = np.stack([np.full(ray_count, -source_distance), base[:, 0], base[:, 1]], axis=1)
+    sources = make_rays(starts, dirs, YELLOW, extra={"rank": rank})
+    tv, tf_ = mesh_tools.plane_mesh((source_distance * magnification, 0.0, 0.0), 50.0, axis=0)
+    return {
+        "name": f"{name}_lens_optimize_{ray_count}rays_hex{step_count}",
+        "dimension": 3,
+        "sources": sources,
+        "surfaces": lens_surfaces(step_count),
+        "targets": [static_mesh(tv, tf_)],
+        "stops": [],
+        "materials": ["vacuum", "acrylic"],
+        "max_iterations": 3,
+        "goal_scale": -(magnification * object_size),
+    }
+
+
+def config3(ray_count=1048576, step_count=41, seed=1234):
+    return lens_optimize_config(ray_count, step_count, seed, "cfg3")
+
+
+def config5(ray_count=16777216, step_count=91, seed=1234):
+    return lens_optimize_config(ray_count, step_count, seed, "cfg5")
+
+
+def config4(ray_count=4194304, theta_res=100, z_res=250, seed=4321, max_iterations=16):
+    """Acrylic light guide with multi-bounce TIR and six wavelengths (3D analogue of
+    dev/light_guide.py:31-49)."""
+    rng = np.random.default_rng(seed)
+    pts, faces = mesh_tools.cylindrical_mesh((0.0, 0.0, 0.0), (10.0, 0.0, 0.0), 0.5, theta_res, z_res)
+    rad = 0.4 * np.sqrt(rng.uniform(0.0, 1.0, ray_count))
+    ang = rng.uniform(0.0, 2.0 * math.pi, ray_count)
+    starts = np.stack([np.full(ray_count, 0.01), rad * np.cos(ang), rad * np.sin(ang)], axis=1)
+    dirs = random_lambertian_sphere(math.pi / 2.5, ray_count, rng)
+    wl = np.asarray(RAINBOW_6, dtype=np.float64)[np.arange(ray_count) % 6]
+    sources = make_rays(starts, dirs, wl, ray_length=0.1)
+    guide = {
+        "zero_points": pts, "vectors": np.zeros_like(pts), "parameters": np.zeros(pts.shape[0]),
+        "faces": faces, "mat_in": 1, "mat_out": 0,
+    }
+    tv, tf_ = mesh_tools.plane_mesh((10.05, 0.0, 0.0), 5.0, axis=0)
+    return {
+        "name": f"cfg4_light_guide_{ray_count}rays_cyl{theta_res}x{z_res}",
+        "dimension": 3,
+        "sources": sources,
+        "surfaces": [guide],
+        "targets": [static_mesh(tv, tf_)],
+        "stops": [],
+        "materials": ["vacuum", "acrylic"],
+        "max_iterations": max_iterations,
+    }
+
+
+def surface_vertices(surface):
+    """zero + parameter * vector (tfrt/boundaries.py:1081-1083)."""
+    return surface["zero_points"] + surface["parameters"][:, None] * surface["vectors"]
+
+
+def triangle_count(scene):
+    n = sum(s["faces"].shape[0] for s in scene["surfaces"])
+    n += sum(s["faces"].shape[0] for s in scene["targets"])
+    n += sum(s["faces"].shape[0] for s in scene["stops"])
+    return n
