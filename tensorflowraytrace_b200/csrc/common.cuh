@@ -39,15 +39,16 @@ static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 
 // ---------------------------------------------------------------------------------------------
 // packed triangle layout
 //
-// One triangle = 24 floats = six float4, each coefficient stored twice so that a broadcast
-// LDS.128 yields two ready-made f32x2 operands for the two rays a thread processes together:
-//   q0 = (nx, nx, ny, ny)   q1 = (nz, nz, d , d )      plane:   det = n.D, t' = d - n.O
-//   q2 = (ax, ax, ay, ay)   q3 = (az, az, ad, ad)      u-plane: u = a.P + ad   (+size_eps)
-//   q4 = (bx, bx, by, by)   q5 = (bz, bz, bd, bd)      v-plane: v = b.P + bd   (+size_eps)
+// One triangle = 12 floats = three float4 (one broadcast LDS.128 each):
+//   q0 = (nx, ny, nz, d )      plane:   det = n.D, t' = d - n.O
+//   q1 = (ax, ay, az, ad)      u-plane: u = a.P + ad   (+size_eps)
+//   q2 = (bx, by, bz, bd)      v-plane: v = b.P + bd   (+size_eps)
 // with n = e1 x e2 (un-normalised, so |det| is the reference's |denominator|,
 // tfrt/geometry.py:300), d = n.A, a = (e2 x n)/|n|^2, b = (n x e1)/|n|^2.
-#define TFRT_TRI_FLOATS 24
-#define TFRT_TILE_TRIS 128                      // triangles per shared-memory stage
+// FFMA2 takes a 32-bit register broadcast to both halves (SASS operand `R.F32`), so a
+// coefficient multiplies the two rays of a pair without being stored twice.
+#define TFRT_TRI_FLOATS 12
+#define TFRT_TILE_TRIS 256                      // triangles per shared-memory stage
 #define TFRT_TILE_BYTES (TFRT_TILE_TRIS * TFRT_TRI_FLOATS * 4)
 
 #define TFRT_NOHIT_KEY 0x7f800000u              // +inf bits: "no valid hit yet"

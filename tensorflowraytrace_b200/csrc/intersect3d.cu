@@ -26,7 +26,7 @@ constexpr int kThreads = 128;
 constexpr int kStages = 3;
 
 struct __align__(16) IntersectSmem {
-    float4 tile[kStages][TFRT_TILE_TRIS * 6];
+    float4 tile[kStages][TFRT_TILE_TRIS * 3];
     uint64_t full[kStages];
     uint64_t empty[kStages];
 };
@@ -74,7 +74,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         const int pre = min(kStages, my_tiles);
         for (int s = 0; s < pre; ++s) {
             mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
-            bulk_g2s(sm.tile[s], packed + (size_t)(tile_begin + s) * TFRT_TILE_TRIS * 6,
+            bulk_g2s(sm.tile[s], packed + (size_t)(tile_begin + s) * TFRT_TILE_TRIS * 3,
                      TFRT_TILE_BYTES, &sm.full[s]);
         }
     }
@@ -121,18 +121,16 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
 
 #pragma unroll 2
         for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
-            const float4 q0 = tile[j * 6 + 0];
-            const float4 q1 = tile[j * 6 + 1];
-            const float4 q2 = tile[j * 6 + 2];
-            const float4 q3 = tile[j * 6 + 3];
-            const float4 q4 = tile[j * 6 + 4];
-            const float4 q5 = tile[j * 6 + 5];
-            const float2 nx = f2(q0.x, q0.y), ny = f2(q0.z, q0.w), nz = f2(q1.x, q1.y),
-                         nd = f2(q1.z, q1.w);
-            const float2 ax = f2(q2.x, q2.y), ay = f2(q2.z, q2.w), az = f2(q3.x, q3.y),
-                         ad = f2(q3.z, q3.w);
-            const float2 bx = f2(q4.x, q4.y), by = f2(q4.z, q4.w), bz = f2(q5.x, q5.y),
-                         bd = f2(q5.z, q5.w);
+            const float4 q0 = tile[j * 3 + 0];
+            const float4 q1 = tile[j * 3 + 1];
+            const float4 q2 = tile[j * 3 + 2];
+            // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
+            const float2 nx = f2(q0.x, q0.x), ny = f2(q0.y, q0.y), nz = f2(q0.z, q0.z),
+                         nd = f2(q0.w, q0.w);
+            const float2 ax = f2(q1.x, q1.x), ay = f2(q1.y, q1.y), az = f2(q1.z, q1.z),
+                         ad = f2(q1.w, q1.w);
+            const float2 bx = f2(q2.x, q2.x), by = f2(q2.y, q2.y), bz = f2(q2.z, q2.z),
+                         bd = f2(q2.w, q2.w);
             const int tri = tri0 + j;
             uint32_t key[2 * R2];
             bool cand = false;
@@ -198,7 +196,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             mbar_wait(&sm.empty[s], parity);
             mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
             bulk_g2s(sm.tile[s],
-                     packed + (size_t)(tile_begin + it + kStages) * TFRT_TILE_TRIS * 6,
+                     packed + (size_t)(tile_begin + it + kStages) * TFRT_TILE_TRIS * 3,
                      TFRT_TILE_BYTES, &sm.full[s]);
         }
         (void)warp;

@@ -4,7 +4,7 @@
 
 namespace {
 
-// One thread per (padded) triangle: writes the 24-float record described in common.cuh.
+// One thread per (padded) triangle: writes the 12-float record described in common.cuh.
 __global__ void k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
                                  const float *__restrict__ zp, const float *__restrict__ x1,
                                  const float *__restrict__ y1, const float *__restrict__ z1,
@@ -42,13 +42,10 @@ __global__ void k_pack_triangles(const float *__restrict__ xp, const float *__re
             bd = (float)(-(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + (double)size_eps);
         }
     }
-    float4 *o = packed + (size_t)i * 6;
-    o[0] = make_float4(n[0], n[0], n[1], n[1]);
-    o[1] = make_float4(n[2], n[2], d, d);
-    o[2] = make_float4(a[0], a[0], a[1], a[1]);
-    o[3] = make_float4(a[2], a[2], ad, ad);
-    o[4] = make_float4(b[0], b[0], b[1], b[1]);
-    o[5] = make_float4(b[2], b[2], bd, bd);
+    float4 *o = packed + (size_t)i * 3;
+    o[0] = make_float4(n[0], n[1], n[2], d);
+    o[1] = make_float4(a[0], a[1], a[2], ad);
+    o[2] = make_float4(b[0], b[1], b[2], bd);
 }
 
 // K3 forward: gather face corners, unit normal normalize((p2-p1) x (p3-p2))
