@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""
+bench.py -- the headline benchmark of the tfrt ray-trace hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one fwd+bwd lens-optimisation step (SGD_Optimizer.process_gradient: system update,
+OpticalEngine.ray_trace, imaging loss, back-propagation to the surface parameters, and for N > 1
+the NCCL all-reduce of the parameter gradients) on BASELINE.json's headline configuration:
+16 777 216 rays x 99 374 triangles x 3 trace iterations (config 5), synthetic data.
+
+Metric: ray-triangle tests per second over the whole job, tests = sum_k live_rays_k x triangles
+(SURVEY.md 8(d)); rays/s, forward-only numbers, the roofline of the dominant kernel, the CPU
+baseline and the end-to-end (host buffers) number travel in the same JSON line.
+
+--impl reference times the reference's own CPU algorithm (the float64 dense restatement in
+oracle/, the only form of the reference that can run here: TensorFlow is not installable) on a
+bounded ray sample of the same workload, on the box's host cores.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FLOP_PER_TEST = 45.0        # algorithmic Moller-Trumbore count
+BWD_BYTES_PER_RAY_ITER = 100.0   # algorithmic bytes of the backward pass
+METRIC = "ray_triangle_tests_per_s_fwd_bwd"
+UNIT = "tests/s"
+
+CONFIGS = {
+    # name: (scene factory kwargs, has backward)
+    "cfg2": dict(factory="config2", kwargs={}, backward=False),
+    "cfg3": dict(factory="config3", kwargs={}, backward=True),
+    "cfg4": dict(factory="config4", kwargs={}, backward=False),
+    "cfg5": dict(factory="config5", kwargs={}, backward=True),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg5", choices=sorted(CONFIGS))
+    ap.add_argument("--rays", type=int, default=0, help="override the ray count (debugging)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the named config's rays are sharded over the GPUs (BASELINE "
+                         "config 5); weak: every GPU traces the full ray count")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0,
+                    help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def make_scene(args, ray_count=None):
+    from tensorflowraytrace_b200 import scenes
+    cfg = CONFIGS[args.config]
+    kwargs = dict(cfg["kwargs"])
+    if ray_count:
+        kwargs["ray_count"] = int(ray_count)
+    elif args.rays:
+        kwargs["ray_count"] = int(args.rays)
+    return getattr(scenes, cfg["factory"])(**kwargs), cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="tfrt_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)),
+                       power_w_max=float(max(power)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle): used for cpu_baseline and for --impl reference
+
+def oracle_step(scene, n_rays, backward, threads):
+    """One fwd(+bwd) step of the float64 dense restatement on the first n_rays rays of the scene.
+    Returns (seconds, tests, live_counts)."""
+    import torch
+    import helpers
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    eng, params = helpers.oracle_from_scene(scene, ray_slice=slice(0, n_rays),
+                                            requires_grad=backward, compile_active_rays=False)
+    # cache-sized (triangles x ray-chunk) temporaries: 4x faster than the 256 MB default on the
+    # build container, i.e. the most favourable setting for the CPU arm
+    eng.optical_system.chunk_bytes = 4 << 20
+    eng.ray_trace(scene["max_iterations"])
+    if backward:
+        fin = eng.finished_rays
+        goal = scene["goal_scale"] * fin["rank"]
+        err = (fin["y_end"] - goal[:, 0]) ** 2 + (fin["z_end"] - goal[:, 1]) ** 2
+        torch.autograd.grad(err.sum(), params)
+    dt = time.perf_counter() - t0
+    return dt, float(eng.optical_system.tests_done), eng.live_counts
+
+
+def size_cpu_sample(scene, backward, threads, target_s):
+    """Pick a ray count whose oracle step takes about target_s seconds (probe, then scale)."""
+    probe = 256
+    dt, tests, _ = oracle_step(scene, probe, backward, threads)
+    n_total = scene["sources"]["x_start"].shape[0]
+    n = int(probe * max(target_s / max(dt, 1e-3), 1.0))
+    n = max(probe, min(n, 65536, n_total))
+    return n
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement timed on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    scene, cfg = make_scene(args)
+    backward = cfg["backward"]
+    T = scene_triangles(scene)
+    n = size_cpu_sample(scene, backward, threads, target_s=max(2.0, 90.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        oracle_step(scene, n, backward, threads)
+    total_s, total_tests, live = 0.0, 0.0, None
+    for _ in range(args.steps):
+        dt, tests, live = oracle_step(scene, n, backward, threads)
+        total_s += dt
+        total_tests += tests
+    value = total_tests / total_s
+    sample = (f"first {n} of {scene['sources']['x_start'].shape[0]} rays x {T} triangles x "
+              f"{scene['max_iterations']} iterations, {'fwd+bwd' if backward else 'fwd'}, "
+              f"float64 dense (triangles x ray-chunk) restatement, torch CPU")
+    line = {
+        "impl": "reference", "metric": METRIC if backward else "ray_triangle_tests_per_s_fwd",
+        "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(args.steps, 1),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": bench_config(args, scene, 1),
+        "rays_per_s": n / (total_s / max(args.steps, 1)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "TensorFlow is not installable in this image, so the reference's own code cannot "
+                "run; this is its algorithm restated op-for-op (oracle/).",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def scene_triangles(scene):
+    from tensorflowraytrace_b200 import scenes
+    return scenes.triangle_count(scene)
+
+
+def bench_config(args, scene, world):
+    n = scene["sources"]["x_start"].shape[0]
+    return {
+        "workload": f"{args.config}: {scene['name']} -- {n} rays x {scene_triangles(scene)} "
+                    f"triangles x {scene['max_iterations']} trace iterations, "
+                    f"{'fwd+bwd optimisation step' if CONFIGS[args.config]['backward'] else 'forward trace'}",
+        "rays": int(n), "triangles": int(scene_triangles(scene)),
+        "iterations": int(scene["max_iterations"]),
+        "parallelism": f"rays sharded over {world} GPU(s), mesh replicated, "
+                       f"NCCL all-reduce of parameter gradients" if world > 1 else "single GPU",
+        "l2": "per-step inputs (rays + tape, hundreds of MB) exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+
+def run_ours(args):
+    import torch
+    from tensorflowraytrace_b200 import kernels, optimizer, parallel, scenes
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    rank, world, local = parallel.init_from_env()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    scene, cfg = make_scene(args)
+    backward = cfg["backward"]
+    n_total = scene["sources"]["x_start"].shape[0]
+    T = scene_triangles(scene)
+    K = scene["max_iterations"]
+
+    # ---- this rank's rays, as pinned HOST buffers (the e2e path copies them every step)
+    if args.scaling == "strong":
+        lo, hi = parallel.shard_range(n_total, rank, world)
+    else:
+        lo, hi = 0, n_total
+    host = {}
+    for k, v in scene["sources"].items():
+        t = torch.from_numpy(np.ascontiguousarray(v[lo:hi]).astype(np.float32))
+        host[k] = t.pin_memory()
+    n_local = hi - lo
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+
+    scene_local = dict(scene)
+    scene_local["sources"] = {k: v[lo:hi] for k, v in scene["sources"].items()}
+    engine, params, src = scenes.build_engine(
+        scene_local, compile_active_rays=False, compile_finished_rays=True)
+    errf = scenes.imaging_error(scene) if backward else None
+    opt = optimizer.SGD_Optimizer(engine, params, errf, K) if backward else None
+    acc = [None] * len(params)
+    d2h_bytes = sum(p.numel() * 4 for p in params) + 4 if backward else 4
+
+    def step_resident():
+        """Inputs already in HBM: update + trace (+ loss + backward + all-reduce)."""
+        if backward:
+            grads, err = opt.process_gradient(acc)
+            return grads, err
+        engine.optical_system.update()
+        engine.ray_trace(K)
+        return None, None
+
+    def step_e2e():
+        """Public API from HOST buffers: H2D of this step's rays, step, D2H of loss + grads."""
+        for k, t in host.items():
+            src[k] = t.to(dev, non_blocking=True)
+        grads, err = step_resident()
+        if backward:
+            out = [g.cpu() for g in grads] + [err.cpu()]
+        else:
+            out = [engine.finished_rays["x_end"][:1].cpu()]
+        return out
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    fp32_peak = kernels.fp32_peak(packed=0, iters=4096)
+    fp32_peak_packed = kernels.fp32_peak(packed=1, iters=4096)
+
+    # ---- warm-up, then the device-resident timed region
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    live = engine.last_trace.live_counts()
+    tests_local = float(sum(live)) * T
+    tests_total = parallel.sum_over_ranks(tests_local)
+    rays_total = parallel.sum_over_ranks(n_local)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    kernels.profile_enable(True)
+    kernels.profile_read()
+    kernels.launch_count(reset=True)
+    seconds = timed(step_resident, args.steps)
+    launches = kernels.launch_count(reset=True)
+    k_ms, k_n = kernels.profile_read()
+    kernels.profile_enable(False)
+    clocks = sampler.stop()
+
+    # forward-only (update + trace), same inputs
+    def step_forward():
+        engine.optical_system.update()
+        engine.ray_trace(K)
+    step_forward()
+    fwd_seconds = timed(step_forward, args.steps)
+
+    # backward kernel share: time fwd+bwd minus fwd
+    value = tests_total * args.steps / seconds
+    line = {
+        "metric": METRIC if backward else "ray_triangle_tests_per_s_fwd",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * seconds / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": bench_config(args, scene, world),
+        "rays_per_s": rays_total * args.steps / seconds,
+        "tests_per_step": tests_total, "live_rays_per_iteration_rank0": live,
+        "forward_only": {"tests_per_s": tests_total * args.steps / fwd_seconds,
+                         "rays_per_s": rays_total * args.steps / fwd_seconds,
+                         "ms_per_step": 1e3 * fwd_seconds / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    # ---- roofline of the dominant kernel (k_intersect3d), rank 0's launches
+    if k_n > 0 and k_ms > 0:
+        tests_per_launch = tests_local * args.steps / k_n
+        achieved = FLOP_PER_TEST * tests_per_launch / (k_ms / k_n * 1e-3) / 1e12
+        line["roofline"] = {
+            "kernel": "k_intersect3d", "bound": "fp32_fma", "achieved": achieved,
+            "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
+            "traffic": None,
+            "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
+            "share_of_step": k_ms * 1e-3 / seconds,
+            "flop_per_test": FLOP_PER_TEST,
+            "issued_flop_per_test": 18.0,
+            "frac_of_issued": 18.0 * tests_per_launch / (k_ms / k_n * 1e-3) / fp32_peak,
+            "peak_source": "measured in this run by tfrt_fp32_peak (register-only FFMA loop on "
+                           "all SMs); MEASURED_PEAKS.json carries no fp32 figure. Nominal "
+                           "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
+            "peak_ffma2_tflops": fp32_peak_packed / 1e12,
+        }
+    if backward:
+        bwd_s = max(seconds - fwd_seconds, 1e-9) / args.steps
+        hbm = measured_peaks().get("hbm_gbs")
+        gbs = BWD_BYTES_PER_RAY_ITER * float(sum(live)) / bwd_s / 1e9
+        line["roofline_backward"] = {
+            "kernel": "k_backward3d (+loss, faces backward)", "bound": "hbm", "achieved": gbs,
+            "peak": hbm, "unit": "GB/s", "frac": (gbs / hbm) if hbm else None,
+            "ms_per_step": 1e3 * bwd_s, "share_of_step": bwd_s * args.steps / seconds,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm else "absent"}
+
+    # ---- end to end through the public API with host buffers
+    if not args.no_e2e:
+        step_e2e()
+        e2e_seconds = timed(step_e2e, args.steps)
+        line["e2e"] = {"value": tests_total * args.steps / e2e_seconds, "unit": UNIT,
+                       "h2d_bytes_per_step": int(parallel.sum_over_ranks(h2d_bytes)),
+                       "d2h_bytes_per_step": int(d2h_bytes * world),
+                       "ms_per_step": 1e3 * e2e_seconds / args.steps,
+                       "rays_per_s": rays_total * args.steps / e2e_seconds}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample, same workload
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n = size_cpu_sample(scene, backward, threads, args.cpu_seconds)
+        dt, tests, _ = oracle_step(scene, n, backward, threads)
+        line["cpu_baseline"] = {
+            "value": tests / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "rays_per_s": n / dt,
+            "sample": f"first {n} of {n_total} rays x {T} triangles x {K} iterations, "
+                      f"{'fwd+bwd' if backward else 'fwd'}, float64 dense restatement of the "
+                      f"reference (oracle/), torch CPU, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,6 +182,18 @@ int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_ho
  * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2). */
 int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream);
 
+/* Number of kernel launches libtfrt_b200 has issued in this process since the last reset
+ * (bench.py reports it as gpu_launches); reset != 0 zeroes the counter after reading. */
+long long tfrt_launch_count(int reset);
+
+/* Optional device timing of the dominant kernel (the ray x triangle intersection): when enabled,
+ * every launch of it is bracketed by CUDA events on its own stream.  tfrt_profile_read waits for
+ * the recorded events, returns their summed duration and the launch count since the last read,
+ * and clears the records.  At most 4096 launches are recorded between reads; later ones run
+ * untimed. */
+int tfrt_profile_enable(int on);
+int tfrt_profile_read(double *total_ms, long long *n_launches);
+
 #ifdef __cplusplus
 }
 #endif

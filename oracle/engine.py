@@ -199,6 +199,7 @@ class OracleEngine3D:
         self.clear_ray_history()
         self.last_projection_result = {}
         self.last_intersect_result = []  # test helper: per-iteration intersect() output
+        self.last_input_rays = []        # test helper: rays entering each iteration
 
     # --- history (engine.py:1379-1403, 2304-2309)
     def clear_ray_history(self):
@@ -233,6 +234,7 @@ class OracleEngine3D:
         result = {"rays": {}}
         input_ray_fields = list(input_rays.keys())
 
+        self.last_input_rays.append({k: v.detach().clone() for k, v in input_rays.items()})
         intersect_result = system.intersect(input_rays)
         self.last_intersect_result.append(
             {k: (v.detach() if torch.is_tensor(v) else v) for k, v in intersect_result.items()})
@@ -346,6 +348,7 @@ class OracleEngine3D:
     def ray_trace(self, max_iterations=25):
         self.clear_ray_history()
         self.last_intersect_result = []
+        self.last_input_rays = []
         starting_rays = dict(self.optical_system._amalgamated_sources)
         self.live_counts = []
         for _ in range(max_iterations):

@@ -74,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "tfrt_intersect3d",
     "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
     "tfrt_trace3d_backward",
-    "tfrt_fp32_peak",
+    "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
 _lib = None
@@ -99,6 +99,8 @@ def load():
     lib.tfrt_abi_version.restype = ctypes.c_int
     lib.tfrt_packed_floats.restype = ctypes.c_size_t
     lib.tfrt_packed_floats.argtypes = [ctypes.c_int32]
+    lib.tfrt_launch_count.restype = ctypes.c_longlong
+    lib.tfrt_launch_count.argtypes = [ctypes.c_int]
     _lib = lib
     return lib
 

@@ -1,0 +1,109 @@
+"""
+torch.autograd wrappers around the CUDA kernels: the replacement of the reference's
+`tf.GradientTape` seam (tfrt/optimizer.py:216-220).
+
+FacesFunction : vertices -> triangle fields + unit normals (K3, tfrt/boundaries.py:890-923)
+TraceFunction : (triangle fields, normals, source rays) -> ray histories of the whole
+                OpticalEngine.ray_trace loop (K1 + K2, tfrt/engine.py:2311-2330)
+
+Gradient semantics follow the reference exactly: nothing flows through
+argmin / masks / barycentrics / material indices; `vertex_update_map` blocks per-(face,corner)
+contributions.
+"""
+
+import torch
+
+from . import kernels
+
+
+class FacesFunction(torch.autograd.Function):
+    """vertices (V,3) f32 -> (tri (9,F), norm (F,3)); faces (F,3) int32; update_map (F,3) uint8."""
+
+    @staticmethod
+    def forward(ctx, vertices, faces, update_map):
+        vertices = vertices.contiguous()
+        tri, norm = kernels.faces_forward(vertices, faces)
+        ctx.save_for_backward(vertices)
+        ctx.faces, ctx.update_map = faces, update_map
+        return tri, norm
+
+    @staticmethod
+    def backward(ctx, g_tri, g_norm):
+        (vertices,) = ctx.saved_tensors
+        g_vertices = kernels.faces_backward(
+            vertices, ctx.faces, ctx.update_map,
+            None if g_tri is None else g_tri.contiguous(),
+            None if g_norm is None else g_norm.contiguous())
+        return g_vertices, None, None
+
+
+class TraceFunction(torch.autograd.Function):
+    """Whole-loop trace.  Inputs: tri (9,T), norm (T,3), src (7,N) [x_start..z_end, wavelength],
+    and a `plan` (TracePlan) carrying the non-tensor configuration.  Outputs: the four history
+    ray sets (6,n_which) in the reference's order -- active, stopped, finished, dead -- with
+    (6,0) for sets the engine does not compile.  The kernels.Trace3D object (tape) is left in
+    plan.trace for the caller (slots / iterations of the history entries, live counts)."""
+
+    @staticmethod
+    def forward(ctx, tri, norm, src, plan):
+        tr = kernels.Trace3D(
+            src, tri, norm, plan.category, plan.n_optical, plan.max_iterations,
+            packed=plan.packed, mat_in=plan.mat_in, mat_out=plan.mat_out, n_in=plan.n_in, n_out=plan.n_out,
+            materials=plan.materials, n_materials=plan.n_materials,
+            intersect_eps=plan.intersect_eps, size_eps=plan.size_eps,
+            ray_start_eps=plan.ray_start_eps, new_ray_length=plan.new_ray_length)
+        tr.forward()
+        plan.trace = tr
+        outs, plan.slots, plan.iters = [], {}, {}
+        for name in ("active", "stopped", "finished", "dead"):
+            if name in plan.compile:
+                rays, slot, it = tr.history(
+                    name, dead_ray_length=plan.dead_ray_length if name == "dead" else None)
+            else:
+                rays = torch.empty((6, 0), dtype=torch.float32, device=src.device)
+                slot = it = torch.empty((0,), dtype=torch.int32, device=src.device)
+            outs.append(rays)
+            plan.slots[name], plan.iters[name] = slot, it
+        ctx.plan = plan
+        ctx.trace = tr
+        ctx.src_shape = src.shape
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_active, g_stopped, g_finished, g_dead):
+        plan, tr = ctx.plan, ctx.trace
+        g_hist = {}
+        for name, g in (("active", g_active), ("stopped", g_stopped), ("finished", g_finished),
+                        ("dead", g_dead)):
+            if g is not None and name in plan.compile and g.shape[1] > 0:
+                g_hist[name] = g.contiguous()
+        want_src = ctx.needs_input_grad[2]
+        g_tri, g_norm, g_src = tr.backward(g_hist, want_src_grad=want_src,
+                                           dead_ray_length=plan.dead_ray_length)
+        g_src_full = None
+        if want_src:
+            g_src_full = torch.zeros(ctx.src_shape, dtype=torch.float32, device=g_tri.device)
+            g_src_full[:6] = g_src
+        return (g_tri if ctx.needs_input_grad[0] else None,
+                g_norm if ctx.needs_input_grad[1] else None, g_src_full, None)
+
+
+class TracePlan:
+    """Non-tensor configuration of one fused trace (filled by OpticalEngine.ray_trace)."""
+
+    def __init__(self, **kw):
+        self.category = kw["category"]
+        self.n_optical = kw["n_optical"]
+        self.max_iterations = kw["max_iterations"]
+        self.mat_in, self.mat_out = kw.get("mat_in"), kw.get("mat_out")
+        self.n_in, self.n_out = kw.get("n_in"), kw.get("n_out")
+        self.materials, self.n_materials = kw.get("materials"), kw.get("n_materials", 0)
+        self.intersect_eps = kw["intersect_eps"]
+        self.size_eps = kw["size_eps"]
+        self.ray_start_eps = kw["ray_start_eps"]
+        self.new_ray_length = kw["new_ray_length"]
+        self.dead_ray_length = kw.get("dead_ray_length")
+        self.compile = set(kw["compile"])
+        self.packed = kw.get("packed")   # tfrt_pack_triangles output (built when None)
+        self.trace = None
+        self.slots, self.iters = {}, {}

@@ -15,6 +15,61 @@ void tfrt_set_error(const char *fmt, ...) {
 extern "C" const char *tfrt_last_error(void) { return g_err; }
 extern "C" int tfrt_abi_version(void) { return TFRT_B200_ABI_VERSION; }
 
+// ---------------------------------------------------------------------------------------------
+// launch counter + optional event timing of the intersect kernel
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+static std::atomic<long long> g_launches{0};
+void tfrt_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long tfrt_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_events;   // pairs: begin, end
+static size_t g_prof_used = 0;                   // events used (even)
+static const size_t kProfMaxEvents = 8192;
+
+bool tfrt_profile_begin(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_on || g_prof_used + 2 > kProfMaxEvents) return false;
+    while (g_prof_events.size() < g_prof_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return false;
+        g_prof_events.push_back(e);
+    }
+    cudaEventRecord(g_prof_events[g_prof_used], st);
+    return true;
+}
+void tfrt_profile_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof_events[g_prof_used + 1], st);
+    g_prof_used += 2;
+}
+extern "C" int tfrt_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int tfrt_profile_read(double *total_ms, long long *n_launches) {
+    TFRT_REQUIRE(total_ms && n_launches, "tfrt_profile_read: null argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+        TFRT_CHECK_CUDA(cudaEventSynchronize(g_prof_events[i + 1]));
+        float ms = 0.f;
+        TFRT_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *n_launches = (long long)(g_prof_used / 2);
+    g_prof_used = 0;
+    return 0;
+}
+
 namespace {
 
 // 8 independent accumulator chains per thread, register-only: measures the FMA pipe.

@@ -297,11 +297,13 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         }
         P.g_acc = b->g_acc;
         k_backward3d<<<tfrt_div_up(n_live, kBwdThreads), kBwdThreads, 0, st>>>(P);
+        tfrt_note_launch(1);
     }
     k_finish_tri_grads<<<tfrt_div_up(T, 256), 256, 0, st>>>(
         b->g_acc, T, b->g_tri_out[0], b->g_tri_out[1], b->g_tri_out[2], b->g_tri_out[3],
         b->g_tri_out[4], b->g_tri_out[5], b->g_tri_out[6], b->g_tri_out[7], b->g_tri_out[8],
         b->g_norm_out);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -34,6 +34,10 @@ void tfrt_set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
+void tfrt_note_launch(int n);                     // launch counter (abi.cu)
+bool tfrt_profile_begin(cudaStream_t st);          // event before the intersect kernel
+void tfrt_profile_end(cudaStream_t st);            // event after it
+
 static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

@@ -267,10 +267,13 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
             ray_start_eps, 1.0f + 3.0f * size_eps, reinterpret_cast<unsigned long long *>(hit),       \
             use_atomic);            \
     } while (0)
+    const bool timed = tfrt_profile_begin(stream);
     if (r2 == 4) TFRT_LAUNCH(4);
     else if (r2 == 2) TFRT_LAUNCH(2);
     else TFRT_LAUNCH(1);
 #undef TFRT_LAUNCH
+    if (timed) tfrt_profile_end(stream);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -140,6 +140,7 @@ extern "C" int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, flo
     k_pack_triangles<<<tfrt_div_up(n_padded, 128), 128, 0, (cudaStream_t)stream>>>(
         tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], n_tri, n_padded,
         size_eps, reinterpret_cast<float4 *>(packed));
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -151,6 +152,7 @@ extern "C" int tfrt_faces_forward(const float *vertices, const int32_t *faces, i
     k_faces_forward<<<tfrt_div_up(n_faces, 128), 128, 0, (cudaStream_t)stream>>>(
         vertices, faces, n_faces, tri_out[0], tri_out[1], tri_out[2], tri_out[3], tri_out[4],
         tri_out[5], tri_out[6], tri_out[7], tri_out[8], norm_out);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -166,6 +168,7 @@ extern "C" int tfrt_faces_backward(const float *vertices, const int32_t *faces,
     k_faces_backward<<<tfrt_div_up(n_faces, 128), 128, 0, st>>>(
         vertices, faces, update_map, n_faces, g_tri[0], g_tri[1], g_tri[2], g_tri[3], g_tri[4],
         g_tri[5], g_tri[6], g_tri[7], g_tri[8], g_norm, g_vertices);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -344,6 +344,7 @@ extern "C" int tfrt_intersect3d(const float *const ray[6], int32_t n_rays,
         ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tri[0], tri[1], tri[2], tri[3], tri[4],
         tri[5], tri[6], tri[7], tri[8], hit_ws, n_rays, (double)intersect_eps, x, y, z, valid,
         ray_u, trig_u, trig_v, gather_trig);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -371,6 +372,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
                                     a->src[5], a->cur[0], a->cur[1], a->cur[2], a->cur[3],
                                     a->cur[4], a->cur[5], N);
     k_iota<<<nb, 256, 0, st>>>(a->live, N);
+    tfrt_note_launch(3);
     TFRT_CHECK_CUDA(cudaMemsetAsync(a->tape_status, 0xff, (size_t)K * N, st));
 
     const int n_blocks = tfrt_div_up(N, kReactThreads);
@@ -404,6 +406,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
         k_scatter<<<n_blocks, kReactThreads, 0, st>>>(
             live_k, P.tape_status, a->block_counts, counters_k, live_next, a->cat_ids[0],
             a->cat_ids[1], a->cat_ids[2], a->tape_outpos + (size_t)k * N);
+        tfrt_note_launch(3);
     }
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -455,6 +458,7 @@ extern "C" int tfrt_materialize3d(const TfrtTrace3DArgs *a, const int32_t *count
                     out[0] + begin, out[1] + begin, out[2] + begin, out[3] + begin,
                     out[4] + begin, out[5] + begin, out_slot ? out_slot + begin : nullptr,
                     out_iter ? out_iter + begin : nullptr);
+            if (cnt > 0) tfrt_note_launch(1);
             begin = seg[k];
         }
         TFRT_CHECK_CUDA(cudaGetLastError());
@@ -464,6 +468,7 @@ extern "C" int tfrt_materialize3d(const TfrtTrace3DArgs *a, const int32_t *count
         a->cat_ids[which - 1], a->counters, which, K, -1, (int)total, a->tape_f, N,
         which == 3 ? dead_ray_length : -1.f, out[0], out[1], out[2], out[3], out[4], out[5],
         out_slot, out_iter);
+    tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,707 @@
+"""
+OpticalSystem3D / OpticalEngine: the tracing engine of tfrt/engine.py on B200.
+
+`OpticalEngine.ray_trace` is the hot path.  When the operation list is made of
+`StandardReaction` (+ optionally `OldestAncestor`) the whole iteration loop -- intersection of
+every live ray with every triangle, nearest hit, classification, material look-up, Snell /
+reflection / TIR, order-preserving compaction, history -- runs fused on the GPU through
+libtfrt_b200.so (one autograd node, `autograd.TraceFunction`).  Any other operation list runs
+the same loop one projection at a time (`single_pass`): the O(rays x triangles) search is still
+the CUDA kernel (the `_intersection` seam, tfrt/engine.py:1102-1166), the O(rays) bookkeeping is
+torch on the GPU.  There is no CPU path.
+
+Mirrored reference interfaces (same names, arguments, result field names and ordering):
+  amalgamate, ReadOnlySet           tfrt/engine.py:27-76
+  OpticalSystemBase / 3D            tfrt/engine.py:146-250, 870-1166
+  OpticalEngine                     tfrt/engine.py:1216-1403, 1988-2330
+"""
+
+from abc import abstractmethod
+
+import torch
+
+from . import geometry, kernels
+from . import operation as op
+from .autograd import TraceFunction, TracePlan
+from .materials import descriptor_of
+from .update import RecursivelyUpdatable
+
+OPTICAL = 0
+STOP = 1
+TARGET = 2
+
+SEGMENT_GEO_SIG = {"x_start", "y_start", "x_end", "y_end"}
+ARC_GEO_SIG = {"x_center", "y_center", "angle_start", "angle_end", "radius"}
+SOURCE_3D_SIG = {"x_start", "y_start", "z_start", "x_end", "y_end", "z_end"}
+TRIANGLE_GEO_SIG = {"xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2", "norm"}
+
+TRI_FIELDS = kernels.TRI_FIELDS
+RAY_FIELDS_3D = kernels.RAY_FIELDS
+
+
+class ReadOnlySet:
+    """Read-only view of a ray or boundary field dict (tfrt/engine.py:27-46)."""
+
+    def __init__(self, fields):
+        self._fields = fields
+
+    def __getitem__(self, key):
+        try:
+            return self._fields[key]
+        except KeyError as e:
+            raise KeyError(f"key {key} not in the signature of this set.") from e
+
+    def __bool__(self):
+        return bool(self._fields)
+
+    @property
+    def keys(self):
+        return self._fields.keys
+
+
+def _field_dict(item):
+    return item._fields if hasattr(item, "_fields") else item
+
+
+def amalgamate(stuff, signature=None):
+    """Concatenate field dicts along axis 0 over the common (or given) signature
+    (tfrt/engine.py:50-76).  Empty items are skipped."""
+    processed = [_field_dict(item) for item in stuff if bool(item)]
+    if not processed:
+        return {}
+    if not signature:
+        signature = None
+        for item in processed:
+            keys = set(item.keys())
+            signature = keys if signature is None else (signature & keys)
+    if len(processed) == 1:
+        return {field: processed[0][field] for field in signature}
+    return {field: torch.cat([item[field] for item in processed], 0) for field in signature}
+
+
+# =========================================================================================
+
+class OpticalSystemBase(RecursivelyUpdatable):
+    """Holds sources, boundaries and materials (tfrt/engine.py:146-250).
+
+    intersect_epsilion / size_epsilion / ray_start_epsilion have the reference's meaning
+    (tfrt/engine.py:160-179).  Their defaults here are fp32-appropriate (the reference's 1e-10
+    is below fp32 resolution at unit scale): 1e-10 on |det|, 1e-5 edge
+    inflation, 1e-4 ray-start exclusion.
+
+    ray_shard : None or (rank, world_size).  When set, `update()` keeps only this rank's
+    contiguous block of the amalgamated source rays (multi-GPU ray sharding, parallel.py).
+    """
+
+    def __init__(self, manual_update_management=False, intersect_epsilion=1e-10,
+                 size_epsilion=1e-5, ray_start_epsilion=1e-4, ray_shard=None, **kwargs):
+        self._sources = []
+        self._read_only_sources = None
+        self.source_handles = []
+        self._amalgamated_sources = {}
+        self.manual_update_management = manual_update_management
+        self.materials = []
+        self.intersect_epsilion = intersect_epsilion
+        self.size_epsilion = size_epsilion
+        self.ray_start_epsilion = ray_start_epsilion
+        self.ray_shard = ray_shard
+        self.projection_results = {}
+        super().__init__(**kwargs)
+
+    @abstractmethod
+    def refresh_update_handles(self):
+        raise NotImplementedError
+
+    @property
+    @abstractmethod
+    def dimension(self):
+        raise NotImplementedError
+
+    @property
+    def sources(self):
+        if not bool(self._read_only_sources):
+            self._read_only_sources = ReadOnlySet(self._amalgamated_sources)
+        return self._read_only_sources
+
+    @sources.setter
+    def sources(self, new):
+        self.source_handles = []
+        for each in new:
+            assert each.dimension == self.dimension
+            self.source_handles.append(each.update)
+        self._sources = new
+        self.refresh_update_handles()
+
+    @property
+    def materials(self):
+        return self._materials
+
+    @materials.setter
+    def materials(self, val):
+        assert type(val) is list
+        self._materials = val
+        self._material_table = None
+
+    def _amalgamate_sources(self):
+        if bool(self._sources):
+            merged = amalgamate(self._sources)
+            if self.ray_shard is not None and merged:
+                from .parallel import shard_range
+                n = next(iter(merged.values())).shape[0]
+                lo, hi = shard_range(n, *self.ray_shard)
+                merged = {k: v[lo:hi] for k, v in merged.items()}
+            self._amalgamated_sources = merged
+
+    def material_table(self, device):
+        """Device table of kernel material descriptors for `self.materials` (cached)."""
+        if self._material_table is None or self._material_table.device != device:
+            self._material_table = kernels.material_table(
+                [descriptor_of(m) for m in self._materials], device)
+        return self._material_table
+
+    @abstractmethod
+    def intersect(self, rays):
+        raise NotImplementedError
+
+
+class OpticalSystem3D(OpticalSystemBase):
+    """Triangle-boundary optical system (tfrt/engine.py:870-1166)."""
+
+    def __init__(self, **kwargs):
+        self._optical = []
+        self.optical_handles = []
+        self._amalgamated_optical = {}
+        self._stop = []
+        self.stop_handles = []
+        self._amalgamated_stop = {}
+        self._target = []
+        self.target_handles = []
+        self._amalgamated_target = {}
+        self._materials = []
+        self._merged = {}
+        self._optical_count = self._stop_count = self._target_count = 0
+        self._dev_cache = None
+        self.clear_read_only()
+        super().__init__(**kwargs)
+
+    def clear_read_only(self):
+        self._read_only_sources = None
+        self._read_only_optical = None
+        self._read_only_stop = None
+        self._read_only_target = None
+
+    def refresh_update_handles(self):
+        if not self.manual_update_management:
+            self.update_handles = self._generate_update_handles()
+
+    def _generate_update_handles(self):
+        return (self.source_handles + self.optical_handles + self.stop_handles
+                + self.target_handles)
+
+    @property
+    def dimension(self):
+        return 3
+
+    def _update(self):
+        self._amalgamate_sources()
+        if bool(self._optical):
+            self._amalgamated_optical = amalgamate(self._optical)
+        if bool(self._stop):
+            self._amalgamated_stop = amalgamate(self._stop)
+        if bool(self._target):
+            self._amalgamated_target = amalgamate(self._target)
+        self._merge_boundaries()
+        self.clear_read_only()
+
+    def _boundary_property(name, store, handles, cache):  # noqa: N805  (class-body helper)
+        def getter(self):
+            if not bool(getattr(self, cache)):
+                setattr(self, cache, ReadOnlySet(getattr(self, "_amalgamated_" + store)))
+            return getattr(self, cache)
+
+        def setter(self, new):
+            hs = []
+            for each in new:
+                assert each.dimension == self.dimension
+                hs.append(each.update)
+            setattr(self, handles, hs)
+            setattr(self, "_" + store, new)
+            self.refresh_update_handles()
+
+        return property(getter, setter)
+
+    optical = _boundary_property("optical", "optical", "optical_handles", "_read_only_optical")
+    stops = _boundary_property("stops", "stop", "stop_handles", "_read_only_stop")
+    targets = _boundary_property("targets", "target", "target_handles", "_read_only_target")
+    del _boundary_property
+
+    def _merge_boundaries(self):
+        """Label and merge optical -> stop -> target (tfrt/engine.py:971-1018)."""
+        counts, parts = [], []
+        for cat, d in ((OPTICAL, self._amalgamated_optical), (STOP, self._amalgamated_stop),
+                       (TARGET, self._amalgamated_target)):
+            if bool(d):
+                d["catagory"] = torch.full_like(d["xp"], cat, dtype=torch.int64)
+                counts.append(d["xp"].shape[0])
+            else:
+                counts.append(0)
+            parts.append(d)
+        self._optical_count, self._stop_count, self._target_count = counts
+        self._merged = amalgamate(parts, TRIANGLE_GEO_SIG | {"catagory"})
+        self._dev_cache = None
+
+    # ------------------------------------------------------------------ kernel-side views
+    def merged_device_arrays(self):
+        """(tri (9,T) f32, norm (T,3) f32, category (T,) int32, packed) of the merged set.  tri
+        and norm stay attached to the autograd graph of the boundary parameters; the packed
+        plane records for the intersection kernel are rebuilt once per update()."""
+        if self._dev_cache is None:
+            m = self._merged
+            tri = torch.stack([m[k] for k in TRI_FIELDS]).to(torch.float32).contiguous()
+            norm = m["norm"].to(torch.float32).contiguous()
+            category = m["catagory"].to(torch.int32).contiguous()
+            packed = kernels.pack_triangles(tri.detach(), self.size_epsilion)
+            self._dev_cache = (tri, norm, category, packed)
+        return self._dev_cache
+
+    def intersect(self, rays):
+        """Nearest valid intersection of each ray with the merged triangles
+        (tfrt/engine.py:1020-1078): dict with x, y, z, valid, ray_u, trig_u, trig_v,
+        gather_ray, gather_trig, norm."""
+        result = {}
+        if bool(self._merged):
+            (result["x"], result["y"], result["z"], result["valid"], result["ray_u"],
+             result["trig_u"], result["trig_v"], result["gather_ray"],
+             result["gather_trig"]) = self._intersection(
+                *[rays[k] for k in RAY_FIELDS_3D], *[self._merged[k] for k in TRI_FIELDS],
+                self.intersect_epsilion, self.size_epsilion, self.ray_start_epsilion,
+                _packed=self.merged_device_arrays()[3])
+            result["norm"] = self._merged["norm"][result["gather_trig"]]
+        return result
+
+    @staticmethod
+    def _intersection(rx1, ry1, rz1, rx2, ry2, rz2, xp, yp, zp, x1, y1, z1, x2, y2, z2,
+                      intersect_epsilion, size_epsilion, ray_start_epsilion, _packed=None):
+        """The intersection seam (tfrt/engine.py:1102-1166): N rays x M triangles -> per-ray
+        nearest hit.  The search runs in the CUDA kernel; the gathered values are then
+        re-evaluated 1-to-1 in torch so they carry the reference's gradient (through ray_u
+        only).  Outputs for rays without a valid hit are unspecified, as in the reference."""
+        rays = torch.stack([rx1, ry1, rz1, rx2, ry2, rz2]).detach()
+        tri = torch.stack([xp, yp, zp, x1, y1, z1, x2, y2, z2]).detach()
+        if _packed is None:
+            _packed = kernels.pack_triangles(tri, size_epsilion)
+        raw = kernels.intersect3d(rays, tri, _packed, intersect_epsilion, size_epsilion,
+                                  ray_start_epsilion)
+        g = raw["gather_trig"]
+        hit, _, ray_u, trig_u, trig_v = geometry.ray_triangle_hit(
+            torch.stack([rx1, ry1, rz1], 1), torch.stack([rx2, ry2, rz2], 1),
+            torch.stack([xp[g], yp[g], zp[g]], 1), torch.stack([x1[g], y1[g], z1[g]], 1),
+            torch.stack([x2[g], y2[g], z2[g]], 1), intersect_epsilion)
+        return (hit[:, 0], hit[:, 1], hit[:, 2], raw["valid"], ray_u, trig_u, trig_v,
+                raw["gather_ray"], g)
+
+
+# =========================================================================================
+
+class OpticalEngine:
+    """The ray tracer (tfrt/engine.py:1170-2330).  Constructor arguments as in the reference
+    (tfrt/engine.py:1216-1230)."""
+
+    def __init__(self, dimension, operations, optical_system=None,
+                 compile_technical_intersections=False, compile_stopped_rays=False,
+                 compile_dead_rays=False, compile_finished_rays=True, compile_active_rays=True,
+                 dead_ray_length=None, compile_geometry_specific_result=False,
+                 new_ray_length=1.0, simple_ray_inheritance={"wavelength"}):
+        if dimension == 2:
+            self.process_projection = self.process_projection_2D
+        elif dimension == 3:
+            self.process_projection = self.process_projection_3D
+        else:
+            raise ValueError(f"RayEngine: dimension must be 2 or 3, but was given {dimension}.")
+        self._dimension = dimension
+        self._check_exclusions(operations)
+        self._operations = operations
+        self._optical_system = optical_system
+        self.compile_technical_intersections = compile_technical_intersections
+        self.compile_stopped_rays = compile_stopped_rays
+        self.compile_dead_rays = compile_dead_rays
+        self.compile_finished_rays = compile_finished_rays
+        self.compile_active_rays = compile_active_rays
+        self.dead_ray_length = dead_ray_length
+        self.compile_geometry_specific_result = compile_geometry_specific_result
+        self.new_ray_length = new_ray_length
+        self.clear_ray_history()
+        self.last_projection_result = {}
+        self.last_trace = None     # kernels.Trace3D of the last fused trace (tape, live counts)
+
+        self.input_signature = set()
+        self.output_signature = set()
+        self.optical_signature = set()
+        self.stop_signature = set()
+        self.target_signature = set()
+        self.material_signature = set()
+        self.simple_ray_inheritance = set(simple_ray_inheritance)
+        for o in operations:
+            self.input_signature |= o.input_signature
+            self.output_signature |= o.output_signature
+            self.optical_signature |= o.optical_signature
+            self.stop_signature |= o.stop_signature
+            self.target_signature |= o.target_signature
+            self.material_signature |= o.material_signature
+            self.simple_ray_inheritance |= o.simple_ray_inheritance
+
+    def add_inheritable_field(self, fields):
+        if type(fields) is str:
+            fields = {fields}
+        self.simple_ray_inheritance = self.simple_ray_inheritance | set(fields)
+
+    def _check_exclusions(self, operations):
+        exclusions, used = set(), set()
+        for o in operations:
+            used.add(o.__class__)
+            exclusions |= o.exclusions
+        matches = used & exclusions
+        if bool(matches):
+            raise RuntimeError(f"RayEngine: discovered exclusive operations: {matches}")
+        self.operations = operations
+
+    def update(self):
+        if self.optical_system is not None:
+            self.optical_system.update()
+
+    def annotate(self, op_list=None):
+        if self.optical_system is not None:
+            for o in (self._operations if op_list is None else op_list):
+                o.annotate(self)
+        else:
+            print("No optical system found, so annotating nothing.")
+
+    @property
+    def dimension(self):
+        return self._dimension
+
+    @property
+    def new_ray_length(self):
+        return self._new_ray_length
+
+    @new_ray_length.setter
+    def new_ray_length(self, val):
+        self._new_ray_length = float(val)
+
+    @property
+    def optical_system(self):
+        return self._optical_system
+
+    @optical_system.setter
+    def optical_system(self, val):
+        if val.dimension != self.dimension:
+            raise ValueError(
+                f"OpticalEngine: attempted to set an optical system with dimension "
+                f"{val.dimension}, but this engine is set to dimension {self.dimension}")
+        self._optical_system = val
+
+    # ------------------------------------------------------------------ histories
+    @property
+    def active_rays(self):
+        return ReadOnlySet(amalgamate(self._active_rays))
+
+    @property
+    def finished_rays(self):
+        return ReadOnlySet(amalgamate(self._finished_rays))
+
+    @property
+    def dead_rays(self):
+        return ReadOnlySet(amalgamate(self._dead_rays))
+
+    @property
+    def stopped_rays(self):
+        return ReadOnlySet(amalgamate(self._stopped_rays))
+
+    @property
+    def all_rays(self):
+        return ReadOnlySet(amalgamate(
+            self._active_rays + self._finished_rays + self._dead_rays + self._stopped_rays))
+
+    @property
+    def unfinished_rays(self):
+        return self._unfinished_rays
+
+    def clear_ray_history(self):
+        self._active_rays = []
+        self._finished_rays = []
+        self._stopped_rays = []
+        self._dead_rays = []
+        self._unfinished_rays = {}
+
+    # ------------------------------------------------------------------ validation
+    def validate_system(self):
+        """Signature checks of materials, sources and boundaries (tfrt/engine.py:1416-1522)."""
+        system = self.optical_system
+        if system is None:
+            print("No optical system found, so validating nothing.")
+            return
+        for material in system.materials:
+            sig = set(material.keys())
+            if not (sig >= self.material_signature):
+                raise RuntimeError(
+                    f"Optical engine failed materials signature check.  System signature is "
+                    f"{sig} but needed {self.material_signature}")
+
+        def check(fields, required, what):
+            if bool(fields):
+                sig = set(fields.keys())
+                if not (sig >= required):
+                    raise RuntimeError(
+                        f"Optical engine failed {what} signature check.  System signature is "
+                        f"{sig}, but needed {required}.")
+
+        if self.dimension == 2:
+            check(system._amalgamated_sources, SEGMENT_GEO_SIG | self.input_signature, "sources")
+            for kind, sig in (("optical", self.optical_signature), ("stop", self.stop_signature),
+                              ("target", self.target_signature)):
+                check(getattr(system, f"_amalgamated_{kind}_segments"), SEGMENT_GEO_SIG | sig,
+                      f"{kind} segments")
+                check(getattr(system, f"_amalgamated_{kind}_arcs"), ARC_GEO_SIG | sig,
+                      f"{kind} arcs")
+        else:
+            check(system._amalgamated_sources, SOURCE_3D_SIG | self.input_signature, "sources")
+            check(system._amalgamated_optical, TRIANGLE_GEO_SIG | self.optical_signature,
+                  "optical segments")
+            check(system._amalgamated_stop, TRIANGLE_GEO_SIG | self.stop_signature,
+                  "stop segments")
+            check(system._amalgamated_target, TRIANGLE_GEO_SIG | self.target_signature,
+                  "target segments")
+
+    def validate_output(self):
+        if self.dimension == 2:
+            required = SEGMENT_GEO_SIG | self.output_signature
+            for rays in (self.active_rays, self.finished_rays, self.stopped_rays, self.dead_rays):
+                if bool(rays):
+                    sig = set(rays.keys())
+                    if not (sig >= required):
+                        raise RuntimeError(
+                            f"Optical engine failed output signature check.  System signature "
+                            f"is {sig}, but needed {required}.")
+
+    # ------------------------------------------------------------------ the trace loop
+    def _fusable(self):
+        return (self.dimension == 3 and not self.compile_technical_intersections
+                and not self.compile_geometry_specific_result
+                and any(type(o) is op.StandardReaction for o in self._operations)
+                and all(type(o) in (op.StandardReaction, op.OldestAncestor) and o.active
+                        for o in self._operations))
+
+    def ray_trace(self, max_iterations=25):
+        """Trace the optical system (tfrt/engine.py:2311-2330): iterate projection + reaction
+        until `max_iterations` or until no active rays remain."""
+        if not bool(self.optical_system):
+            return
+        self.clear_ray_history()
+        if self._fusable():
+            self._ray_trace_fused(int(max_iterations))
+            return
+        starting_rays = dict(self.optical_system._amalgamated_sources)
+        for _ in range(max_iterations):
+            result = self.single_pass(starting_rays)
+            if bool(result):
+                starting_rays = result
+            else:
+                break
+        self._unfinished_rays = starting_rays
+
+    def _ray_trace_fused(self, max_iterations):
+        system = self.optical_system
+        src_fields = system._amalgamated_sources
+        if not bool(src_fields) or not bool(system._merged):
+            return
+        reaction = next(o for o in self._operations if type(o) is op.StandardReaction)
+        tri, norm, category, packed = system.merged_device_arrays()
+        dev = tri.device
+        n = src_fields["x_start"].shape[0]
+        rows = [src_fields[k] for k in RAY_FIELDS_3D]
+        rows.append(src_fields["wavelength"] if "wavelength" in src_fields
+                    else torch.zeros(n, dtype=torch.float32, device=dev))
+        src = torch.stack([r.to(torch.float32) for r in rows]).contiguous()
+
+        optical = system._amalgamated_optical
+        kw = {}
+        if reaction.refractive_index_type == "index":
+            kw.update(mat_in=optical["mat_in"], mat_out=optical["mat_out"],
+                      materials=system.material_table(dev), n_materials=len(system.materials))
+        else:
+            kw.update(n_in=optical["n_in"], n_out=optical["n_out"])
+        compile_sets = set()
+        if self.compile_active_rays:
+            compile_sets.add("active")
+        if self.compile_finished_rays:
+            compile_sets.add("finished")
+        if self.compile_stopped_rays:
+            compile_sets.add("stopped")
+        if self.compile_dead_rays:
+            compile_sets.add("dead")
+        plan = TracePlan(
+            category=category, n_optical=system._optical_count, max_iterations=max_iterations,
+            intersect_eps=system.intersect_epsilion, size_eps=system.size_epsilion,
+            ray_start_eps=system.ray_start_epsilion, new_ray_length=self.new_ray_length,
+            dead_ray_length=self.dead_ray_length if bool(self.dead_ray_length) else None,
+            compile=compile_sets, **kw)
+        plan.packed = packed
+        active, stopped, finished, dead = TraceFunction.apply(tri, norm, src, plan)
+        self.last_trace = plan.trace
+
+        inherit = [f for f in src_fields if f not in RAY_FIELDS_3D]
+
+        def as_set(name, rays):
+            if rays.shape[1] == 0:
+                return None
+            out = {k: rays[i] for i, k in enumerate(RAY_FIELDS_3D)}
+            slot = plan.slots[name].long()
+            for f in inherit:
+                out[f] = src_fields[f][slot]
+            return out
+
+        for name, rays, store in (("active", active, self._active_rays),
+                                  ("finished", finished, self._finished_rays),
+                                  ("stopped", stopped, self._stopped_rays),
+                                  ("dead", dead, self._dead_rays)):
+            if name in compile_sets:
+                s = as_set(name, rays)
+                if s is not None:
+                    store.append(s)
+        self.last_projection_result = {}
+
+    # ------------------------------------------------------------------ unfused single pass
+    def process_projection_2D(self, input_rays):
+        raise NotImplementedError(
+            "OpticalEngine: the 2D projection is provided by engine2d (OpticalSystem2D).")
+
+    def process_projection_3D(self, input_rays):
+        """Project rays onto the system and split them by what they hit
+        (tfrt/engine.py:1988-2191).  Order-preserving masks, same result layout."""
+        system = self.optical_system
+        result = {"rays": {}}
+        fields = list(input_rays.keys())
+        inter = system.intersect(input_rays)
+        valid = inter["valid"]
+
+        if self.compile_dead_rays:
+            is_dead = torch.logical_not(valid)
+            dead = {f: input_rays[f][is_dead] for f in fields}
+            if bool(self.dead_ray_length):
+                for c in "xyz":
+                    dead[c + "_end"] = dead[c + "_start"] + self.dead_ray_length * (
+                        dead[c + "_end"] - dead[c + "_start"])
+            self._dead_rays.append(dead)
+            result["rays"]["dead"] = dead
+
+        input_rays = dict(input_rays)
+        for c in "xyz":
+            input_rays[c + "_end"] = torch.where(valid, inter[c], input_rays[c + "_end"])
+        boundary_type = system._merged["catagory"][inter["gather_trig"]]
+
+        is_active = valid & (boundary_type == OPTICAL)
+        active = {f: input_rays[f][is_active] for f in fields}
+        if self.compile_active_rays:
+            self._active_rays.append(active)
+        result["rays"]["active"] = active
+
+        is_finished = valid & (boundary_type == TARGET)
+        if self.compile_finished_rays:
+            finished = {f: input_rays[f][is_finished] for f in fields}
+            self._finished_rays.append(finished)
+            result["rays"]["finished"] = finished
+
+        is_stopped = valid & (boundary_type == STOP)
+        if self.compile_stopped_rays:
+            stopped = {f: input_rays[f][is_stopped] for f in fields}
+            self._stopped_rays.append(stopped)
+            result["rays"]["stopped"] = stopped
+
+        gather_optical = inter["gather_trig"][is_active]
+        optical = {f: v[gather_optical] for f, v in system._amalgamated_optical.items()}
+        if gather_optical.shape[0] > 0:
+            optical["norm"] = inter["norm"][is_active]
+        result["optical"] = optical
+
+        if self.compile_technical_intersections and self.compile_stopped_rays:
+            g = (inter["gather_trig"] - system._optical_count)[is_stopped]
+            stop = {f: v[g] for f, v in system._amalgamated_stop.items()}
+            if g.shape[0] > 0:
+                stop["norm"] = inter["norm"][is_stopped]
+            result["stop"] = stop
+        if self.compile_technical_intersections and self.compile_finished_rays:
+            g = (inter["gather_trig"] - system._optical_count - system._stop_count)[is_finished]
+            target = {f: v[g] for f, v in system._amalgamated_target.items()}
+            if g.shape[0] > 0:
+                target["norm"] = inter["norm"][is_finished]
+            result["target"] = target
+        return result
+
+    def _react_projection(self, reaction, proj_result):
+        """StandardReaction.main on one projection result (tfrt/operation.py:255-307)."""
+        rays = proj_result["rays"]["active"]
+        optical = proj_result["optical"]
+        if reaction.refractive_index_type == "index":
+            wavelength = rays["wavelength"]
+            n_stack = torch.stack(
+                [(m["n"] if isinstance(m, dict) else m)(wavelength)
+                 for m in self.optical_system.materials])
+            idx = torch.arange(wavelength.shape[0], device=wavelength.device)
+            n_in = n_stack[optical["mat_in"].long(), idx]
+            n_out = n_stack[optical["mat_out"].long(), idx]
+        else:
+            n_in, n_out = optical["n_in"], optical["n_out"]
+        new_rays = {}
+        if self.dimension == 2:
+            (new_rays["x_start"], new_rays["y_start"], new_rays["x_end"],
+             new_rays["y_end"]) = geometry.snells_law_2D(
+                rays["x_start"], rays["y_start"], rays["x_end"], rays["y_end"],
+                optical["norm"], n_in, n_out, self.new_ray_length)
+        else:
+            (new_rays["x_start"], new_rays["y_start"], new_rays["z_start"], new_rays["x_end"],
+             new_rays["y_end"], new_rays["z_end"]) = geometry.snells_law_3D(
+                rays["x_start"], rays["y_start"], rays["z_start"], rays["x_end"],
+                rays["y_end"], rays["z_end"], optical["norm"], n_in, n_out,
+                self.new_ray_length)
+        valid = torch.ones_like(rays["x_end"], dtype=torch.bool)
+        return {"active": {"rays": new_rays, "valid": valid}}
+
+    def single_pass(self, input_rays):
+        """One projection + reaction step (tfrt/engine.py:2193-2302)."""
+        if not bool(self.optical_system):
+            return {}
+        self.last_projection_result = self.process_projection(input_rays)
+        for branch in (self.last_projection_result,
+                       self.last_projection_result.get("arc", {}),
+                       self.last_projection_result.get("seg", {})):
+            domain = branch.get("rays")
+            if domain:
+                for t in list(domain.keys()):
+                    if domain[t]["x_start"].shape[0] == 0:
+                        domain.pop(t)
+
+        for o in self._operations:
+            o.preprocess(self, self.last_projection_result)
+        new_ray_dict = {}
+        for o in self._operations:
+            op_result = o.main(self, self.last_projection_result)
+            if bool(op_result):
+                new_ray_dict[o] = op_result
+
+        for op_entry in new_ray_dict.values():
+            for entry_type, entry in op_entry.items():
+                base, _, geo = entry_type.partition("_")
+                parent = (self.last_projection_result[geo]["rays"][base] if geo
+                          else self.last_projection_result["rays"][base])
+                for sig in self.simple_ray_inheritance:
+                    entry["rays"][sig] = parent[sig]
+
+        for o in self._operations:
+            o.postprocess(self, self.last_projection_result, new_ray_dict)
+
+        new_ray_list = []
+        for op_entry in new_ray_dict.values():
+            for geo_entry in op_entry.values():
+                valid = geo_entry["valid"]
+                new_ray_list.append({k: f[valid] for k, f in geo_entry["rays"].items()})
+        return amalgamate(new_ray_list)

@@ -39,6 +39,23 @@ def fp32_peak(packed=1, iters=4096):
     return out.value
 
 
+def launch_count(reset=False):
+    """Kernel launches issued by libtfrt_b200 in this process (bench.py: gpu_launches)."""
+    return int(_lib.load().tfrt_launch_count(1 if reset else 0))
+
+
+def profile_enable(on=True):
+    """Bracket every launch of the intersect kernel with CUDA events on its stream."""
+    check(_lib.load().tfrt_profile_enable(1 if on else 0), "tfrt_profile_enable")
+
+
+def profile_read():
+    """(total milliseconds, launches) of the intersect kernel since the last read."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+    check(_lib.load().tfrt_profile_read(ctypes.byref(ms), ctypes.byref(n)), "tfrt_profile_read")
+    return ms.value, int(n.value)
+
+
 def faces_forward(vertices, faces):
     """K3 forward.  vertices (V,3) f32 cuda, faces (F,3) int32 cuda -> (tri (9,F), norm (F,3))."""
     _require_cuda(vertices, faces)

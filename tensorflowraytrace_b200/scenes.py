@@ -208,3 +208,72 @@ def triangle_count(scene):
     n += sum(s["faces"].shape[0] for s in scene["targets"])
     n += sum(s["faces"].shape[0] for s in scene["stops"])
     return n
+
+
+# ----------------------------------------------------------------------------- public-API build
+
+def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, **engine_kwargs):
+    """Instantiate a scene through the public API (boundaries / sources / OpticalSystem3D /
+    OpticalEngine with one StandardReaction), the way the reference's scripts do
+    (dev/simple_3d_optimize.py:69-120).  Returns (engine, parameters, source).
+
+    ray_slice : optional slice of the source rays (parity sub-samples).
+    ray_shard : optional (rank, world_size) for multi-GPU ray sharding.
+    eps       : optional dict intersect_epsilion / size_epsilion / ray_start_epsilion.
+    """
+    from . import boundaries, engine as eng, materials, operation, sources
+
+    optical, params = [], []
+    for s in scene["surfaces"]:
+        mesh = boundaries.TriangleMesh(s["zero_points"], s["faces"])
+        b = boundaries.ParametricTriangleBoundary(
+            mesh, boundaries.FromVectorVG(s["vectors"]) if np.any(s["vectors"])
+            else _ZeroVG(), initial_parameters=s["parameters"],
+            vertex_update_map=s.get("vertex_update_map"),
+            material_dict={"mat_in": np.int64(s["mat_in"]), "mat_out": np.int64(s["mat_out"])})
+        optical.append(b)
+        params.append(b.parameters)
+
+    def static(lst):
+        return [boundaries.ManualTriangleBoundary(
+            mesh=boundaries.TriangleMesh(m["vertices"], m["faces"])) for m in lst]
+
+    src = sources.ManualSource(3)
+    src.feed({k: (v if ray_slice is None else v[ray_slice]) for k, v in scene["sources"].items()})
+
+    system = eng.OpticalSystem3D(ray_shard=ray_shard, **(eps or {}))
+    system.optical = optical
+    system.stops = static(scene["stops"])
+    system.targets = static(scene["targets"])
+    system.sources = [src]
+    system.materials = [{"n": materials.BY_NAME[name]} for name in scene["materials"]]
+    system.update()
+    inherit = {k for k in scene["sources"] if k not in
+               ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")}
+    engine = eng.OpticalEngine(3, [operation.StandardReaction()],
+                               simple_ray_inheritance=inherit, **engine_kwargs)
+    engine.optical_system = system
+    engine.validate_system()
+    return engine, params, src
+
+
+class _ZeroVG:
+    """Vector generator of an immovable surface (all-zero vectors): a parametric boundary whose
+    parameters have no effect, used for the static light guide of config 4."""
+
+    def generate(self, zero):
+        import torch
+        return torch.zeros_like(zero)
+
+
+def imaging_error(scene):
+    """The reference's imaging loss (dev/simple_3d_optimize.py:128-140): squared distance of
+    every finished ray's (y_end, z_end) to goal = goal_scale * rank."""
+    goal_scale = float(scene["goal_scale"])
+
+    def error_function(engine):
+        fin = engine.finished_rays
+        goal = goal_scale * fin["rank"]
+        return (fin["y_end"] - goal[:, 0]) ** 2 + (fin["z_end"] - goal[:, 1]) ** 2
+
+    return error_function

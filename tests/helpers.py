@@ -30,6 +30,8 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
     for k, v in scene["sources"].items():
         v = v if ray_slice is None else v[ray_slice]
         src[k] = torch.from_numpy(np.ascontiguousarray(rnd(v)))
+    n_src = src["x_start"].shape[0]
+    src["slot"] = torch.arange(n_src, dtype=torch.float64)   # source-ray id (local)
     params, optical = [], []
     for s in scene["surfaces"]:
         p = torch.from_numpy(rnd(s["parameters"])).clone().requires_grad_(requires_grad)
@@ -53,7 +55,7 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
     system = oe.OracleSystem3D(
         [src], optical, static(scene["stops"]), static(scene["targets"]),
         materials=[{"n": om.BY_NAME[name]} for name in scene["materials"]], **eps)
-    inherit = tuple(k for k in scene["sources"] if k not in RAY_FIELDS)
+    inherit = tuple(k for k in src if k not in RAY_FIELDS)
     engine = oe.OracleEngine3D(system, simple_ray_inheritance=inherit, **engine_kwargs)
     return engine, params
 
@@ -63,3 +65,75 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-30)
     return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA-vs-oracle comparison of a whole trace
+
+def compare_trace(engine, oracle, near_tie_rel=1e-6):
+    """Compare the fused CUDA trace held by `engine.last_trace` with a traced oracle engine,
+    iteration by iteration and slot by slot.
+
+    Returns a dict: mismatches (total hit-index mismatches), near_ties (how many of those were
+    near ties: gap to the runner-up < near_tie_rel relative), exempt (set of slots whose path
+    diverged after a near tie), max_rel (worst relative error of S / hit point / ray_u over
+    matching slots).  Raises AssertionError on a mismatch that is not a near tie."""
+    tr = engine.last_trace
+    K, exempt = tr.K, set()
+    out = {"mismatches": 0, "near_ties": 0, "max_rel": 0.0, "iterations": 0}
+    tape_tri = tr.tape_tri.cpu().numpy()
+    tape_status = tr.tape_status.cpu().numpy()
+    tape_f = tr.tape_f.cpu().numpy()
+    for k in range(min(K, len(oracle.last_intersect_result))):
+        ores, oin = oracle.last_intersect_result[k], oracle.last_input_rays[k]
+        slots = oin["slot"].numpy().astype(np.int64)
+        keep = np.array([s not in exempt for s in slots], dtype=bool)
+        ovalid = ores["valid"].numpy()
+        otri = np.where(ovalid, ores["gather_trig"].numpy(), -1)
+        # every non-exempt oracle-live slot must be live in the kernel at iteration k
+        assert np.all(tape_status[k][slots[keep]] != 255), f"iteration {k}: live sets differ"
+        ktri = tape_tri[k][slots]
+        bad = keep & (ktri != otri)
+        if bad.any():
+            idx = np.nonzero(bad)[0]
+            rays = {f: v[idx] for f, v in oin.items()}
+            excl = torch.from_numpy(np.where(otri[idx] >= 0, otri[idx], 0))
+            second = oracle.optical_system.second_best(rays, excl).numpy()
+            best = np.where(ovalid[idx], ores["ray_u"].numpy()[idx], np.inf)
+            for j, i in enumerate(idx):
+                both_inf = not np.isfinite(best[j]) and not np.isfinite(second[j])
+                gap = 0.0 if both_inf else abs(second[j] - best[j]) / max(abs(best[j]), 1e-30)
+                # the kernel's pick must be (numerically) as near as the oracle's
+                assert np.isfinite(gap) and gap < near_tie_rel, (
+                    f"iteration {k} slot {slots[i]}: kernel tri {ktri[i]} vs oracle {otri[i]}, "
+                    f"gap to runner-up {gap:.3e} is not a near tie")
+                exempt.add(int(slots[i]))
+            out["mismatches"] += int(bad.sum())
+            out["near_ties"] += int(bad.sum())
+        good = keep & ~bad & ovalid
+        if good.any():
+            s = slots[good]
+            for c, f in enumerate(("x_start", "y_start", "z_start")):
+                out["max_rel"] = max(out["max_rel"], rel_err(tape_f[k][c][s], oin[f].numpy()[good]))
+            for c, f in enumerate(("x", "y", "z")):
+                out["max_rel"] = max(out["max_rel"], rel_err(tape_f[k][3 + c][s], ores[f].numpy()[good]))
+            out["max_rel"] = max(out["max_rel"], rel_err(tape_f[k][6][s], ores["ray_u"].numpy()[good]))
+        out["iterations"] += 1
+    out["exempt"] = exempt
+    return out
+
+
+def compare_sets(engine_set, oracle_set, exempt, fields, slot_field="slot", engine_slots=None):
+    """Worst relative error over `fields` between an engine history set and the oracle's, matched
+    by source slot, skipping exempt slots.  engine_slots: (n,) source slot of each engine row."""
+    oslots = oracle_set[slot_field].numpy().astype(np.int64)
+    eslots = np.asarray(engine_slots, dtype=np.int64)
+    okeep = np.array([s not in exempt for s in oslots], dtype=bool)
+    ekeep = np.array([s not in exempt for s in eslots], dtype=bool)
+    assert np.array_equal(oslots[okeep], eslots[ekeep]), "history order / membership differs"
+    worst = 0.0
+    for f in fields:
+        e = engine_set[f].detach().cpu().numpy()[ekeep]
+        o = oracle_set[f].detach().numpy()[okeep]
+        worst = max(worst, rel_err(e, o))
+    return worst

@@ -1,0 +1,57 @@
+"""The C-ABI library builds, loads and exports every symbol include/tfrt_b200.h declares
+(no compute calls: runs without a GPU)."""
+
+import ctypes
+import os
+import re
+
+from tensorflowraytrace_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tfrt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tfrt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    assert lib.tfrt_abi_version() == 1
+    assert lib.tfrt_last_error() is not None
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ctypes.CDLL(_build.build())
+    names = declared_symbols()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in tfrt_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_struct_layouts_match_header_sizes():
+    # pointer-size sanity of the ctypes mirrors (a mismatch would corrupt every call)
+    assert ctypes.sizeof(_lib.TfrtMaterial) == 8 + 7 * 8
+    a = _lib.TfrtTrace3DArgs()
+    assert ctypes.sizeof(a) % 8 == 0
+    assert _lib.TfrtTrace3DArgs.src.offset == 40
+    assert _lib.load().tfrt_packed_floats(1) == 256 * 12
+    assert _lib.load().tfrt_packed_floats(257) == 512 * 12
+
+
+def test_sass_is_blackwell_native():
+    """The intersect kernel must use the TMA bulk copy (UBLKCP) and packed FFMA2 on sm_100a."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", _build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out
+    assert "FFMA2" in out
