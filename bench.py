@@ -358,8 +358,11 @@ def run_ours(args):
             "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
             "share_of_step": k_ms * 1e-3 / seconds,
             "flop_per_test": FLOP_PER_TEST,
-            "issued_flop_per_test": 18.0,
-            "frac_of_issued": 18.0 * tests_per_launch / (k_ms / k_n * 1e-3) / fp32_peak,
+            # the kernel's plane form issues 14 FFMA + 2 FMUL + 2 FADD (as 9 packed f32x2
+            # instructions per ray pair) + 1 MUFU.RCP per test: 18 FMA-pipe lane-slots
+            "fma_pipe_slots_per_test": 18.0,
+            "fma_pipe_utilisation": 18.0 * tests_per_launch / (k_ms / k_n * 1e-3)
+                                    / (fp32_peak / 2.0),
             "peak_source": "measured in this run by tfrt_fp32_peak (register-only FFMA loop on "
                            "all SMs); MEASURED_PEAKS.json carries no fp32 figure. Nominal "
                            "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",

@@ -152,7 +152,7 @@ def test_trace_cfg2_forward_parity():
     worst = helpers.compare_sets(act, oact, cmp["exempt"], RAYS, engine_slots=_slots(engine, "active"))
     assert worst < POINT_TOL, worst
     # output ray directions (unit vectors) to 1e-5
-    d = np.stack([(fin[a + "_end"] - fin[a + "_start"]).cpu().numpy() for a in "xyz"], 1)
+    d = np.stack([(fin[a + "_end"] - fin[a + "_start"]).detach().cpu().numpy() for a in "xyz"], 1)
     od = np.stack([(ofin[a + "_end"] - ofin[a + "_start"]).numpy() for a in "xyz"], 1)
     keep = np.array([s not in cmp["exempt"] for s in _slots(engine, "finished")])
     okeep = np.array([s not in cmp["exempt"] for s in ofin["slot"].numpy().astype(int)])
@@ -301,7 +301,7 @@ def test_unfused_single_pass_path_matches_fused():
         a, b = getattr(fused, name + "_rays"), getattr(unf, name + "_rays")
         assert a["x_start"].shape == b["x_start"].shape
         for f in RAYS + ("wavelength",):
-            assert helpers.rel_err(b[f].cpu().numpy(), a[f].cpu().numpy()) < POINT_TOL, (name, f)
+            assert helpers.rel_err(b[f].detach().cpu().numpy(), a[f].detach().cpu().numpy()) < POINT_TOL, (name, f)
 
 
 def test_unfused_gradient_matches_fused():
