@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TFRT_B200_ABI_VERSION 1
+#define TFRT_B200_ABI_VERSION 2
 
 /* ray status after one projection (tfrt/engine.py:2063-2111) */
 #define TFRT_STATUS_ACTIVE 0   /* hit an OPTICAL boundary: reacts and continues */
@@ -55,6 +55,10 @@ typedef struct {
 
 const char *tfrt_last_error(void);
 int tfrt_abi_version(void);
+/* sizeof() of the ABI structs as compiled into the library, so a binding can verify its mirror:
+ * which = 0 TfrtMaterial, 1 TfrtTrace3DArgs, 2 TfrtTrace3DBwdArgs, 3 TfrtTrace2DArgs;
+ * 0 for an unknown code. */
+size_t tfrt_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
  * K3  vertices -> triangle fields.
@@ -118,7 +122,10 @@ typedef struct {
 
     const float *src[7];    /* x_start,y_start,z_start,x_end,y_end,z_end,wavelength; N each */
     const float *tri[9];    /* xp,yp,zp,x1,y1,z1,x2,y2,z2; T each */
-    const float *norm;      /* (T,3) */
+    const float *norm;      /* (T,3) stored normals, or NULL: the normal of a hit triangle is then
+                               normalize((p2-p1) x (p3-p2)) evaluated in fp64 from its corners
+                               (what tfrt/boundaries.py:918-923 stores), and the backward pass
+                               routes its cotangent straight into the corner cotangents */
     const int32_t *category; /* T */
     const int32_t *mat_in;  /* n_optical (index mode) */
     const int32_t *mat_out;
@@ -128,7 +135,12 @@ typedef struct {
     const float *packed;    /* tfrt_pack_triangles output */
 
     /* workspace + history ("tape"), all caller-allocated */
-    float *cur[6];          /* N each: working ray state (start, end) per slot */
+    float *cur[6];          /* N each: working ray state per slot: start (3) and
+                               direction = end - start (3), fp32 copy read by the
+                               intersection search */
+    double *cur_d;          /* 6*N: the same state in fp64: the per-ray chain from one iteration
+                               to the next is carried in fp64 so rounding does not compound
+                               over bounces (O(N) work; the O(N*T) search is fp32) */
     uint64_t *hit;          /* N */
     float *tape_f;          /* K*9*N : per iteration Sx,Sy,Sz,Px,Py,Pz,ray_u,trig_u,trig_v */
     int32_t *tape_tri;      /* K*N : merged triangle index of the hit (-1: none) */
@@ -179,7 +191,8 @@ int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_ho
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (roofline denominators): run an FFMA-only loop on every SM and return the
- * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2). */
+ * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2),
+ * 2 / 3: FFMA2 interleaved with scalar FFMA at 1:1 / 2:1 (do the two forms share one pipe?). */
 int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream);
 
 /* Number of kernel launches libtfrt_b200 has issued in this process since the last reset

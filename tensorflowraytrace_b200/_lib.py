@@ -42,6 +42,7 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("materials", c_void_p),
         ("packed", c_void_p),
         ("cur", c_void_p * 6),
+        ("cur_d", c_void_p),
         ("hit", c_void_p),
         ("tape_f", c_void_p),
         ("tape_tri", c_void_p),
@@ -68,7 +69,7 @@ class TfrtTrace3DBwdArgs(ctypes.Structure):
 
 # every symbol include/tfrt_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "tfrt_last_error", "tfrt_abi_version",
+    "tfrt_last_error", "tfrt_abi_version", "tfrt_struct_size",
     "tfrt_faces_forward", "tfrt_faces_backward",
     "tfrt_packed_floats", "tfrt_pack_triangles",
     "tfrt_intersect3d",
@@ -76,6 +77,9 @@ EXPORTED_SYMBOLS = [
     "tfrt_trace3d_backward",
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
+
+ABI_VERSION = 2
+STRUCT_MIRRORS = (TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs)
 
 _lib = None
 
@@ -97,10 +101,21 @@ def load():
         raise RuntimeError(f"tensorflowraytrace_b200: cannot load {_build.LIB_PATH}: {e}") from e
     lib.tfrt_last_error.restype = ctypes.c_char_p
     lib.tfrt_abi_version.restype = ctypes.c_int
+    lib.tfrt_struct_size.restype = ctypes.c_size_t
+    lib.tfrt_struct_size.argtypes = [ctypes.c_int]
     lib.tfrt_packed_floats.restype = ctypes.c_size_t
     lib.tfrt_packed_floats.argtypes = [ctypes.c_int32]
     lib.tfrt_launch_count.restype = ctypes.c_longlong
     lib.tfrt_launch_count.argtypes = [ctypes.c_int]
+    if lib.tfrt_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"tensorflowraytrace_b200: {_build.LIB_PATH} has ABI version "
+                           f"{lib.tfrt_abi_version()}, this package needs {ABI_VERSION}; rebuild "
+                           f"with `python -m tensorflowraytrace_b200._build --force`")
+    for code, mirror in enumerate(STRUCT_MIRRORS):
+        if lib.tfrt_struct_size(code) != ctypes.sizeof(mirror):
+            raise RuntimeError(f"tensorflowraytrace_b200: ctypes mirror of {mirror.__name__} is "
+                               f"{ctypes.sizeof(mirror)} bytes, the library's is "
+                               f"{lib.tfrt_struct_size(code)}")
     _lib = lib
     return lib
 

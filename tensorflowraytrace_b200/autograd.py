@@ -38,7 +38,9 @@ class FacesFunction(torch.autograd.Function):
 
 
 class TraceFunction(torch.autograd.Function):
-    """Whole-loop trace.  Inputs: tri (9,T), norm (T,3), src (7,N) [x_start..z_end, wavelength],
+    """Whole-loop trace.  Inputs: tri (9,T), norm (T,3) or None (geometric normals evaluated in
+    the kernel from the corners, their gradient then arrives through `tri`), src (7,N)
+    [x_start..z_end, wavelength],
     and a `plan` (TracePlan) carrying the non-tensor configuration.  Outputs: the four history
     ray sets (6,n_which) in the reference's order -- active, stopped, finished, dead -- with
     (6,0) for sets the engine does not compile.  The kernels.Trace3D object (tape) is left in
@@ -85,7 +87,8 @@ class TraceFunction(torch.autograd.Function):
             g_src_full = torch.zeros(ctx.src_shape, dtype=torch.float32, device=g_tri.device)
             g_src_full[:6] = g_src
         return (g_tri if ctx.needs_input_grad[0] else None,
-                g_norm if ctx.needs_input_grad[1] else None, g_src_full, None)
+                g_norm if (ctx.needs_input_grad[1] and tr.norm is not None) else None,
+                g_src_full, None)
 
 
 class TracePlan:

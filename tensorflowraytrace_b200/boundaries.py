@@ -361,6 +361,11 @@ class TriangleBoundaryBase(BoundaryBase):
         for i, k in enumerate(("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")):
             self[k] = tri[i]
         self["norm"] = norm
+        self._geometric_norm = norm   # the fused trace may re-derive it from the corners in fp64
+
+    def has_geometric_norm(self):
+        """True while the `norm` field is the one computed from the vertices (not overridden)."""
+        return self._fields.get("norm") is getattr(self, "_geometric_norm", None) is not None
 
     def update_from_mesh(self):
         if self._mesh is not None:

@@ -14,6 +14,14 @@ void tfrt_set_error(const char *fmt, ...) {
 
 extern "C" const char *tfrt_last_error(void) { return g_err; }
 extern "C" int tfrt_abi_version(void) { return TFRT_B200_ABI_VERSION; }
+extern "C" size_t tfrt_struct_size(int which) {
+    switch (which) {
+    case 0: return sizeof(TfrtMaterial);
+    case 1: return sizeof(TfrtTrace3DArgs);
+    case 2: return sizeof(TfrtTrace3DBwdArgs);
+    default: return 0;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // launch counter + optional event timing of the intersect kernel
@@ -107,6 +115,34 @@ __global__ void __launch_bounds__(256) k_ffma_packed(int iters, float seed, floa
     if (s == 123.456f) sink[0] = s;
 }
 
+// Mixed loop: 8 packed FFMA2 chains + NS scalar FFMA chains per round.  Tells whether scalar
+// FFMA can issue beside FFMA2 (two fp32 data paths) or shares one pipe with it.
+template <int NS>
+__global__ void __launch_bounds__(256) k_ffma_mixed(int iters, float seed, float *sink) {
+    float2 a[8], b = make_float2(seed, seed * 1.5f), c = make_float2(seed * 0.5f, seed * 0.25f);
+    float s1[NS];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(seed + i, seed - i);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s1[i] = seed * (i + 2);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = __ffma2_rn(a[i], b, c);
+                if (i < NS) s1[i] = fmaf(s1[i], b.x, c.y);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s += s1[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 
 extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream) {
@@ -124,7 +160,11 @@ extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *
     float best_ms = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {   // first repetition is the warm-up
         TFRT_CHECK_CUDA(cudaEventRecord(e0, st));
-        if (packed)
+        if (packed == 2)
+            k_ffma_mixed<8><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
+        else if (packed == 3)
+            k_ffma_mixed<4><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
+        else if (packed)
             k_ffma_packed<<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
         else
             k_ffma_scalar<<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
@@ -134,7 +174,9 @@ extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *
         TFRT_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best_ms) best_ms = ms;
     }
-    const double fmas = (double)blocks * threads * (double)iters * 64.0 * (packed ? 2.0 : 1.0);
+    // lane-FMAs per thread per outer iteration: 64 scalar, 128 packed, 128 + 8*NS mixed
+    const double per_iter = packed == 2 ? 192.0 : packed == 3 ? 160.0 : packed ? 128.0 : 64.0;
+    const double fmas = (double)blocks * threads * (double)iters * per_iter;
     *flops_per_s = 2.0 * fmas / (best_ms * 1e-3);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

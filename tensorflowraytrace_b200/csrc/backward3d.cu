@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
             }
             double gH[3] = {ghP[0], ghP[1], ghP[2]};
             double gSd[3] = {ghS[0], ghS[1], ghS[2]};
+            double gnA[3] = {0, 0, 0}, gnB[3] = {0, 0, 0}, gnC[3] = {0, 0, 0};   // via the normal
             if (status == TFRT_STATUS_ACTIVE) {
                 double gSn[3], gEn[3];
                 for (int c = 0; c < 3; ++c) {
@@ -136,7 +137,16 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                 const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
                 const double dinv = rsqrt(fmax(d2, 1e-12));
                 const double uh[3] = {d[0] * dinv, d[1] * dinv, d[2] * dinv};
-                const double nr[3] = {P.norm[3 * tri], P.norm[3 * tri + 1], P.norm[3 * tri + 2]};
+                double nr[3], cu[3], cv[3], clen = 1.0;
+                if (P.norm) {
+                    nr[0] = P.norm[3 * tri]; nr[1] = P.norm[3 * tri + 1]; nr[2] = P.norm[3 * tri + 2];
+                } else {   // geometric normal from the corners, as in the forward kernel
+                    for (int c = 0; c < 3; ++c) { cu[c] = B[c] - A[c]; cv[c] = C[c] - B[c]; }
+                    const double cr[3] = {cu[1] * cv[2] - cu[2] * cv[1], cu[2] * cv[0] - cu[0] * cv[2],
+                                          cu[0] * cv[1] - cu[1] * cv[0]};
+                    clen = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+                    for (int c = 0; c < 3; ++c) nr[c] = cr[c] / clen;
+                }
                 const double n2 = nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2];
                 const double ninv = rsqrt(fmax(n2, 1e-12));
                 const double nh[3] = {nr[0] * ninv, nr[1] * ninv, nr[2] * ninv};
@@ -188,8 +198,28 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                 }
                 {
                     const double dot = g_nh[0] * nh[0] + g_nh[1] * nh[1] + g_nh[2] * nh[2];
+                    double g_nr[3];   // cotangent of the (unit) normal fed to the reaction
                     for (int c = 0; c < 3; ++c)
-                        acc[9 + c] = (n2 > 1e-12) ? (g_nh[c] - dot * nh[c]) * ninv : g_nh[c] * ninv;
+                        g_nr[c] = (n2 > 1e-12) ? (g_nh[c] - dot * nh[c]) * ninv : g_nh[c] * ninv;
+                    if (P.norm) {
+                        for (int c = 0; c < 3; ++c) acc[9 + c] = g_nr[c];
+                    } else {
+                        // through n = c/|c|, c = u x v, u = B - A, v = C - B  (K3 backward fused):
+                        //   g_c = (g_n - (g_n.n) n)/|c| ; g_u = v x g_c ; g_v = g_c x u
+                        //   g_A -= g_u ; g_B += g_u - g_v ; g_C += g_v
+                        const double dn = g_nr[0] * nr[0] + g_nr[1] * nr[1] + g_nr[2] * nr[2];
+                        const double gc[3] = {(g_nr[0] - dn * nr[0]) / clen, (g_nr[1] - dn * nr[1]) / clen,
+                                              (g_nr[2] - dn * nr[2]) / clen};
+                        const double gu[3] = {cv[1] * gc[2] - cv[2] * gc[1], cv[2] * gc[0] - cv[0] * gc[2],
+                                              cv[0] * gc[1] - cv[1] * gc[0]};
+                        const double gv[3] = {gc[1] * cu[2] - gc[2] * cu[1], gc[2] * cu[0] - gc[0] * cu[2],
+                                              gc[0] * cu[1] - gc[1] * cu[0]};
+                        for (int c = 0; c < 3; ++c) {
+                            gnA[c] = -gu[c];
+                            gnB[c] = gu[c] - gv[c];
+                            gnC[c] = gv[c];
+                        }
+                    }
                 }
             }
             // hit-point block
@@ -205,9 +235,9 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
             const double b0 = 1.0 - u - v;
             for (int c = 0; c < 3; ++c) {
                 const double km = kappa * m[c];
-                acc[c] = b0 * km;
-                acc[3 + c] = u * km;
-                acc[6 + c] = v * km;
+                acc[c] = b0 * km + gnA[c];
+                acc[3 + c] = u * km + gnB[c];
+                acc[6 + c] = v * km + gnC[c];
                 const double proj = gH[c] - km;
                 gS[c] = gSd[c] + (1.0 - t) * proj;
                 gE[c] = t * proj;

@@ -42,7 +42,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const int32_t *__restrict__ live, const int32_t *__restrict__ n_live_ptr,
               int n_live_static, const float4 *__restrict__ packed, int n_tiles,
               int tiles_per_split, float intersect_eps, float ray_start_eps, float w_one,
-              unsigned long long *__restrict__ hit, int use_atomic) {
+              unsigned long long *__restrict__ hit, int use_atomic, int dir_mode) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IntersectSmem &sm = *reinterpret_cast<IntersectSmem *>(smem_raw);
 
@@ -92,9 +92,11 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             if (p < n_live) {
                 const int slot = live ? live[p] : p;
                 const float ax = sx[slot], ay = sy[slot], az = sz[slot];
-                d[h][0] = ex[slot] - ax;
-                d[h][1] = ey[slot] - ay;
-                d[h][2] = ez[slot] - az;
+                // dir_mode: the last three arrays hold the direction (end - start) itself, the
+                // form the trace loop keeps between iterations (no cancellation error)
+                d[h][0] = dir_mode ? ex[slot] : ex[slot] - ax;
+                d[h][1] = dir_mode ? ey[slot] : ey[slot] - ay;
+                d[h][2] = dir_mode ? ez[slot] : ez[slot] - az;
                 // shift the origin by ray_start_eps along the ray: t_shifted >= 0 <=> ray_u >= eps
                 o[h][0] = fmaf(ray_start_eps, d[h][0], ax);
                 o[h][1] = fmaf(ray_start_eps, d[h][1], ay);
@@ -228,7 +230,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
 int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
                             const int32_t *n_live_ptr, int n_upper, const float *packed,
                             int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
-                            uint64_t *hit, cudaStream_t stream) {
+                            uint64_t *hit, int dir_mode, cudaStream_t stream) {
     if (n_upper <= 0 || n_tri <= 0) return 0;
     const int n_tiles = tfrt_div_up(n_tri, TFRT_TILE_TRIS);
     static int num_sms = 0;
@@ -265,7 +267,7 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
             ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,          \
             reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, intersect_eps,  \
             ray_start_eps, 1.0f + 3.0f * size_eps, reinterpret_cast<unsigned long long *>(hit),       \
-            use_atomic);            \
+            use_atomic, dir_mode);  \
     } while (0)
     const bool timed = tfrt_profile_begin(stream);
     if (r2 == 4) TFRT_LAUNCH(4);

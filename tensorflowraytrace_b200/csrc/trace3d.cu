@@ -17,7 +17,7 @@
 int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
                             const int32_t *n_live_ptr, int n_upper, const float *packed,
                             int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
-                            uint64_t *hit, cudaStream_t stream);
+                            uint64_t *hit, int dir_mode, cudaStream_t stream);
 
 namespace {
 
@@ -63,6 +63,7 @@ struct ReactParams {
     const float *n_in, *n_out;
     const TfrtMaterial *materials;
     float *cur[6];
+    double *cur_d;             // 6*N: the same state in fp64 (the chain between iterations)
     const uint64_t *hit;
     const int32_t *live;       // live[k]
     const int32_t *n_live_ptr; // &counters[k*4]
@@ -113,13 +114,14 @@ __global__ void __launch_bounds__(kReactThreads) k_react3d(ReactParams P) {
         const int slot = P.live[p];
         const uint64_t hit = P.hit[p];
         const uint32_t key = (uint32_t)(hit >> 32);
+        // working state = (start, direction) in fp64; end = start + direction
+        const size_t N = (size_t)P.n_rays;
         double S[3], E[3];
         for (int c = 0; c < 3; ++c) {
-            S[c] = P.cur[c][slot];
-            E[c] = P.cur[3 + c][slot];
+            S[c] = P.cur_d[c * N + slot];
+            E[c] = S[c] + P.cur_d[(3 + c) * N + slot];
         }
         float *tf = P.tape_f;
-        const size_t N = (size_t)P.n_rays;
         int tri = -1;
         double Pt[3] = {E[0], E[1], E[2]};
         double t = 0.0, u = 0.0, v = 0.0;
@@ -146,13 +148,31 @@ __global__ void __launch_bounds__(kReactThreads) k_react3d(ReactParams P) {
                     n_in = P.n_in[tri];
                     n_out = P.n_out[tri];
                 }
-                const double nrm[3] = {P.norm[3 * tri], P.norm[3 * tri + 1], P.norm[3 * tri + 2]};
+                double nrm[3];
+                if (P.norm) {
+                    nrm[0] = P.norm[3 * tri]; nrm[1] = P.norm[3 * tri + 1]; nrm[2] = P.norm[3 * tri + 2];
+                } else {
+                    // geometric normal normalize((p2-p1) x (p3-p2)) (tfrt/boundaries.py:918-923)
+                    // in fp64 from the corners: no fp32 rounding of the normal enters the chain
+                    const double ux = B[0] - A[0], uy = B[1] - A[1], uz = B[2] - A[2];
+                    const double vx = C[0] - B[0], vy = C[1] - B[1], vz = C[2] - B[2];
+                    const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+                    const double inv = 1.0 / sqrt(cx * cx + cy * cy + cz * cz);
+                    nrm[0] = cx * inv; nrm[1] = cy * inv; nrm[2] = cz * inv;
+                }
                 double w[3];
                 snell3d(S, Pt, nrm, n_in, n_out, w);
-                // new ray = (hit, hit + new_ray_length * w)   (tfrt/geometry.py:751-753)
+                // new ray = (hit, hit + new_ray_length * w)   (tfrt/geometry.py:751-753), kept as
+                // (hit, new_ray_length * w): the direction keeps its full fp32 precision instead
+                // of being re-derived from two rounded end points
+                // The fp64 copy carries the ray from one iteration to the next, so rounding does
+                // not compound over bounces; the fp32 copy feeds the intersection search.
                 for (int c = 0; c < 3; ++c) {
+                    const double d = P.new_ray_length * w[c];
+                    P.cur_d[c * N + slot] = Pt[c];
+                    P.cur_d[(3 + c) * N + slot] = d;
                     P.cur[c][slot] = (float)Pt[c];
-                    P.cur[3 + c][slot] = (float)(Pt[c] + P.new_ray_length * w[c]);
+                    P.cur[3 + c][slot] = (float)d;
                 }
             }
         }
@@ -260,10 +280,17 @@ __global__ void k_iota(int32_t *out, int n) {
 
 __global__ void k_copy_rays(const float *s0, const float *s1, const float *s2, const float *s3,
                             const float *s4, const float *s5, float *d0, float *d1, float *d2,
-                            float *d3, float *d4, float *d5, int n) {
+                            float *d3, float *d4, float *d5, double *cur_d, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    d0[i] = s0[i]; d1[i] = s1[i]; d2[i] = s2[i]; d3[i] = s3[i]; d4[i] = s4[i]; d5[i] = s5[i];
+    // working state = (start, direction); the fp64 difference of two floats is exact
+    const double a0 = s0[i], a1 = s1[i], a2 = s2[i];
+    const double b0 = (double)s3[i] - a0, b1 = (double)s4[i] - a1, b2 = (double)s5[i] - a2;
+    const size_t N = (size_t)n;
+    cur_d[i] = a0; cur_d[N + i] = a1; cur_d[2 * N + i] = a2;
+    cur_d[3 * N + i] = b0; cur_d[4 * N + i] = b1; cur_d[5 * N + i] = b2;
+    d0[i] = (float)a0; d1[i] = (float)a1; d2[i] = (float)a2;
+    d3[i] = (float)b0; d4[i] = (float)b1; d5[i] = (float)b2;
 }
 
 __global__ void k_init_counters(int32_t *counters, int n_rays, int n_entries) {
@@ -338,7 +365,7 @@ extern "C" int tfrt_intersect3d(const float *const ray[6], int32_t n_rays,
     if (n_rays == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = tfrt_launch_intersect3d(ray, nullptr, nullptr, n_rays, packed, n_tri, intersect_eps,
-                                     ray_start_eps, size_eps, hit_ws, st);
+                                     ray_start_eps, size_eps, hit_ws, /*dir_mode=*/0, st);
     if (rc) return rc;
     k_intersect_outputs<<<tfrt_div_up(n_rays, 256), 256, 0, st>>>(
         ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], tri[0], tri[1], tri[2], tri[3], tri[4],
@@ -354,7 +381,8 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
     TFRT_REQUIRE(a->n_rays >= 0 && a->n_tri > 0 && a->max_iterations > 0,
                  "tfrt_trace3d_forward: n_rays=%d n_tri=%d max_iterations=%d", a->n_rays,
                  a->n_tri, a->max_iterations);
-    TFRT_REQUIRE(a->packed && a->norm && a->category && a->hit && a->tape_f && a->tape_tri &&
+    TFRT_REQUIRE(a->cur_d, "tfrt_trace3d_forward: null cur_d workspace");
+    TFRT_REQUIRE(a->packed && a->category && a->hit && a->tape_f && a->tape_tri &&
                      a->tape_status && a->tape_outpos && a->live && a->block_counts && a->counters,
                  "tfrt_trace3d_forward: null workspace pointer");
     TFRT_REQUIRE(a->index_mode ? (a->materials && a->mat_in && a->mat_out && a->src[6])
@@ -370,7 +398,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
     const int nb = tfrt_div_up(N, 256);
     k_copy_rays<<<nb, 256, 0, st>>>(a->src[0], a->src[1], a->src[2], a->src[3], a->src[4],
                                     a->src[5], a->cur[0], a->cur[1], a->cur[2], a->cur[3],
-                                    a->cur[4], a->cur[5], N);
+                                    a->cur[4], a->cur[5], a->cur_d, N);
     k_iota<<<nb, 256, 0, st>>>(a->live, N);
     tfrt_note_launch(3);
     TFRT_CHECK_CUDA(cudaMemsetAsync(a->tape_status, 0xff, (size_t)K * N, st));
@@ -383,7 +411,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
         const float *cur_c[6] = {a->cur[0], a->cur[1], a->cur[2], a->cur[3], a->cur[4], a->cur[5]};
         int rc = tfrt_launch_intersect3d(cur_c, live_k, counters_k, N, a->packed, a->n_tri,
                                          a->intersect_eps, a->ray_start_eps, a->size_eps, a->hit,
-                                         st);
+                                         /*dir_mode=*/1, st);
         if (rc) return rc;
         ReactParams P;
         P.n_tri = a->n_tri; P.n_optical = a->n_optical; P.index_mode = a->index_mode;
@@ -394,6 +422,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
         P.norm = a->norm; P.category = a->category; P.mat_in = a->mat_in; P.mat_out = a->mat_out;
         P.n_in = a->n_in; P.n_out = a->n_out; P.materials = a->materials;
         for (int c = 0; c < 6; ++c) P.cur[c] = a->cur[c];
+        P.cur_d = a->cur_d;
         P.hit = a->hit; P.live = live_k; P.n_live_ptr = counters_k;
         P.tape_f = a->tape_f + (size_t)k * 9 * N;
         P.tape_tri = a->tape_tri + (size_t)k * N;

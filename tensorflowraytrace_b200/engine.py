@@ -179,6 +179,7 @@ class OpticalSystem3D(OpticalSystemBase):
         self._amalgamated_target = {}
         self._materials = []
         self._merged = {}
+        self._norm_is_geometric = False
         self._optical_count = self._stop_count = self._target_count = 0
         self._dev_cache = None
         self.clear_read_only()
@@ -248,6 +249,11 @@ class OpticalSystem3D(OpticalSystemBase):
             parts.append(d)
         self._optical_count, self._stop_count, self._target_count = counts
         self._merged = amalgamate(parts, TRIANGLE_GEO_SIG | {"catagory"})
+        # every `norm` is the geometric face normal of its triangle (not user-overridden): the
+        # fused trace then evaluates normals in fp64 from the corners instead of the fp32 field
+        self._norm_is_geometric = all(
+            getattr(b, "has_geometric_norm", lambda: False)()
+            for b in list(self._optical) + list(self._stop) + list(self._target) if bool(b))
         self._dev_cache = None
 
     # ------------------------------------------------------------------ kernel-side views
@@ -333,6 +339,8 @@ class OpticalEngine:
         self.clear_ray_history()
         self.last_projection_result = {}
         self.last_trace = None     # kernels.Trace3D of the last fused trace (tape, live counts)
+        self.last_history_slots = {}
+        self.last_history_iterations = {}
 
         self.input_signature = set()
         self.output_signature = set()
@@ -546,14 +554,15 @@ class OpticalEngine:
             dead_ray_length=self.dead_ray_length if bool(self.dead_ray_length) else None,
             compile=compile_sets, **kw)
         plan.packed = packed
-        active, stopped, finished, dead = TraceFunction.apply(tri, norm, src, plan)
+        active, stopped, finished, dead = TraceFunction.apply(
+            tri, None if system._norm_is_geometric else norm, src, plan)
         self.last_trace = plan.trace
 
         inherit = [f for f in src_fields if f not in RAY_FIELDS_3D]
 
         def as_set(name, rays):
-            if rays.shape[1] == 0:
-                return None
+            # a compiled set exists even when no ray fell into it: the reference appends one
+            # (possibly empty) field dict per iteration (tfrt/engine.py:2028-2111)
             out = {k: rays[i] for i, k in enumerate(RAY_FIELDS_3D)}
             slot = plan.slots[name].long()
             for f in inherit:
@@ -565,9 +574,10 @@ class OpticalEngine:
                                   ("stopped", stopped, self._stopped_rays),
                                   ("dead", dead, self._dead_rays)):
             if name in compile_sets:
-                s = as_set(name, rays)
-                if s is not None:
-                    store.append(s)
+                store.append(as_set(name, rays))
+        # source-ray index / iteration of every row of each compiled history set
+        self.last_history_slots = dict(plan.slots)
+        self.last_history_iterations = dict(plan.iters)
         self.last_projection_result = {}
 
     # ------------------------------------------------------------------ unfused single pass

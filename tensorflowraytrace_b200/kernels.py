@@ -137,10 +137,10 @@ class Trace3D:
     def __init__(self, src, tri, norm, category, n_optical, max_iterations, *, packed=None,
                  mat_in=None, mat_out=None, n_in=None, n_out=None, materials=None, n_materials=0,
                  intersect_eps=1e-10, size_eps=1e-10, ray_start_eps=1e-10, new_ray_length=1.0):
-        _require_cuda(src, tri, norm, category)
+        _require_cuda(src, tri, norm, category)   # norm may be None: geometric normals
         self.src = _f32(src)          # (7,N): x_start..z_end, wavelength
         self.tri = _f32(tri)          # (9,T)
-        self.norm = _f32(norm)        # (T,3)
+        self.norm = None if norm is None else _f32(norm)        # (T,3)
         self.category = category.to(torch.int32).contiguous()
         dev = self.src.device
         N, T, K = self.src.shape[1], self.tri.shape[1], int(max_iterations)
@@ -156,6 +156,7 @@ class Trace3D:
         n1 = max(N, 1)
         i32 = dict(dtype=torch.int32, device=dev)
         self.cur = torch.empty((6, n1), dtype=torch.float32, device=dev)
+        self.cur_d = torch.empty((6, n1), dtype=torch.float64, device=dev)
         self.hit = torch.empty((n1,), dtype=torch.int64, device=dev)
         self.tape_f = torch.empty((K, 9, n1), dtype=torch.float32, device=dev)
         self.tape_tri = torch.empty((K, n1), **i32)
@@ -176,7 +177,8 @@ class Trace3D:
             a.src[i] = self.src[i].data_ptr()
         for i in range(9):
             a.tri[i] = self.tri[i].data_ptr()
-        a.norm, a.category = self.norm.data_ptr(), self.category.data_ptr()
+        a.norm = 0 if self.norm is None else self.norm.data_ptr()
+        a.category = self.category.data_ptr()
         a.mat_in = 0 if self.mat_in is None else self.mat_in.data_ptr()
         a.mat_out = 0 if self.mat_out is None else self.mat_out.data_ptr()
         a.n_in = 0 if self.n_in is None else self.n_in.data_ptr()
@@ -185,6 +187,7 @@ class Trace3D:
         a.packed = self.packed.data_ptr()
         for i in range(6):
             a.cur[i] = self.cur[i].data_ptr()
+        a.cur_d = self.cur_d.data_ptr()
         a.hit, a.tape_f = self.hit.data_ptr(), self.tape_f.data_ptr()
         a.tape_tri, a.tape_status = self.tape_tri.data_ptr(), self.tape_status.data_ptr()
         a.tape_outpos, a.live = self.tape_outpos.data_ptr(), self.live.data_ptr()

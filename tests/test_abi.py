@@ -20,7 +20,7 @@ def test_library_builds_and_loads():
     path = _build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.tfrt_abi_version() == 1
+    assert lib.tfrt_abi_version() == _lib.ABI_VERSION
     assert lib.tfrt_last_error() is not None
 
 
@@ -39,6 +39,9 @@ def test_struct_layouts_match_header_sizes():
     a = _lib.TfrtTrace3DArgs()
     assert ctypes.sizeof(a) % 8 == 0
     assert _lib.TfrtTrace3DArgs.src.offset == 40
+    lib = _lib.load()
+    for code, mirror in enumerate(_lib.STRUCT_MIRRORS):
+        assert lib.tfrt_struct_size(code) == ctypes.sizeof(mirror), mirror.__name__
     assert _lib.load().tfrt_packed_floats(1) == 256 * 12
     assert _lib.load().tfrt_packed_floats(257) == 512 * 12
 

@@ -187,6 +187,7 @@ def test_trace_gradient_parity_lens():
     ograds = torch.autograd.grad(oerr[keep].sum(), oparams)
     if cmp["exempt"]:   # drop the same rays from the CUDA loss
         ekeep = torch.tensor([int(s) not in cmp["exempt"] for s in _slots(engine, "finished")], device=DEV)
+        engine.optical_system.update()     # fresh graph (the reference updates inside the tape)
         engine.ray_trace(3)
         err = scenes.imaging_error(scene)(engine)
         grads = torch.autograd.grad(err[ekeep].sum(), params)
@@ -208,8 +209,8 @@ def test_trace_light_guide_tir_multiwavelength():
     assert live[0] == 3000 and live[-1] < live[0]
     for name in ("finished", "dead", "active"):
         e, o = getattr(engine, name + "_rays"), getattr(oracle, name + "_rays")
-        if not bool(o):
-            assert not bool(e)
+        if not bool(o) or o["x_start"].shape[0] == 0:
+            assert not bool(e) or e["x_start"].shape[0] == 0
             continue
         worst = helpers.compare_sets(e, o, cmp["exempt"], RAYS + ("wavelength",),
                                      engine_slots=_slots(engine, name))
@@ -273,8 +274,11 @@ def test_value_mode_mirrors_and_stop():
     seen = 0
     for name in ("finished", "stopped", "dead", "active"):
         e, o = getattr(engine, name + "_rays"), getattr(oracle, name + "_rays")
-        assert bool(e) == bool(o), name
-        if bool(o):
+        assert bool(e) == bool(o), name           # compiled sets exist even when empty
+        n_o = o["x_start"].shape[0] if bool(o) else 0
+        n_e = e["x_start"].shape[0] if bool(e) else 0
+        assert n_e == n_o or cmp["exempt"], name
+        if n_o:
             seen += 1
             assert helpers.compare_sets(e, o, cmp["exempt"], RAYS, engine_slots=_slots(engine, name)) < POINT_TOL
     assert seen >= 3
@@ -352,14 +356,27 @@ def test_full_size_cfg3_properties():
     whole.ray_trace(3)
     for k in RAYS:
         assert torch.equal(whole.finished_rays[k], ref[k])       # (c)
-    parts, g_parts = [], None
+    # (d): histories are iteration-major, so shards are compared per source ray (slot), which is
+    # also how a multi-GPU caller reassembles them
+    def per_slot(engine, offset):
+        slot = engine.last_history_slots["finished"].long() + offset
+        return slot, {k: engine.finished_rays[k].detach() for k in RAYS}
+
+    wslot, wrays = per_slot(whole, 0)
+    dense = {k: torch.full((n,), float("nan"), device=DEV) for k in RAYS}
+    for k in RAYS:
+        dense[k][wslot] = wrays[k]
+    g_parts, seen = None, 0
+    from tensorflowraytrace_b200.parallel import shard_range
     for r in range(2):
         sh, p, _ = scenes.build_engine(scene, eps=helpers.EPS, ray_shard=(r, 2), compile_active_rays=False)
         sh.ray_trace(3)
-        parts.append({k: sh.finished_rays[k] for k in RAYS})
+        sslot, srays = per_slot(sh, shard_range(n, r, 2)[0])
+        for k in RAYS:
+            assert torch.equal(srays[k], dense[k][sslot])                    # (d)
+        seen += sslot.numel()
         g = torch.autograd.grad(errf(sh).sum(), p)
         g_parts = g if g_parts is None else [a + b for a, b in zip(g_parts, g)]
-    for k in RAYS:
-        assert torch.equal(torch.cat([parts[0][k], parts[1][k]]), ref[k])    # (d)
+    assert seen == wslot.numel()
     for a, b in zip(g_whole, g_parts):
         assert helpers.rel_err(b.cpu().numpy(), a.cpu().numpy()) < GRAD_TOL   # (e)
