@@ -190,6 +190,73 @@ int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_ho
                           const TfrtTrace3DBwdArgs *bwd, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4  2D path: segments + arcs.
+ *
+ * tfrt_intersect2d replaces OpticalSystem2D.intersect (tfrt/engine.py:523-616), i.e.
+ * _segment_intersection (:687-749, geometry.line_intersect tfrt/geometry.py:27-167),
+ * _arc_intersection (:767-866, geometry.line_circle_intersect tfrt/geometry.py:338-547,
+ * angle_in_interval :766-802), the segment norm atan2(dy,dx)+pi/2 (:580-586), _get_arc_norm
+ * (:666-670) and _seg_or_arc (:626-657).  All arithmetic is fp64 on the fp32 inputs: the 2D
+ * path is launch-latency bound, so the search itself runs at the reference's
+ * precision and hit indices need no near-tie exemption.
+ *
+ * ray[4] = x_start,y_start,x_end,y_end (N).  seg[4] = x_start,y_start,x_end,y_end (n_seg, merged
+ * optical -> stop -> target); arc[5] = x_center,y_center,angle_start,angle_end,radius (n_arc).
+ * Outputs (N each, any may be NULL): seg_out[5] / arc_out[5] = x, y, ray_u, segment_u|arc_u,
+ * norm;  seg_valid / arc_valid (after _seg_or_arc when both kinds exist);  gather_segment /
+ * gather_arc (argmin index, 0 when nothing is valid, like the reference's argmin).
+ */
+int tfrt_intersect2d(const float *const ray[4], int32_t n_rays, const float *const seg[4],
+                     int32_t n_seg, const float *const arc[5], int32_t n_arc,
+                     float intersect_eps, float size_eps, float ray_start_eps,
+                     float *const seg_out[5], uint8_t *seg_valid, int32_t *gather_segment,
+                     float *const arc_out[5], uint8_t *arc_valid, int32_t *gather_arc,
+                     void *stream);
+
+/* Whole-loop 2D trace: OpticalEngine.ray_trace (tfrt/engine.py:2311-2330) with
+ * process_projection_2D (:1544-1986), single_pass (:2193-2302), StandardReaction.main
+ * (tfrt/operation.py:255-307) and geometry.snells_law_2D (tfrt/geometry.py:565-653) fused: one
+ * thread follows one source ray through all iterations (rays never split or interact).
+ * The result is a per-(iteration, slot) tape; the caller orders it into the reference's history
+ * sets (per iteration: segment hits, then arc hits, each order-preserving).
+ */
+#define TFRT_HIT2D_NONE (-1)
+typedef struct {
+    int32_t n_rays;
+    int32_t max_iterations;
+    int32_t n_seg, n_seg_optical, n_seg_stop;   /* merged order optical -> stop -> target */
+    int32_t n_arc, n_arc_optical, n_arc_stop;
+    float intersect_eps, size_eps, ray_start_eps, new_ray_length;
+    int32_t index_mode;     /* as TfrtTrace3DArgs */
+    int32_t n_materials;
+    const float *src[5];    /* x_start,y_start,x_end,y_end,wavelength; N each */
+    const float *seg[4];
+    const float *arc[5];
+    const int32_t *seg_mat_in, *seg_mat_out;   /* n_seg_optical (index mode) */
+    const float *seg_n_in, *seg_n_out;         /* n_seg_optical (value mode) */
+    const int32_t *arc_mat_in, *arc_mat_out;   /* n_arc_optical */
+    const float *arc_n_in, *arc_n_out;
+    const TfrtMaterial *materials;
+    /* tape, caller-allocated */
+    float *tape_f;          /* K*4*N: Sx,Sy,Px,Py (ray start, projected end) per iteration */
+    double *tape_d;         /* K*2*N: ray_u, boundary parameter (segment_u | arc_u) */
+    int32_t *tape_hit;      /* K*N: merged segment index s >= 0, arc index a as -2-a, or
+                               TFRT_HIT2D_NONE */
+    uint8_t *tape_status;   /* K*N: TFRT_STATUS_*; 255 = slot not live at that iteration */
+    int32_t *live_counts;   /* K: live rays entering each iteration */
+} TfrtTrace2DArgs;
+
+int tfrt_trace2d_forward(const TfrtTrace2DArgs *args, void *stream);
+
+/* VJP of tfrt_trace2d_forward.  g_tape is the cotangent of tape_f (K*4*N, zeros where unused).
+ * g_seg[4] (n_seg each) / g_arc[5] (n_arc each; angle_start / angle_end get zeros, they only
+ * enter comparisons) / g_src[4] (N each, may be NULL) are overwritten.  g_acc is
+ * (4*n_seg + 3*n_arc) doubles of workspace. */
+int tfrt_trace2d_backward(const TfrtTrace2DArgs *fwd, const float *g_tape, double *g_acc,
+                          float *const g_seg[4], float *const g_arc[5], float *const g_src[4],
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helpers (roofline denominators): run an FFMA-only loop on every SM and return the
  * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2),
  * 2 / 3: FFMA2 interleaved with scalar FFMA at 1:1 / 2:1 (do the two forms share one pipe?). */

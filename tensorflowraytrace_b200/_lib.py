@@ -67,6 +67,42 @@ class TfrtTrace3DBwdArgs(ctypes.Structure):
     ]
 
 
+class TfrtTrace2DArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_rays", ctypes.c_int32),
+        ("max_iterations", ctypes.c_int32),
+        ("n_seg", ctypes.c_int32),
+        ("n_seg_optical", ctypes.c_int32),
+        ("n_seg_stop", ctypes.c_int32),
+        ("n_arc", ctypes.c_int32),
+        ("n_arc_optical", ctypes.c_int32),
+        ("n_arc_stop", ctypes.c_int32),
+        ("intersect_eps", ctypes.c_float),
+        ("size_eps", ctypes.c_float),
+        ("ray_start_eps", ctypes.c_float),
+        ("new_ray_length", ctypes.c_float),
+        ("index_mode", ctypes.c_int32),
+        ("n_materials", ctypes.c_int32),
+        ("src", c_void_p * 5),
+        ("seg", c_void_p * 4),
+        ("arc", c_void_p * 5),
+        ("seg_mat_in", c_void_p),
+        ("seg_mat_out", c_void_p),
+        ("seg_n_in", c_void_p),
+        ("seg_n_out", c_void_p),
+        ("arc_mat_in", c_void_p),
+        ("arc_mat_out", c_void_p),
+        ("arc_n_in", c_void_p),
+        ("arc_n_out", c_void_p),
+        ("materials", c_void_p),
+        ("tape_f", c_void_p),
+        ("tape_d", c_void_p),
+        ("tape_hit", c_void_p),
+        ("tape_status", c_void_p),
+        ("live_counts", c_void_p),
+    ]
+
+
 # every symbol include/tfrt_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "tfrt_last_error", "tfrt_abi_version", "tfrt_struct_size",
@@ -75,11 +111,12 @@ EXPORTED_SYMBOLS = [
     "tfrt_intersect3d",
     "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
     "tfrt_trace3d_backward",
+    "tfrt_intersect2d", "tfrt_trace2d_forward", "tfrt_trace2d_backward",
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
 ABI_VERSION = 2
-STRUCT_MIRRORS = (TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs)
+STRUCT_MIRRORS = (TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs, TfrtTrace2DArgs)
 
 _lib = None
 

@@ -110,3 +110,36 @@ class TracePlan:
         self.packed = kw.get("packed")   # tfrt_pack_triangles output (built when None)
         self.trace = None
         self.slots, self.iters = {}, {}
+
+
+class Trace2DFunction(torch.autograd.Function):
+    """Whole-loop 2D trace (K4).  Inputs: seg (4,S) or None, arc (5,A) or None, src (5,N), and a
+    `plan` dict with the non-tensor configuration (kernels.Trace2D keyword arguments + counts +
+    max_iterations).  Output: the tape (K,4,N) f32 -- ray start and projected end per (iteration,
+    source ray) -- from which the engine gathers the reference-ordered history sets with plain
+    torch indexing (so their cotangents scatter back into this tape's cotangent)."""
+
+    @staticmethod
+    def forward(ctx, seg, arc, src, plan):
+        tr = kernels.Trace2D(src, seg, arc, plan["counts"], plan["max_iterations"],
+                             **plan["kwargs"])
+        tr.forward()
+        plan["trace"] = tr
+        ctx.trace = tr
+        ctx.src_shape = src.shape
+        return tr.tape_f[:, :, : tr.N]
+
+    @staticmethod
+    def backward(ctx, g_tape):
+        tr = ctx.trace
+        want_src = ctx.needs_input_grad[2]
+        g_full = g_tape
+        if g_full.shape[2] != tr.tape_f.shape[2]:     # N == 0 padding
+            g_full = torch.zeros_like(tr.tape_f)
+        g_seg, g_arc, g_src = tr.backward(g_full.contiguous(), want_src_grad=want_src)
+        g_src_full = None
+        if want_src:
+            g_src_full = torch.zeros(ctx.src_shape, dtype=torch.float32, device=g_tape.device)
+            g_src_full[:4] = g_src
+        return (g_seg if ctx.needs_input_grad[0] else None,
+                g_arc if ctx.needs_input_grad[1] else None, g_src_full, None)

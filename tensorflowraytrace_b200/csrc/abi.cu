@@ -19,6 +19,7 @@ extern "C" size_t tfrt_struct_size(int which) {
     case 0: return sizeof(TfrtMaterial);
     case 1: return sizeof(TfrtTrace3DArgs);
     case 2: return sizeof(TfrtTrace3DBwdArgs);
+    case 3: return sizeof(TfrtTrace2DArgs);
     default: return 0;
     }
 }

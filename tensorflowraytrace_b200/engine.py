@@ -79,6 +79,25 @@ def amalgamate(stuff, signature=None):
     return {field: torch.cat([item[field] for item in processed], 0) for field in signature}
 
 
+def annotation_helper(parent, field, value, valid_shape_field, dtype=None):
+    """Keep `parent[field]` annotated on every update (tfrt/engine.py:103-142): `value` is
+    broadcast to the shape of `parent[valid_shape_field]` (or, if callable, called with that
+    shape and `dtype`) by a post-update handle, e.g. to apply materials to a boundary."""
+    def f():
+        ref = parent[valid_shape_field]
+        if callable(value):
+            parent[field] = value(ref.shape, dtype)
+        else:
+            t = torch.as_tensor(value, device=ref.device)
+            if dtype is not None:
+                t = t.to(dtype)
+            elif t.is_floating_point():
+                t = t.to(torch.float32)
+            parent[field] = torch.broadcast_to(t, ref.shape).clone()
+    parent.post_update_handles.append(f)
+    f()
+
+
 # =========================================================================================
 
 class OpticalSystemBase(RecursivelyUpdatable):
@@ -307,6 +326,149 @@ class OpticalSystem3D(OpticalSystemBase):
                 raw["gather_ray"], g)
 
 
+class OpticalSystem2D(OpticalSystemBase):
+    """Segment + arc optical system (tfrt/engine.py:253-866): six boundary lists
+    (optical / stop / target x segments / arcs), merged optical -> stop -> target per geometry
+    (tfrt/engine.py:425-521)."""
+
+    _KINDS = ("optical_segments", "optical_arcs", "stop_segments", "stop_arcs",
+              "target_segments", "target_arcs")
+
+    def __init__(self, **kwargs):
+        for kind in self._KINDS:
+            setattr(self, "_" + kind, [])
+            setattr(self, kind + "_handles", [])
+            setattr(self, "_amalgamated_" + kind, {})
+        self._materials = []
+        self._merged_segments = {}
+        self._merged_arcs = {}
+        self._optical_seg_count = self._stop_seg_count = self._target_seg_count = 0
+        self._optical_arc_count = self._stop_arc_count = self._target_arc_count = 0
+        self.clear_read_only()
+        super().__init__(**kwargs)
+
+    def clear_read_only(self):
+        self._read_only_sources = None
+        for kind in self._KINDS:
+            setattr(self, "_read_only_" + kind, None)
+
+    def refresh_update_handles(self):
+        if not self.manual_update_management:
+            self.update_handles = self._generate_update_handles()
+
+    def _generate_update_handles(self):
+        out = list(self.source_handles)
+        for kind in self._KINDS:
+            out += getattr(self, kind + "_handles")
+        return out
+
+    @property
+    def dimension(self):
+        return 2
+
+    def _update(self):
+        self._amalgamate_sources()
+        for kind in self._KINDS:
+            items = getattr(self, "_" + kind)
+            if bool(items):
+                setattr(self, "_amalgamated_" + kind, amalgamate(items))
+        self._merge_boundaries()
+        self.clear_read_only()
+
+    def _kind_property(kind):  # noqa: N805  (class-body helper)
+        def getter(self):
+            if not bool(getattr(self, "_read_only_" + kind)):
+                setattr(self, "_read_only_" + kind,
+                        ReadOnlySet(getattr(self, "_amalgamated_" + kind)))
+            return getattr(self, "_read_only_" + kind)
+
+        def setter(self, new):
+            hs = []
+            for each in new:
+                assert each.dimension == self.dimension
+                hs.append(each.update)
+            setattr(self, kind + "_handles", hs)
+            setattr(self, "_" + kind, new)
+            self.refresh_update_handles()
+
+        return property(getter, setter)
+
+    optical_segments = _kind_property("optical_segments")
+    optical_arcs = _kind_property("optical_arcs")
+    stop_segments = _kind_property("stop_segments")
+    stop_arcs = _kind_property("stop_arcs")
+    target_segments = _kind_property("target_segments")
+    target_arcs = _kind_property("target_arcs")
+    del _kind_property
+
+    def _merge_boundaries(self):
+        """Label and merge optical -> stop -> target, per geometry (tfrt/engine.py:425-521)."""
+        def merge(suffix, key, sig):
+            counts, parts = [], []
+            for cat, name in ((OPTICAL, "optical"), (STOP, "stop"), (TARGET, "target")):
+                d = getattr(self, f"_amalgamated_{name}_{suffix}")
+                if bool(d):
+                    d["catagory"] = torch.full_like(d[key], cat, dtype=torch.int64)
+                    counts.append(d[key].shape[0])
+                else:
+                    counts.append(0)
+                parts.append(d)
+            return counts, amalgamate(parts, sig | {"catagory"})
+
+        (self._optical_seg_count, self._stop_seg_count, self._target_seg_count), \
+            self._merged_segments = merge("segments", "x_start", SEGMENT_GEO_SIG)
+        (self._optical_arc_count, self._stop_arc_count, self._target_arc_count), \
+            self._merged_arcs = merge("arcs", "x_center", ARC_GEO_SIG)
+
+    def merged_device_arrays(self):
+        """(seg (4,S) f32 or None, arc (5,A) f32 or None), attached to the autograd graph of
+        the boundary parameters."""
+        seg = arc = None
+        if bool(self._merged_segments):
+            seg = torch.stack([self._merged_segments[k] for k in kernels.SEG_FIELDS]).to(
+                torch.float32).contiguous()
+        if bool(self._merged_arcs):
+            arc = torch.stack([self._merged_arcs[k] for k in kernels.ARC_FIELDS]).to(
+                torch.float32).contiguous()
+        return seg, arc
+
+    def intersect(self, rays):
+        """Nearest valid intersection of each ray with the merged segments and arcs
+        (tfrt/engine.py:523-616).  Returns (segment_result, arc_result), each a dict with x, y,
+        valid, ray_u, segment_u | arc_u, gather_ray, gather_segment | gather_arc, norm ({} when
+        the system has no boundary of that geometry).  The search runs in the CUDA kernel; the
+        gathered values are re-evaluated 1-to-1 in torch so they carry the reference's
+        gradient."""
+        seg, arc = self.merged_device_arrays()
+        if seg is None and arc is None:
+            return {}, {}
+        ray_rows = torch.stack([rays[k] for k in kernels.RAY_FIELDS_2D])
+        raw_seg, raw_arc = kernels.intersect2d(
+            ray_rows.detach(), None if seg is None else seg.detach(),
+            None if arc is None else arc.detach(), self.intersect_epsilion, self.size_epsilion,
+            self.ray_start_epsilion)
+        xs, ys, xe, ye = (rays[k] for k in kernels.RAY_FIELDS_2D)
+        if raw_seg:
+            g = raw_seg["gather_segment"]
+            m = self._merged_segments
+            x, y, u, v = geometry.line_hit_2d(xs, ys, xe, ye, m["x_start"][g], m["y_start"][g],
+                                              m["x_end"][g], m["y_end"][g],
+                                              self.intersect_epsilion)
+            norm = torch.atan2(m["y_end"] - m["y_start"], m["x_end"] - m["x_start"]) \
+                + geometry.PI / 2.0
+            raw_seg.update(x=x, y=y, ray_u=u, segment_u=v, norm=norm[g])
+        if raw_arc:
+            g = raw_arc["gather_arc"]
+            m = self._merged_arcs
+            x, y, u, v = geometry.circle_hit_2d(xs, ys, xe, ye, m["x_center"][g],
+                                                m["y_center"][g], m["radius"][g],
+                                                raw_arc["ray_u"].detach())
+            arc_norm = torch.where(m["radius"][g] < 0, v + geometry.PI, v)
+            arc_norm = torch.remainder(arc_norm + geometry.PI, 2 * geometry.PI) - geometry.PI
+            raw_arc.update(x=x, y=y, ray_u=u, arc_u=v, norm=arc_norm)
+        return raw_seg, raw_arc
+
+
 # =========================================================================================
 
 class OpticalEngine:
@@ -493,7 +655,7 @@ class OpticalEngine:
 
     # ------------------------------------------------------------------ the trace loop
     def _fusable(self):
-        return (self.dimension == 3 and not self.compile_technical_intersections
+        return (self.dimension in (2, 3) and not self.compile_technical_intersections
                 and not self.compile_geometry_specific_result
                 and any(type(o) is op.StandardReaction for o in self._operations)
                 and all(type(o) in (op.StandardReaction, op.OldestAncestor) and o.active
@@ -506,7 +668,10 @@ class OpticalEngine:
             return
         self.clear_ray_history()
         if self._fusable():
-            self._ray_trace_fused(int(max_iterations))
+            if self.dimension == 2:
+                self._ray_trace_fused_2d(int(max_iterations))
+            else:
+                self._ray_trace_fused(int(max_iterations))
             return
         starting_rays = dict(self.optical_system._amalgamated_sources)
         for _ in range(max_iterations):
@@ -580,10 +745,183 @@ class OpticalEngine:
         self.last_history_iterations = dict(plan.iters)
         self.last_projection_result = {}
 
+    def _ray_trace_fused_2d(self, max_iterations):
+        """Whole 2D trace in one kernel launch (K4); histories are gathered from the
+        per-(iteration, source ray) tape in the reference's order: per iteration the rays that
+        hit segments, then those that hit arcs, each order-preserving
+        (tfrt/engine.py:1640-1660, :1797-1815); the next pass sees them in the same order
+        (:1950-1956)."""
+        from .autograd import Trace2DFunction
+        system = self.optical_system
+        src_fields = system._amalgamated_sources
+        seg, arc = system.merged_device_arrays()
+        if not bool(src_fields) or (seg is None and arc is None):
+            return
+        reaction = next(o for o in self._operations if type(o) is op.StandardReaction)
+        dev = (seg if seg is not None else arc).device
+        n = src_fields["x_start"].shape[0]
+        rows = [src_fields[k] for k in kernels.RAY_FIELDS_2D]
+        rows.append(src_fields["wavelength"] if "wavelength" in src_fields
+                    else torch.zeros(n, dtype=torch.float32, device=dev))
+        src = torch.stack([r.to(torch.float32) for r in rows]).contiguous()
+
+        index_mode = reaction.refractive_index_type == "index"
+        keys = ("mat_in", "mat_out") if index_mode else ("n_in", "n_out")
+
+        def mats(d):
+            return (d[keys[0]], d[keys[1]]) if bool(d) else None
+
+        kw = dict(seg_mat=mats(system._amalgamated_optical_segments),
+                  arc_mat=mats(system._amalgamated_optical_arcs),
+                  intersect_eps=system.intersect_epsilion, size_eps=system.size_epsilion,
+                  ray_start_eps=system.ray_start_epsilion, new_ray_length=self.new_ray_length)
+        if index_mode:
+            kw.update(materials=system.material_table(dev), n_materials=len(system.materials))
+        plan = {"counts": dict(seg_optical=system._optical_seg_count,
+                               seg_stop=system._stop_seg_count,
+                               arc_optical=system._optical_arc_count,
+                               arc_stop=system._stop_arc_count),
+                "max_iterations": max_iterations, "kwargs": kw}
+        tape = Trace2DFunction.apply(seg, arc, src, plan)        # (K, 4, N)
+        tr = plan["trace"]
+        self.last_trace = tr
+
+        status = tr.tape_status[:, :n]
+        is_arc = tr.tape_hit[:, :n] < -1
+        both = seg is not None and arc is not None
+        sets = {"active": ([], []), "stopped": ([], []), "finished": ([], []), "dead": ([], [])}
+        code = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}
+        if not both:
+            # one geometry: the live list stays in source order, so every set is the row-major
+            # (iteration, slot) list of its status code
+            for name, c in code.items():
+                it, slot = torch.nonzero(status == c, as_tuple=True)
+                sets[name] = ([it], [slot])
+        else:
+            order = torch.arange(n, device=dev)
+            for k in range(max_iterations):
+                if order.numel() == 0:
+                    break
+                st, ka = status[k, order], is_arc[k, order]
+                for name, c in code.items():
+                    parts = [order[st == c]] if name == "dead" else \
+                        [order[(st == c) & ~ka], order[(st == c) & ka]]
+                    for part in parts:
+                        sets[name][0].append(torch.full_like(part, k))
+                        sets[name][1].append(part)
+                order = torch.cat([order[(st == 0) & ~ka], order[(st == 0) & ka]])
+
+        inherit = [f for f in src_fields if f not in kernels.RAY_FIELDS_2D]
+        self.last_history_slots, self.last_history_iterations = {}, {}
+        for name, flag, store in (("active", self.compile_active_rays, self._active_rays),
+                                  ("finished", self.compile_finished_rays, self._finished_rays),
+                                  ("stopped", self.compile_stopped_rays, self._stopped_rays),
+                                  ("dead", self.compile_dead_rays, self._dead_rays)):
+            if not flag:
+                continue
+            it = torch.cat(sets[name][0]) if sets[name][0] else torch.zeros(0, dtype=torch.long, device=dev)
+            slot = torch.cat(sets[name][1]) if sets[name][1] else torch.zeros(0, dtype=torch.long, device=dev)
+            rays = tape[it, :, slot]                              # (n_set, 4)
+            out = {k: rays[:, i] for i, k in enumerate(kernels.RAY_FIELDS_2D)}
+            if name == "dead" and bool(self.dead_ray_length):
+                for c in "xy":
+                    out[c + "_end"] = out[c + "_start"] + self.dead_ray_length * (
+                        out[c + "_end"] - out[c + "_start"])
+            for f in inherit:
+                out[f] = src_fields[f][slot]
+            store.append(out)
+            self.last_history_slots[name] = slot
+            self.last_history_iterations[name] = it
+        self.last_projection_result = {}
+
     # ------------------------------------------------------------------ unfused single pass
     def process_projection_2D(self, input_rays):
-        raise NotImplementedError(
-            "OpticalEngine: the 2D projection is provided by engine2d (OpticalSystem2D).")
+        """Project rays onto the 2D system and split them by what they hit
+        (tfrt/engine.py:1544-1986).  Result layout as in the reference (`rays`, `optical`,
+        optionally `stop` / `target`); with both geometries present the combined sets are
+        segment hits followed by arc hits, rays and boundary data alike (the reference
+        concatenates the boundary data arc-first, tfrt/engine.py:1958-1965: a latent bug that
+        mis-pairs rays and boundaries, not reproduced -- DESIGN.md section 9)."""
+        system = self.optical_system
+        fields = list(input_rays.keys())
+        seg_proj, arc_proj = system.intersect(input_rays)
+        has_segments, has_arcs = bool(seg_proj), bool(arc_proj)
+        result = {}
+        if self.compile_dead_rays:
+            valid_any = None
+            for proj in (seg_proj, arc_proj):
+                if proj:
+                    valid_any = proj["valid"] if valid_any is None else (valid_any | proj["valid"])
+            is_dead = torch.logical_not(valid_any)
+            dead = {f: input_rays[f][is_dead] for f in fields}
+            if bool(self.dead_ray_length):
+                for c in "xy":
+                    dead[c + "_end"] = dead[c + "_start"] + self.dead_ray_length * (
+                        dead[c + "_end"] - dead[c + "_start"])
+            self._dead_rays.append(dead)
+
+        input_rays = dict(input_rays)
+        geo = {}
+        for name, proj, merged, gkey, counts in (
+                ("segment", seg_proj, system._merged_segments, "gather_segment",
+                 (system._optical_seg_count, system._stop_seg_count)),
+                ("arc", arc_proj, system._merged_arcs, "gather_arc",
+                 (system._optical_arc_count, system._stop_arc_count))):
+            if not proj:
+                continue
+            suffix = "segments" if name == "segment" else "arcs"
+            valid = proj["valid"]
+            for c in "xy":
+                input_rays[c + "_end"] = torch.where(valid, proj[c], input_rays[c + "_end"])
+            btype = merged["catagory"][proj[gkey]]
+            entry = {"rays": {}}
+            masks = {"active": valid & (btype == OPTICAL), "finished": valid & (btype == TARGET),
+                     "stopped": valid & (btype == STOP)}
+            entry["rays"]["active"] = {f: input_rays[f][masks["active"]] for f in fields}
+            if self.compile_active_rays:
+                self._active_rays.append(entry["rays"]["active"])
+            if self.compile_finished_rays:
+                entry["rays"]["finished"] = {f: input_rays[f][masks["finished"]] for f in fields}
+                self._finished_rays.append(entry["rays"]["finished"])
+            if self.compile_stopped_rays:
+                entry["rays"]["stopped"] = {f: input_rays[f][masks["stopped"]] for f in fields}
+                self._stopped_rays.append(entry["rays"]["stopped"])
+            g = proj[gkey][masks["active"]]
+            optical = {f: v[g] for f, v in getattr(system, f"_amalgamated_optical_{suffix}").items()}
+            optical["norm"] = proj["norm"][masks["active"]]
+            entry["optical"] = optical
+            if self.compile_technical_intersections and self.compile_stopped_rays:
+                g = (proj[gkey] - counts[0])[masks["stopped"]]
+                entry["stop"] = {f: v[g] for f, v in
+                                 getattr(system, f"_amalgamated_stop_{suffix}").items()}
+                entry["stop"]["norm"] = proj["norm"][masks["stopped"]]
+            if self.compile_technical_intersections and self.compile_finished_rays:
+                g = (proj[gkey] - counts[0] - counts[1])[masks["finished"]]
+                entry["target"] = {f: v[g] for f, v in
+                                   getattr(system, f"_amalgamated_target_{suffix}").items()}
+                entry["target"]["norm"] = proj["norm"][masks["finished"]]
+            if self.compile_dead_rays:
+                entry["rays"]["dead"] = dead
+            geo[name] = entry
+        if self.compile_geometry_specific_result:
+            result.update(geo)
+        if has_segments != has_arcs:
+            only = geo["segment" if has_segments else "arc"]
+            result["rays"] = dict(only["rays"])
+            for k in ("optical", "stop", "target"):
+                if k in only:
+                    result[k] = only[k]
+        else:
+            a, b = geo["segment"], geo["arc"]
+            result["rays"] = {t: amalgamate([a["rays"][t], b["rays"][t]])
+                              for t in a["rays"] if t != "dead"}
+            for k in ("optical", "stop", "target"):
+                if k in a:
+                    common = set(a[k].keys()) & set(b[k].keys())
+                    result[k] = {f: torch.cat([a[k][f], b[k][f]], 0) for f in common}
+        if self.compile_dead_rays:
+            result["rays"]["dead"] = dead
+        return result
 
     def process_projection_3D(self, input_rays):
         """Project rays onto the system and split them by what they hit

@@ -87,3 +87,45 @@ def snells_law_2D(x_start, y_start, x_end, y_end, norm, n_in, n_out, new_ray_len
     w = _react(u, n, n_in, n_out, "2d")
     end = torch.stack([x_end, y_end], dim=1) + new_ray_length * w
     return x_end, y_end, end[:, 0], end[:, 1]
+
+
+# ---------------------------------------------------------------------------------------------
+# 2D, paired (1-to-1) and differentiable
+
+import math  # noqa: E402
+
+PI = math.pi
+
+
+def line_hit_2d(xs, ys, xe, ye, sx1, sy1, sx2, sy2, epsilion):
+    """Ray / segment-line solve for paired rays and segments (tfrt/geometry.py:136-167).
+    Returns (x, y, ray_u, segment_u)."""
+    x1, y1, x2, y2 = xe - xs, ye - ys, sx2 - sx1, sy2 - sy1
+    den = x1 * y2 - y1 * x2
+    valid = torch.abs(den) >= epsilion
+    inv = 1.0 / torch.where(valid, den, torch.ones_like(den))
+    one = torch.ones_like(den)
+    u = torch.where(valid, (x2 * (ys - sy1) - y2 * (xs - sx1)) * inv, one)
+    v = torch.where(valid, (y1 * (sx1 - xs) - x1 * (sy1 - ys)) * inv, one)
+    return xs + u * x1, ys + u * y1, u, v
+
+
+def circle_hit_2d(xs, ys, xe, ye, xc, yc, r, u_hint):
+    """Ray / circle solve for paired rays and arcs (tfrt/geometry.py:464-547), returning the
+    root the search kernel selected (`u_hint`, its ray parameter).  Returns (x, y, ray_u,
+    arc_u) where arc_u is the polar angle of the hit about the centre."""
+    inv_r = 1.0 / r
+    xr, yr = (xs - xc) * inv_r, (ys - yc) * inv_r
+    xd, yd = (xe - xs) * inv_r, (ye - ys) * inv_r
+    a = xd * xd + yd * yd
+    b = 2.0 * xr * xd + 2.0 * yr * yd
+    c = xr * xr + yr * yr - 1.0
+    rad = b * b - 4.0 * a * c
+    bad = (rad < 0) | (a == 0)
+    sq = torch.sqrt(torch.where(bad, torch.ones_like(rad), rad))
+    inv = 1.0 / torch.where(bad, torch.ones_like(a), 2.0 * a)
+    um, up = (-b - sq) * inv, (-b + sq) * inv
+    u = torch.where((um - u_hint).abs() <= (up - u_hint).abs(), um, up)
+    u = torch.where(bad, torch.ones_like(u), u)
+    x, y = xs + (xe - xs) * u, ys + (ye - ys) * u
+    return x, y, u, torch.atan2(y - yc, x - xc)

@@ -274,3 +274,145 @@ class Trace3D:
             _stream()), "tfrt_trace3d_backward")
         del keep
         return g_tri, g_norm, (None if g_src is None else g_src[:, : self.N])
+
+
+# ==============================================================================================
+# 2D (K4)
+
+SEG_FIELDS = ("x_start", "y_start", "x_end", "y_end")
+ARC_FIELDS = ("x_center", "y_center", "angle_start", "angle_end", "radius")
+RAY_FIELDS_2D = ("x_start", "y_start", "x_end", "y_end")
+
+
+def _rows(t, n):
+    return None if t is None else [t[i] for i in range(n)]
+
+
+def intersect2d(rays, seg, arc, intersect_eps, size_eps, ray_start_eps):
+    """2D intersection seam (tfrt/engine.py:523-616).  rays (4,N) f32; seg (4,S) f32 or None;
+    arc (5,A) f32 or None.  Returns (seg_result, arc_result) dicts with the reference's field
+    names ({} for an absent geometry)."""
+    _require_cuda(rays, seg, arc)
+    rays = _f32(rays)
+    seg = None if seg is None or seg.shape[1] == 0 else _f32(seg)
+    arc = None if arc is None or arc.shape[1] == 0 else _f32(arc)
+    if seg is None and arc is None:
+        raise ValueError("intersect2d: no boundaries")
+    N, dev = rays.shape[1], rays.device
+
+    def outputs(present):
+        if not present:
+            return None, None, None
+        return (torch.empty((5, N), dtype=torch.float32, device=dev),
+                torch.empty((N,), dtype=torch.uint8, device=dev),
+                torch.empty((N,), dtype=torch.int32, device=dev))
+
+    so, sv, sg = outputs(seg is not None)
+    ao, av, ag = outputs(arc is not None)
+    check(_lib.load().tfrt_intersect2d(
+        ptr_array(_rows(rays, 4), 4), N,
+        ptr_array(_rows(seg, 4) or [], 4), 0 if seg is None else seg.shape[1],
+        ptr_array(_rows(arc, 5) or [], 5), 0 if arc is None else arc.shape[1],
+        ctypes.c_float(intersect_eps), ctypes.c_float(size_eps), ctypes.c_float(ray_start_eps),
+        ptr_array(_rows(so, 5) or [], 5), ptr(sv), ptr(sg),
+        ptr_array(_rows(ao, 5) or [], 5), ptr(av), ptr(ag), _stream()), "tfrt_intersect2d")
+    ray_range = torch.arange(N, device=dev)
+    seg_res, arc_res = {}, {}
+    if seg is not None:
+        seg_res = {"x": so[0], "y": so[1], "ray_u": so[2], "segment_u": so[3], "norm": so[4],
+                   "valid": sv.bool(), "gather_ray": ray_range, "gather_segment": sg.long()}
+    if arc is not None:
+        arc_res = {"x": ao[0], "y": ao[1], "ray_u": ao[2], "arc_u": ao[3], "norm": ao[4],
+                   "valid": av.bool(), "gather_ray": ray_range, "gather_arc": ag.long()}
+    return seg_res, arc_res
+
+
+class Trace2D:
+    """One whole-loop 2D trace: owns the per-(iteration, slot) tape."""
+
+    def __init__(self, src, seg, arc, counts, max_iterations, *, seg_mat=None, arc_mat=None,
+                 materials=None, n_materials=0, intersect_eps=1e-10, size_eps=1e-10,
+                 ray_start_eps=1e-10, new_ray_length=1.0):
+        """src (5,N): x_start,y_start,x_end,y_end,wavelength.  seg (4,S) / arc (5,A) merged
+        optical -> stop -> target (either may be None).  counts = dict(seg_optical, seg_stop,
+        arc_optical, arc_stop).  seg_mat / arc_mat: (in, out) tensors over the OPTICAL
+        boundaries -- int material indices when `materials` is given, else float n values."""
+        _require_cuda(src, seg, arc)
+        self.src = _f32(src)
+        self.seg = None if seg is None or seg.shape[1] == 0 else _f32(seg)
+        self.arc = None if arc is None or arc.shape[1] == 0 else _f32(arc)
+        dev = self.src.device
+        N, K = self.src.shape[1], int(max_iterations)
+        self.N, self.K = N, K
+        self.S = 0 if self.seg is None else self.seg.shape[1]
+        self.A = 0 if self.arc is None else self.arc.shape[1]
+        self.index_mode = 1 if materials is not None else 0
+        self.materials = materials
+        n1 = max(N, 1)
+        self.tape_f = torch.zeros((K, 4, n1), dtype=torch.float32, device=dev)
+        self.tape_d = torch.zeros((K, 2, n1), dtype=torch.float64, device=dev)
+        self.tape_hit = torch.full((K, n1), -1, dtype=torch.int32, device=dev)
+        self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
+        self.live = torch.empty((K,), dtype=torch.int32, device=dev)
+        self._live_host = None
+
+        def conv(pair):
+            if pair is None:
+                return None, None
+            if self.index_mode:
+                return (pair[0].to(torch.int32).contiguous(), pair[1].to(torch.int32).contiguous())
+            return _f32(pair[0]), _f32(pair[1])
+
+        self._seg_mat, self._arc_mat = conv(seg_mat), conv(arc_mat)
+        a = _lib.TfrtTrace2DArgs()
+        a.n_rays, a.max_iterations = N, K
+        a.n_seg, a.n_seg_optical, a.n_seg_stop = self.S, int(counts.get("seg_optical", 0)), int(counts.get("seg_stop", 0))
+        a.n_arc, a.n_arc_optical, a.n_arc_stop = self.A, int(counts.get("arc_optical", 0)), int(counts.get("arc_stop", 0))
+        a.intersect_eps, a.size_eps = float(intersect_eps), float(size_eps)
+        a.ray_start_eps, a.new_ray_length = float(ray_start_eps), float(new_ray_length)
+        a.index_mode, a.n_materials = self.index_mode, int(n_materials)
+        for i in range(5):
+            a.src[i] = self.src[i].data_ptr()
+        for i in range(4):
+            a.seg[i] = 0 if self.seg is None else self.seg[i].data_ptr()
+        for i in range(5):
+            a.arc[i] = 0 if self.arc is None else self.arc[i].data_ptr()
+        p = lambda t: 0 if t is None else t.data_ptr()   # noqa: E731
+        if self.index_mode:
+            a.seg_mat_in, a.seg_mat_out = p(self._seg_mat[0]), p(self._seg_mat[1])
+            a.arc_mat_in, a.arc_mat_out = p(self._arc_mat[0]), p(self._arc_mat[1])
+        else:
+            a.seg_n_in, a.seg_n_out = p(self._seg_mat[0]), p(self._seg_mat[1])
+            a.arc_n_in, a.arc_n_out = p(self._arc_mat[0]), p(self._arc_mat[1])
+        a.materials = p(materials)
+        a.tape_f, a.tape_d = self.tape_f.data_ptr(), self.tape_d.data_ptr()
+        a.tape_hit, a.tape_status = self.tape_hit.data_ptr(), self.tape_status.data_ptr()
+        a.live_counts = self.live.data_ptr()
+        self.args = a
+
+    def forward(self):
+        self._live_host = None
+        check(_lib.load().tfrt_trace2d_forward(ctypes.byref(self.args), _stream()),
+              "tfrt_trace2d_forward")
+        return self
+
+    def live_counts(self):
+        if self._live_host is None:
+            self._live_host = [int(v) for v in self.live.cpu().tolist()]
+        return self._live_host
+
+    def backward(self, g_tape, want_src_grad=False):
+        """g_tape (K,4,N) f32 -> (g_seg (4,S) | None, g_arc (5,A) | None, g_src (4,N) | None)."""
+        dev = self.src.device
+        g_tape = _f32(g_tape)
+        if tuple(g_tape.shape) != tuple(self.tape_f.shape):
+            raise ValueError(f"cotangent of the 2D tape has shape {tuple(g_tape.shape)}")
+        g_acc = torch.empty((4 * self.S + 3 * self.A + 1,), dtype=torch.float64, device=dev)
+        g_seg = torch.empty((4, self.S), dtype=torch.float32, device=dev) if self.S else None
+        g_arc = torch.empty((5, self.A), dtype=torch.float32, device=dev) if self.A else None
+        g_src = torch.empty((4, max(self.N, 1)), dtype=torch.float32, device=dev) if want_src_grad else None
+        check(_lib.load().tfrt_trace2d_backward(
+            ctypes.byref(self.args), ptr(g_tape), ptr(g_acc),
+            ptr_array(_rows(g_seg, 4) or [], 4), ptr_array(_rows(g_arc, 5) or [], 5),
+            ptr_array(_rows(g_src, 4) or [], 4), _stream()), "tfrt_trace2d_backward")
+        return g_seg, g_arc, (None if g_src is None else g_src[:, : self.N])

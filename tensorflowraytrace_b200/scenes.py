@@ -198,6 +198,132 @@ def config4(ray_count=4194304, theta_res=100, z_res=250, seed=4321, max_iteratio
     }
 
 
+# ----------------------------------------------------------------------------- 2D configs
+
+def rays_2d(starts, angles, wavelengths, ray_length=1.0):
+    """2D source fields: end = start + ray_length (cos a, sin a) (tfrt/sources.py:598-603)."""
+    angles = np.asarray(angles, dtype=np.float64)
+    starts = np.broadcast_to(np.asarray(starts, dtype=np.float64), (angles.shape[0], 2))
+    return {
+        "x_start": np.ascontiguousarray(starts[:, 0]),
+        "y_start": np.ascontiguousarray(starts[:, 1]),
+        "x_end": starts[:, 0] + ray_length * np.cos(angles),
+        "y_end": starts[:, 1] + ray_length * np.sin(angles),
+        "wavelength": np.ascontiguousarray(
+            np.broadcast_to(np.asarray(wavelengths, dtype=np.float64), angles.shape)),
+    }
+
+
+def _scene2d(name, sources, max_iterations, **boundaries):
+    scene = {"name": name, "dimension": 2, "sources": sources, "materials": ["vacuum", "acrylic"],
+             "max_iterations": max_iterations}
+    for kind in ("optical_segments", "optical_arcs", "stop_segments", "stop_arcs",
+                 "target_segments", "target_arcs"):
+        scene[kind] = boundaries.get(kind, [])
+    return scene
+
+
+def config1(ray_count=1000):
+    """BASELINE config 1: point source at (-2, 0), 1 000 rays over
+    [-0.2, 0.2] rad (StaticUniformAngularDistribution = linspace, tfrt/distributions.py:302-309),
+    575 nm, through an acrylic wedge made of two optical segments, onto a target segment at
+    x = 10 (as dev/performance.py:38-39); 3 iterations."""
+    src = rays_2d((-2.0, 0.0), np.linspace(-0.2, 0.2, ray_count), YELLOW)
+    wedge = {"segments": np.array([[0.0, -1.0, 0.0, 1.0], [0.4, 1.0, 0.5, -1.0]]),
+             "mat_in": 1, "mat_out": 0}
+    target = {"segments": np.array([[10.0, -5.0, 10.0, 5.0]])}
+    return _scene2d(f"cfg1_2d_wedge_{ray_count}rays", src, 3,
+                    optical_segments=[wedge], target_segments=[target])
+
+
+def arc_lens_2d(ray_count=600):
+    """The arc lens of dev/single_pass.py:34-57: one optical arc (centre (5,0), radius 5, from
+    3pi/4 to 5pi/4), a parallel beam of six wavelengths from x = -1; plus a target segment."""
+    y = np.linspace(-1.5, 1.5, ray_count)
+    wl = np.asarray(RAINBOW_6)[np.arange(ray_count) % 6]
+    src = rays_2d(np.stack([np.full(ray_count, -1.0), y], 1), np.zeros(ray_count), wl)
+    arc = {"arcs": np.array([[5.0, 0.0, 3 * math.pi / 4, 5 * math.pi / 4, 5.0]]),
+           "mat_in": 1, "mat_out": 0}
+    target = {"segments": np.array([[6.0, -5.0, 6.0, 5.0]])}
+    return _scene2d(f"arc_lens_2d_{ray_count}rays", src, 3, optical_arcs=[arc],
+                    target_segments=[target])
+
+
+def mixed_2d(ray_count=2000, seed=7):
+    """Segments AND arcs, every category, mirrors and TIR: a plano-convex acrylic lens (flat
+    segment face + arc face, negative-radius arc included), a mirror segment, a stop arc, a
+    target segment; random fan of rays with six wavelengths; 6 iterations."""
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-0.45, 0.45, ray_count)
+    starts = np.stack([np.full(ray_count, -3.0), rng.uniform(-0.3, 0.3, ray_count)], 1)
+    wl = np.asarray(RAINBOW_6)[rng.integers(0, 6, ray_count)]
+    src = rays_2d(starts, ang, wl)
+    flat = {"segments": np.array([[0.0, 1.2, 0.0, -1.2]]), "mat_in": 1, "mat_out": 0}
+    # convex back face: circle centre (-1.0, 0), radius 2 => apex at x = 1; normal outward
+    back = {"arcs": np.array([[-1.0, 0.0, -0.6435, 0.6435, 2.0]]), "mat_in": 1, "mat_out": 0}
+    # a negative-radius arc (normal flipped) acting as a second element further right
+    meniscus = {"arcs": np.array([[5.5, 0.0, 2.6, -2.6, -2.5]]), "mat_in": 0, "mat_out": 1}
+    mirror = {"segments": np.array([[-1.0, 1.6, 4.0, 1.9]]), "mat_in": 2, "mat_out": 0}
+    stop = {"arcs": np.array([[2.0, -2.2, 0.3, 2.8, 0.5]])}
+    target = {"segments": np.array([[9.0, -6.0, 9.0, 6.0]])}
+    scene = _scene2d(f"mixed_2d_{ray_count}rays", src, 6,
+                     optical_segments=[flat, mirror], optical_arcs=[back, meniscus],
+                     stop_arcs=[stop], target_segments=[target])
+    scene["materials"] = ["vacuum", "acrylic", "reflective"]
+    return scene
+
+
+def build_engine_2d(scene, eps=None, parametric=False, **engine_kwargs):
+    """Instantiate a 2D scene through the public API (ManualSegmentBoundary / ManualArcBoundary
+    / OpticalSystem2D / OpticalEngine + StandardReaction), as dev/single_pass.py:34-72 does.
+    Returns (engine, boundary parameter tensors, source).  With parametric=True the optical
+    boundaries' geometry tensors are leaf tensors with requires_grad (gradient tests)."""
+    import torch
+    from . import boundaries, engine as eng, materials, operation, sources
+
+    params = []
+
+    def make(entries, kind):
+        out = []
+        for e in entries:
+            if kind == "segments":
+                b = boundaries.ManualSegmentBoundary()
+                data = boundaries.as_field(e["segments"]).reshape(-1, 4)
+                names = ("x_start", "y_start", "x_end", "y_end")
+            else:
+                b = boundaries.ManualArcBoundary()
+                data = boundaries.as_field(e["arcs"]).reshape(-1, 5)
+                names = ("x_center", "y_center", "angle_start", "angle_end", "radius")
+            for i, k in enumerate(names):
+                col = data[:, i].contiguous()
+                if parametric and "mat_in" in e:
+                    col = col.clone().requires_grad_(True)
+                    params.append(col)
+                b[k] = col
+            if "mat_in" in e:
+                eng.annotation_helper(b, "mat_in", e["mat_in"], names[0], dtype=torch.int64)
+                eng.annotation_helper(b, "mat_out", e["mat_out"], names[0], dtype=torch.int64)
+            out.append(b)
+        return out
+
+    src = sources.ManualSource(2)
+    src.feed(scene["sources"])
+    system = eng.OpticalSystem2D(**(eps or {}))
+    system.optical_segments = make(scene["optical_segments"], "segments")
+    system.optical_arcs = make(scene["optical_arcs"], "arcs")
+    system.stop_segments = make(scene["stop_segments"], "segments")
+    system.stop_arcs = make(scene["stop_arcs"], "arcs")
+    system.target_segments = make(scene["target_segments"], "segments")
+    system.target_arcs = make(scene["target_arcs"], "arcs")
+    system.sources = [src]
+    system.materials = [{"n": materials.BY_NAME[name]} for name in scene["materials"]]
+    system.update()
+    engine = eng.OpticalEngine(2, [operation.StandardReaction()], **engine_kwargs)
+    engine.optical_system = system
+    engine.validate_system()
+    return engine, params, src
+
+
 def surface_vertices(surface):
     """zero + parameter * vector (tfrt/boundaries.py:1081-1083)."""
     return surface["zero_points"] + surface["parameters"][:, None] * surface["vectors"]

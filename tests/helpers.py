@@ -137,3 +137,52 @@ def compare_sets(engine_set, oracle_set, exempt, fields, slot_field="slot", engi
         o = oracle_set[f].detach().numpy()[okeep]
         worst = max(worst, rel_err(e, o))
     return worst
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D
+
+SEG_FIELDS = ("x_start", "y_start", "x_end", "y_end")
+ARC_FIELDS = ("x_center", "y_center", "angle_start", "angle_end", "radius")
+RAY_FIELDS_2D = ("x_start", "y_start", "x_end", "y_end")
+
+
+def oracle2d_from_scene(scene, requires_grad=False, eps=EPS, **engine_kwargs):
+    """(OracleEngine2D, parameter tensors) for a scenes.*_2d scene; inputs rounded through fp32.
+    Parameters (when requires_grad) are the geometry columns of the optical boundaries, in the
+    order scenes.build_engine_2d(parametric=True) returns them."""
+    from oracle import engine2d as oe2
+    src = {k: torch.from_numpy(np.ascontiguousarray(f32_round(v))) for k, v in scene["sources"].items()}
+    src["slot"] = torch.arange(src["x_start"].shape[0], dtype=torch.float64)
+    params = []
+
+    def make(entries, kind):
+        out = []
+        for e in entries:
+            names = SEG_FIELDS if kind == "segments" else ARC_FIELDS
+            data = f32_round(np.asarray(e[kind]).reshape(-1, len(names)))
+            d = {}
+            for i, k in enumerate(names):
+                col = torch.from_numpy(np.ascontiguousarray(data[:, i]))
+                if requires_grad and "mat_in" in e:
+                    col = col.clone().requires_grad_(True)
+                    params.append(col)
+                d[k] = col
+            if "mat_in" in e:
+                n = data.shape[0]
+                d["mat_in"] = torch.full((n,), e["mat_in"], dtype=torch.int64)
+                d["mat_out"] = torch.full((n,), e["mat_out"], dtype=torch.int64)
+            out.append(d)
+        return out
+
+    # same creation order as scenes.build_engine_2d: optical segments, then optical arcs
+    opt_seg = make(scene["optical_segments"], "segments")
+    opt_arc = make(scene["optical_arcs"], "arcs")
+    system = oe2.OracleSystem2D(
+        [src], opt_seg, opt_arc, make(scene["stop_segments"], "segments"),
+        make(scene["stop_arcs"], "arcs"), make(scene["target_segments"], "segments"),
+        make(scene["target_arcs"], "arcs"),
+        materials=[{"n": om.BY_NAME[name]} for name in scene["materials"]], **eps)
+    engine = oe2.OracleEngine2D(system, simple_ray_inheritance=("wavelength", "slot"),
+                                **engine_kwargs)
+    return engine, params
