@@ -41,6 +41,7 @@ UNIT = "tests/s"
 
 CONFIGS = {
     # name: (scene factory kwargs, has backward)
+    "cfg1": dict(factory="config1", kwargs={}, backward=False),   # 2D, launch-latency bound
     "cfg2": dict(factory="config2", kwargs={}, backward=False),
     "cfg3": dict(factory="config3", kwargs={}, backward=True),
     "cfg4": dict(factory="config4", kwargs={}, backward=False),
@@ -144,6 +145,13 @@ def oracle_step(scene, n_rays, backward, threads):
     import helpers
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
+    if scene["dimension"] == 2:
+        sub = dict(scene)
+        sub["sources"] = {k: v[:n_rays] for k, v in scene["sources"].items()}
+        eng, _ = helpers.oracle2d_from_scene(sub, compile_active_rays=False)
+        eng.ray_trace(scene["max_iterations"])
+        dt = time.perf_counter() - t0
+        return dt, float(sum(eng.live_counts)) * scene_triangles(scene), eng.live_counts
     eng, params = helpers.oracle_from_scene(scene, ray_slice=slice(0, n_rays),
                                             requires_grad=backward, compile_active_rays=False)
     # cache-sized (triangles x ray-chunk) temporaries: 4x faster than the 256 MB default on the
@@ -209,7 +217,14 @@ def run_reference(args):
 
 
 def scene_triangles(scene):
+    """Boundary count of the merged set: triangles (3D) or segments + arcs (2D)."""
     from tensorflowraytrace_b200 import scenes
+    if scene["dimension"] == 2:
+        n = 0
+        for kind in ("optical", "stop", "target"):
+            n += sum(np.asarray(e["segments"]).reshape(-1, 4).shape[0] for e in scene[f"{kind}_segments"])
+            n += sum(np.asarray(e["arcs"]).reshape(-1, 5).shape[0] for e in scene[f"{kind}_arcs"])
+        return n
     return scenes.triangle_count(scene)
 
 
@@ -258,8 +273,12 @@ def run_ours(args):
 
     scene_local = dict(scene)
     scene_local["sources"] = {k: v[lo:hi] for k, v in scene["sources"].items()}
-    engine, params, src = scenes.build_engine(
-        scene_local, compile_active_rays=False, compile_finished_rays=True)
+    if scene["dimension"] == 2:
+        engine, params, src = scenes.build_engine_2d(
+            scene_local, compile_active_rays=False, compile_finished_rays=True)
+    else:
+        engine, params, src = scenes.build_engine(
+            scene_local, compile_active_rays=False, compile_finished_rays=True)
     errf = scenes.imaging_error(scene) if backward else None
     opt = optimizer.SGD_Optimizer(engine, params, errf, K) if backward else None
     acc = [None] * len(params)
@@ -368,6 +387,14 @@ def run_ours(args):
                            "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
             "peak_ffma2_tflops": fp32_peak_packed / 1e12,
         }
+    elif scene["dimension"] == 2:
+        # the 2D path is one launch per trace: launch-latency bound, no roofline fraction
+        line["roofline"] = {
+            "kernel": "k_trace2d_forward", "bound": "latency", "achieved": None, "peak": None,
+            "unit": "us/trace", "frac": None, "traffic": None,
+            "us_per_trace": 1e6 * fwd_seconds / args.steps,
+            "note": "config 1 (1 000 rays x 3 segments x 3 iterations) is launch-latency bound "
+                    "(SURVEY.md 8(d)): one kernel launch per trace, fp64 arithmetic"}
     if backward:
         # the backward leg (loss + K2 + K3 backward + all-reduce) timed on its own with CUDA
         # events around autograd, forward outside the timed span
