@@ -373,7 +373,10 @@ def run_ours(args):
         line["roofline"] = {
             "kernel": "k_intersect3d", "bound": "fp32_fma", "achieved": achieved,
             "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
-            "traffic": None,
+            "traffic": intersect_traffic(n_local),
+            "traffic_source": "ncu dram__bytes_read+write of a 2 097 152-ray launch "
+                              "(profiles/r1_intersect3d_traffic.json) scaled per ray to this "
+                              "launch; DRAM is 0.03 % of peak, the kernel is FP32-issue bound",
             "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
             "share_of_step": k_ms * 1e-3 / seconds,
             "flop_per_test": FLOP_PER_TEST,
@@ -446,6 +449,15 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def intersect_traffic(n_rays):
+    """DRAM bytes per k_intersect3d launch over n_rays rays, from the committed ncu capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_intersect3d_traffic.json")))
+        return float(t["dram_bytes_per_ray_per_launch"]) * float(n_rays)
+    except Exception:
+        return None
 
 
 def measured_peaks():

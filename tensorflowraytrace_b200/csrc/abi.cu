@@ -144,6 +144,43 @@ __global__ void __launch_bounds__(256) k_ffma_mixed(int iters, float seed, float
     if (s == 123.456f) sink[0] = s;
 }
 
+// Issue-mix probe: 8 FFMA2 chains + NALU integer LOP3/IADD ops + NXU MUFU.RCP per round.  Only
+// the FFMA2 flops are counted, so the result tells how much of the FMA pipe survives when the
+// other pipes are fed from the same issue port (the search kernel's mix is about 8 : 3 : 1).
+template <int NALU, int NXU>
+__global__ void __launch_bounds__(256) k_issue_mix(int iters, float seed, float *sink) {
+    float2 a[8], b = make_float2(seed, seed * 1.5f), c = make_float2(seed * 0.5f, seed * 0.25f);
+    uint32_t q[NALU > 0 ? NALU : 1];
+    float x[NXU > 0 ? NXU : 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(seed + i, seed - i);
+#pragma unroll
+    for (int i = 0; i < (NALU > 0 ? NALU : 1); ++i)
+        q[i] = __float_as_uint(seed) + i * 77u + threadIdx.x * 2654435761u;   // per-lane values
+#pragma unroll
+    for (int i = 0; i < (NXU > 0 ? NXU : 1); ++i) x[i] = seed + 0.37f * i + 0.001f * threadIdx.x;
+    const uint32_t m1 = __float_as_uint(seed * 3.f) ^ threadIdx.x, m2 = __float_as_uint(seed * 7.f) + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = __ffma2_rn(a[i], b, c);
+                if (i < NALU) q[i] = ((q[i] | m1) & 0x80000000u) ^ (q[i] + m2);   // LOP3 + IADD
+                if (i < NXU) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+#pragma unroll
+    for (int i = 0; i < (NALU > 0 ? NALU : 1); ++i) s += __uint_as_float(q[i]);
+#pragma unroll
+    for (int i = 0; i < (NXU > 0 ? NXU : 1); ++i) s += x[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 
 extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *stream) {
@@ -165,6 +202,14 @@ extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *
             k_ffma_mixed<8><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
         else if (packed == 3)
             k_ffma_mixed<4><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
+        else if (packed == 4)
+            k_issue_mix<2, 0><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);   // 8 : 4 ALU
+        else if (packed == 5)
+            k_issue_mix<0, 1><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);   // 8 : 1 XU
+        else if (packed == 6)
+            k_issue_mix<2, 1><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);   // 8 : 4 : 1
+        else if (packed == 7)
+            k_issue_mix<4, 0><<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);   // 8 : 8 ALU
         else if (packed)
             k_ffma_packed<<<blocks, threads, 0, st>>>(iters, 1.0001f, sink);
         else
@@ -176,7 +221,7 @@ extern "C" int tfrt_fp32_peak(int packed, int iters, double *flops_per_s, void *
         if (rep > 0 && ms < best_ms) best_ms = ms;
     }
     // lane-FMAs per thread per outer iteration: 64 scalar, 128 packed, 128 + 8*NS mixed
-    const double per_iter = packed == 2 ? 192.0 : packed == 3 ? 160.0 : packed ? 128.0 : 64.0;
+    const double per_iter = packed == 2 ? 192.0 : packed == 3 ? 160.0 : packed ? 128.0 : 64.0;   // modes >= 4 count their FFMA2 only
     const double fmas = (double)blocks * threads * (double)iters * per_iter;
     *flops_per_s = 2.0 * fmas / (best_ms * 1e-3);
     cudaEventDestroy(e0);

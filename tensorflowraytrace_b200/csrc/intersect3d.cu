@@ -20,10 +20,29 @@
 //    (key << 32 | index) -- same tie rule -- so small ray counts still fill 148 SMs.
 #include "common.cuh"
 
+// Tunables.  The defaults are the measured best of the variants timed by tools/k1_variants.sh
+// (profiles/r1_k1_tuning.md); tools/k1_bench.cu compiles the others with -D.
+#ifndef TFRT_K1_THREADS
+#define TFRT_K1_THREADS 128
+#endif
+#ifndef TFRT_K1_STAGES
+#define TFRT_K1_STAGES 3
+#endif
+#ifndef TFRT_K1_UNROLL
+#define TFRT_K1_UNROLL 2
+#endif
+#ifndef TFRT_K1_FORCE_R2    // 0: choose rays per thread from the ray count
+#define TFRT_K1_FORCE_R2 0
+#endif
+#ifndef TFRT_K1_MINBLOCKS   // 4 CTAs of 128 threads per SM <=> at most 128 registers
+#define TFRT_K1_MINBLOCKS 4
+#endif
+
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kStages = 3;
+constexpr int kThreads = TFRT_K1_THREADS;
+constexpr int kStages = TFRT_K1_STAGES;
+constexpr int kUnroll = TFRT_K1_UNROLL;
 
 struct __align__(16) IntersectSmem {
     float4 tile[kStages][TFRT_TILE_TRIS * 3];
@@ -35,7 +54,7 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 template <int R2>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (R2 >= 4 ? TFRT_K1_MINBLOCKS : 1))
 k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const float *__restrict__ sz, const float *__restrict__ ex,
               const float *__restrict__ ey, const float *__restrict__ ez,
@@ -121,7 +140,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         const float4 *__restrict__ tile = sm.tile[s];
         const int tri0 = (tile_begin + it) * TFRT_TILE_TRIS;
 
-#pragma unroll 2
+#pragma unroll kUnroll
         for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
             const float4 q0 = tile[j * 3 + 0];
             const float4 q1 = tile[j * 3 + 1];
@@ -239,13 +258,37 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
         TFRT_CHECK_CUDA(cudaGetDevice(&dev));
         TFRT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // rays per thread: 8 when that still yields >= 2 waves of CTAs, else 4, else 2
-    int r2 = 4;
-    const long long want = 2LL * num_sms * 4;   // ~4 resident CTAs per SM, two waves
-    while (r2 > 1 && tfrt_div_up(n_upper, kThreads * 2 * r2) < want) r2 >>= 1;
+    // Grid shape: rays per thread (2*R2) and the number of triangle-range splits are chosen
+    // together so that the CTA count fills whole waves of resident CTAs (148 SMs x CTAs/SM):
+    // a 1 M-ray trace as 2 048 CTAs of 4 rays/thread is 3.46 waves (13 % idle tail), as
+    // 1 024 x 4 splits of 8 rays/thread it is 6.92 waves (1 %).  Score = wave efficiency x a
+    // per-shape factor (fewer rays per thread re-read the tile more often; every split repeats
+    // the ray load and ring prologue).
+    int r2 = 4, splits = 1;
+    {
+        const int cand_r2[3] = {4, 2, 1};
+        const int occ[3] = {4, 5, 6};                 // resident CTAs per SM (registers / smem)
+        const double shape[3] = {1.0, 0.96, 0.88};
+        double best_score = -1.0;
+        for (int c = 0; c < 3; ++c) {
+            const int rb = tfrt_div_up(n_upper, kThreads * 2 * cand_r2[c]);
+            const int max_splits = n_tiles < 16 ? n_tiles : 16;
+            for (int sp = 1; sp <= max_splits; ++sp) {
+                const int tps = tfrt_div_up(n_tiles, sp);
+                const int real = tfrt_div_up(n_tiles, tps);
+                if (real != sp) continue;
+                const double waves = (double)rb * sp / ((double)num_sms * occ[c]);
+                const double eff = waves / (double)(long long)(waves + 0.999999);
+                const double score = eff * shape[c] * ((double)tps / (tps + 0.35)) *
+                                     (sp > 1 ? 0.995 : 1.0);
+                if (score > best_score) { best_score = score; r2 = cand_r2[c]; splits = sp; }
+            }
+        }
+    }
+#if TFRT_K1_FORCE_R2
+    r2 = TFRT_K1_FORCE_R2;
+#endif
     const int ray_blocks = tfrt_div_up(n_upper, kThreads * 2 * r2);
-    int splits = 1;
-    if (ray_blocks < want) { long long sp = (want + ray_blocks - 1) / ray_blocks; splits = (int)(sp < n_tiles ? sp : n_tiles); }
     const int tiles_per_split = tfrt_div_up(n_tiles, splits);
     splits = tfrt_div_up(n_tiles, tiles_per_split);
     const int use_atomic = splits > 1;
@@ -270,9 +313,13 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
             use_atomic, dir_mode);  \
     } while (0)
     const bool timed = tfrt_profile_begin(stream);
+#if TFRT_K1_FORCE_R2
+    TFRT_LAUNCH(TFRT_K1_FORCE_R2);
+#else
     if (r2 == 4) TFRT_LAUNCH(4);
     else if (r2 == 2) TFRT_LAUNCH(2);
     else TFRT_LAUNCH(1);
+#endif
 #undef TFRT_LAUNCH
     if (timed) tfrt_profile_end(stream);
     tfrt_note_launch(1);

@@ -699,10 +699,12 @@ class OpticalEngine:
         optical = system._amalgamated_optical
         kw = {}
         if reaction.refractive_index_type == "index":
-            kw.update(mat_in=optical["mat_in"], mat_out=optical["mat_out"],
+            none = torch.zeros(0, dtype=torch.int32, device=dev)
+            kw.update(mat_in=optical.get("mat_in", none), mat_out=optical.get("mat_out", none),
                       materials=system.material_table(dev), n_materials=len(system.materials))
         else:
-            kw.update(n_in=optical["n_in"], n_out=optical["n_out"])
+            none = torch.zeros(0, dtype=torch.float32, device=dev)
+            kw.update(n_in=optical.get("n_in", none), n_out=optical.get("n_out", none))
         compile_sets = set()
         if self.compile_active_rays:
             compile_sets.add("active")
@@ -786,30 +788,70 @@ class OpticalEngine:
         tr = plan["trace"]
         self.last_trace = tr
 
-        status = tr.tape_status[:, :n]
-        is_arc = tr.tape_hit[:, :n] < -1
         both = seg is not None and arc is not None
-        sets = {"active": ([], []), "stopped": ([], []), "finished": ([], []), "dead": ([], [])}
         code = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}
-        if not both:
-            # one geometry: the live list stays in source order, so every set is the row-major
-            # (iteration, slot) list of its status code
-            for name, c in code.items():
-                it, slot = torch.nonzero(status == c, as_tuple=True)
-                sets[name] = ([it], [slot])
-        else:
-            order = torch.arange(n, device=dev)
-            for k in range(max_iterations):
-                if order.numel() == 0:
-                    break
-                st, ka = status[k, order], is_arc[k, order]
+        sets = {}
+        if n * max_iterations <= (1 << 20):
+            # small traces are latency bound: ONE device->host copy of the status / hit tape,
+            # the ordering on the host (NumPy), one host->device copy of the gather indices
+            import numpy as np
+            packed = torch.cat([tr.tape_status[:, :n].to(torch.int32), tr.tape_hit[:, :n]]).cpu().numpy()
+            st_h, arc_h = packed[:max_iterations], packed[max_iterations:] < -1
+            if not both:
                 for name, c in code.items():
-                    parts = [order[st == c]] if name == "dead" else \
-                        [order[(st == c) & ~ka], order[(st == c) & ka]]
-                    for part in parts:
-                        sets[name][0].append(torch.full_like(part, k))
-                        sets[name][1].append(part)
-                order = torch.cat([order[(st == 0) & ~ka], order[(st == 0) & ka]])
+                    sets[name] = np.nonzero(st_h == c)
+            else:
+                acc = {name: ([], []) for name in code}
+                order = np.arange(n)
+                for k in range(max_iterations):
+                    if order.size == 0:
+                        break
+                    st, ka = st_h[k, order], arc_h[k, order]
+                    for name, c in code.items():
+                        parts = [order[st == c]] if name == "dead" else \
+                            [order[(st == c) & ~ka], order[(st == c) & ka]]
+                        for part in parts:
+                            acc[name][0].append(np.full(part.shape, k, dtype=np.int64))
+                            acc[name][1].append(part)
+                    order = np.concatenate([order[(st == 0) & ~ka], order[(st == 0) & ka]])
+                for name in code:
+                    sets[name] = (np.concatenate(acc[name][0]) if acc[name][0] else np.zeros(0, np.int64),
+                                  np.concatenate(acc[name][1]) if acc[name][1] else np.zeros(0, np.int64))
+            names = [nm for nm in code]
+            sizes = [sets[nm][0].shape[0] for nm in names]
+            flat = np.concatenate([np.concatenate([sets[nm][0], sets[nm][1]]) for nm in names]) \
+                if sum(sizes) else np.zeros(0, np.int64)
+            flat_dev = torch.from_numpy(flat.astype(np.int64)).to(dev)
+            off = 0
+            for nm, sz in zip(names, sizes):
+                sets[nm] = (flat_dev[off:off + sz], flat_dev[off + sz:off + 2 * sz])
+                off += 2 * sz
+        else:
+            status = tr.tape_status[:, :n]
+            is_arc = tr.tape_hit[:, :n] < -1
+            if not both:
+                # one geometry: the live list stays in source order, so every set is the
+                # row-major (iteration, slot) list of its status code
+                for name, c in code.items():
+                    sets[name] = torch.nonzero(status == c, as_tuple=True)
+            else:
+                acc = {name: ([], []) for name in code}
+                order = torch.arange(n, device=dev)
+                for k in range(max_iterations):
+                    if order.numel() == 0:
+                        break
+                    st, ka = status[k, order], is_arc[k, order]
+                    for name, c in code.items():
+                        parts = [order[st == c]] if name == "dead" else \
+                            [order[(st == c) & ~ka], order[(st == c) & ka]]
+                        for part in parts:
+                            acc[name][0].append(torch.full_like(part, k))
+                            acc[name][1].append(part)
+                    order = torch.cat([order[(st == 0) & ~ka], order[(st == 0) & ka]])
+                empty = torch.zeros(0, dtype=torch.long, device=dev)
+                for name in code:
+                    sets[name] = (torch.cat(acc[name][0]) if acc[name][0] else empty,
+                                  torch.cat(acc[name][1]) if acc[name][1] else empty)
 
         inherit = [f for f in src_fields if f not in kernels.RAY_FIELDS_2D]
         self.last_history_slots, self.last_history_iterations = {}, {}
@@ -819,8 +861,7 @@ class OpticalEngine:
                                   ("dead", self.compile_dead_rays, self._dead_rays)):
             if not flag:
                 continue
-            it = torch.cat(sets[name][0]) if sets[name][0] else torch.zeros(0, dtype=torch.long, device=dev)
-            slot = torch.cat(sets[name][1]) if sets[name][1] else torch.zeros(0, dtype=torch.long, device=dev)
+            it, slot = sets[name]
             rays = tape[it, :, slot]                              # (n_set, 4)
             out = {k: rays[:, i] for i, k in enumerate(kernels.RAY_FIELDS_2D)}
             if name == "dead" and bool(self.dead_ray_length):

@@ -349,9 +349,10 @@ class Trace2D:
         self.index_mode = 1 if materials is not None else 0
         self.materials = materials
         n1 = max(N, 1)
-        self.tape_f = torch.zeros((K, 4, n1), dtype=torch.float32, device=dev)
-        self.tape_d = torch.zeros((K, 2, n1), dtype=torch.float64, device=dev)
-        self.tape_hit = torch.full((K, n1), -1, dtype=torch.int32, device=dev)
+        # entries of slots that are not live at an iteration are never read (status 255)
+        self.tape_f = torch.empty((K, 4, n1), dtype=torch.float32, device=dev)
+        self.tape_d = torch.empty((K, 2, n1), dtype=torch.float64, device=dev)
+        self.tape_hit = torch.empty((K, n1), dtype=torch.int32, device=dev)
         self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
         self.live = torch.empty((K,), dtype=torch.int32, device=dev)
         self._live_host = None
