@@ -512,6 +512,7 @@ int check2d(const TfrtTrace2DArgs *a, const char *who) {
                  "%s: category counts exceed the boundary counts", who);
     TFRT_REQUIRE(a->tape_f && a->tape_d && a->tape_hit && a->tape_status && a->live_counts,
                  "%s: null tape pointer", who);
+    if (a->n_rays == 0) return 0;   // nothing is dereferenced
     if (a->index_mode) {
         TFRT_REQUIRE(a->materials && a->src[4], "%s: index mode needs materials and wavelength", who);
         TFRT_REQUIRE((a->n_seg_optical == 0 || (a->seg_mat_in && a->seg_mat_out)) &&

@@ -385,7 +385,7 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
     TFRT_REQUIRE(a->packed && a->category && a->hit && a->tape_f && a->tape_tri &&
                      a->tape_status && a->tape_outpos && a->live && a->block_counts && a->counters,
                  "tfrt_trace3d_forward: null workspace pointer");
-    TFRT_REQUIRE(a->n_optical == 0 ||
+    TFRT_REQUIRE(a->n_optical == 0 || a->n_rays == 0 ||
                      (a->index_mode ? (a->materials && a->mat_in && a->mat_out && a->src[6])
                                     : (a->n_in && a->n_out)),
                  "tfrt_trace3d_forward: material inputs missing for index_mode=%d", a->index_mode);

@@ -36,10 +36,15 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
     for s in scene["surfaces"]:
         p = torch.from_numpy(rnd(s["parameters"])).clone().requires_grad_(requires_grad)
         params.append(p)
-        verts = ob.parametric_vertices(torch.from_numpy(rnd(s["zero_points"])),
-                                       torch.from_numpy(rnd(s["vectors"])), p)
-        if round_inputs and not requires_grad:
-            verts = torch.from_numpy(f32_round(verts.detach().numpy()))
+        zero = torch.from_numpy(rnd(s["zero_points"]))
+        vec = torch.from_numpy(rnd(s["vectors"]))
+        verts = ob.parametric_vertices(zero, vec, p)
+        if round_inputs:
+            # The CUDA path stores vertices as fp32 fields, formed in fp32 (one multiply, one
+            # add, no contraction).  Give the oracle exactly those values -- with a
+            # straight-through gradient, so autograd still reaches the parameters.
+            v32 = (zero.float() + p.detach().float().reshape(-1, 1) * vec.float()).double()
+            verts = verts + (v32 - verts.detach())
         fields = ob.fields_from_vertices(verts, s["faces"], s.get("vertex_update_map"))
         F = s["faces"].shape[0]
         fields["mat_in"] = torch.full((F,), s["mat_in"], dtype=torch.int64)
