@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TFRT_B200_ABI_VERSION 2
+#define TFRT_B200_ABI_VERSION 3
 
 /* ray status after one projection (tfrt/engine.py:2063-2111) */
 #define TFRT_STATUS_ACTIVE 0   /* hit an OPTICAL boundary: reacts and continues */
@@ -184,6 +184,11 @@ typedef struct {
     float *g_norm_out;
     float *g_src[6];
     float dead_ray_length;    /* value used when materialising dead rays; < 0 => unchanged */
+    int32_t n_grad_tri;       /* only the first n_grad_tri merged triangles receive cotangents
+                                 (<= 0: all).  The merged order is optical -> stop -> target and
+                                 stop / target boundaries are rarely differentiable
+                                 (tfrt/engine.py:971-1018); skipping them removes the atomics of
+                                 every finished ray into the few target triangles. */
 } TfrtTrace3DBwdArgs;
 
 int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_host,

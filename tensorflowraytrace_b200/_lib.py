@@ -64,6 +64,7 @@ class TfrtTrace3DBwdArgs(ctypes.Structure):
         ("g_norm_out", c_void_p),
         ("g_src", c_void_p * 6),
         ("dead_ray_length", ctypes.c_float),
+        ("n_grad_tri", ctypes.c_int32),
     ]
 
 
@@ -115,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STRUCT_MIRRORS = (TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs, TfrtTrace2DArgs)
 
 _lib = None

@@ -81,7 +81,8 @@ class TraceFunction(torch.autograd.Function):
                 g_hist[name] = g.contiguous()
         want_src = ctx.needs_input_grad[2]
         g_tri, g_norm, g_src = tr.backward(g_hist, want_src_grad=want_src,
-                                           dead_ray_length=plan.dead_ray_length)
+                                           dead_ray_length=plan.dead_ray_length,
+                                           n_grad_tri=plan.n_grad_tri)
         g_src_full = None
         if want_src:
             g_src_full = torch.zeros(ctx.src_shape, dtype=torch.float32, device=g_tri.device)
@@ -108,6 +109,7 @@ class TracePlan:
         self.dead_ray_length = kw.get("dead_ray_length")
         self.compile = set(kw["compile"])
         self.packed = kw.get("packed")   # tfrt_pack_triangles output (built when None)
+        self.n_grad_tri = kw.get("n_grad_tri", 0)   # leading triangles that need cotangents
         self.trace = None
         self.slots, self.iters = {}, {}
 

@@ -27,7 +27,7 @@ namespace {
 constexpr int kBwdThreads = 256;
 
 struct BwdParams {
-    int n_rays, k, is_last, index_mode;
+    int n_rays, k, is_last, index_mode, n_grad_tri;
     int n_live;
     int active_offset;          // position of this iteration's first ray in the active history
     double new_ray_length, dead_ray_length;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                 gS[c] = gSd[c] + (1.0 - t) * proj;
                 gE[c] = t * proj;
             }
-            contributes = true;
+            contributes = tri < P.n_grad_tri;
         }
         for (int c = 0; c < 3; ++c) {
             P.g_ray[c][slot] = (float)gS[c];
@@ -307,6 +307,7 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         BwdParams P;
         P.n_rays = N; P.k = k; P.is_last = (k == K - 1); P.index_mode = a->index_mode;
         P.n_live = n_live;
+        P.n_grad_tri = b->n_grad_tri > 0 ? b->n_grad_tri : T;
         P.active_offset = (int)active_before;
         P.new_ray_length = a->new_ray_length;
         P.dead_ray_length = b->dead_ray_length;

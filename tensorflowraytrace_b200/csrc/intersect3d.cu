@@ -18,6 +18,9 @@
 //    index on exact ties (the behaviour of argmin in the reference's CPU kernels);
 //  * optional split of the triangle range over blockIdx.y, merged with a 64-bit atomicMin on
 //    (key << 32 | index) -- same tie rule -- so small ray counts still fill 148 SMs.
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
 
 // Tunables.  The defaults are the measured best of the variants timed by tools/k1_variants.sh
@@ -60,23 +63,22 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const float *__restrict__ ey, const float *__restrict__ ez,
               const int32_t *__restrict__ live, const int32_t *__restrict__ n_live_ptr,
               int n_live_static, const float4 *__restrict__ packed, int n_tiles,
-              int tiles_per_split, float intersect_eps, float ray_start_eps, float w_one,
-              unsigned long long *__restrict__ hit, int use_atomic, int dir_mode) {
+              int tiles_per_split, int splits, float intersect_eps, float ray_start_eps,
+              float w_one, unsigned long long *__restrict__ hit, int use_atomic, int dir_mode,
+              unsigned int *__restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IntersectSmem &sm = *reinterpret_cast<IntersectSmem *>(smem_raw);
+    __shared__ int s_item;
 
+    // Persistent CTAs pull work items (ray block x triangle split) from a global counter, so
+    // the tail of a launch is one item, not one wave, whatever the live count turns out to be
+    // (it is only known on the device).  Consecutive items are different ray blocks of the
+    // same split: neighbouring CTAs stream the same triangle tiles out of L2.
     const int n_live = n_live_ptr ? *n_live_ptr : n_live_static;
     const int rays_per_cta = kThreads * 2 * R2;
-    const int base = blockIdx.x * rays_per_cta;
-    if (base >= n_live) return;
-
-    const int tile_begin = blockIdx.y * tiles_per_split;
-    const int tile_end = min(n_tiles, tile_begin + tiles_per_split);
-    const int my_tiles = tile_end - tile_begin;
-    if (my_tiles <= 0) return;
-
+    const int ray_blocks = (n_live + rays_per_cta - 1) / rays_per_cta;
+    const int total_items = ray_blocks * splits;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
 
     if (tid == 0) {
 #pragma unroll
@@ -86,156 +88,166 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         }
         mbar_fence_init();
     }
-    __syncthreads();
+    uint32_t seq = 0;   // tiles this CTA has pushed through the ring so far (stage / parity)
 
-    // producer prologue: fill the ring
-    if (tid == 0) {
-        const int pre = min(kStages, my_tiles);
-        for (int s = 0; s < pre; ++s) {
-            mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
-            bulk_g2s(sm.tile[s], packed + (size_t)(tile_begin + s) * TFRT_TILE_TRIS * 3,
-                     TFRT_TILE_BYTES, &sm.full[s]);
-        }
-    }
-
-    // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
-    float2 Ox[R2], Oy[R2], Oz[R2], Dx[R2], Dy[R2], Dz[R2];
-    uint32_t best[2 * R2];
-    int32_t bidx[2 * R2];
-#pragma unroll
-    for (int r = 0; r < R2; ++r) {
-        float o[2][3], d[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int p = base + (2 * r + h) * kThreads + tid;
-            if (p < n_live) {
-                const int slot = live ? live[p] : p;
-                const float ax = sx[slot], ay = sy[slot], az = sz[slot];
-                // dir_mode: the last three arrays hold the direction (end - start) itself, the
-                // form the trace loop keeps between iterations (no cancellation error)
-                d[h][0] = dir_mode ? ex[slot] : ex[slot] - ax;
-                d[h][1] = dir_mode ? ey[slot] : ey[slot] - ay;
-                d[h][2] = dir_mode ? ez[slot] : ez[slot] - az;
-                // shift the origin by ray_start_eps along the ray: t_shifted >= 0 <=> ray_u >= eps
-                o[h][0] = fmaf(ray_start_eps, d[h][0], ax);
-                o[h][1] = fmaf(ray_start_eps, d[h][1], ay);
-                o[h][2] = fmaf(ray_start_eps, d[h][2], az);
-            } else {  // padding lane: zero direction => det == 0 => never a hit
-                o[h][0] = o[h][1] = o[h][2] = 0.f;
-                d[h][0] = d[h][1] = d[h][2] = 0.f;
-            }
-            best[2 * r + h] = TFRT_NOHIT_KEY;
-            bidx[2 * r + h] = 0;
-        }
-        Ox[r] = f2(o[0][0], o[1][0]); Oy[r] = f2(o[0][1], o[1][1]); Oz[r] = f2(o[0][2], o[1][2]);
-        Dx[r] = f2(d[0][0], d[1][0]); Dy[r] = f2(d[0][1], d[1][1]); Dz[r] = f2(d[0][2], d[1][2]);
-    }
+    // producer: tile `g` of the CTA's running sequence <- global tile `tile`
+    auto issue = [&](uint32_t g, int tile) {
+        const int s = g % kStages;
+        if (g >= (uint32_t)kStages) mbar_wait(&sm.empty[s], ((g / kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
+        bulk_g2s(sm.tile[s], packed + (size_t)tile * TFRT_TILE_TRIS * 3, TFRT_TILE_BYTES,
+                 &sm.full[s]);
+    };
 
     const float2 one2 = f2(w_one, w_one);   // 1 + 3*size_eps (eps is folded into ad, bd)
 
-    for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % kStages;
-        const uint32_t parity = (uint32_t)((it / kStages) & 1);
-        mbar_wait(&sm.full[s], parity);
-        const float4 *__restrict__ tile = sm.tile[s];
-        const int tri0 = (tile_begin + it) * TFRT_TILE_TRIS;
+    for (;;) {
+        __syncthreads();                    // previous item done; barriers initialised
+        if (tid == 0) s_item = (int)atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        const int base = (item % ray_blocks) * rays_per_cta;
+        const int tile_begin = (item / ray_blocks) * tiles_per_split;
+        const int my_tiles = min(n_tiles, tile_begin + tiles_per_split) - tile_begin;
+
+        if (tid == 0) {                     // producer prologue: fill the ring
+            const int pre = min(kStages, my_tiles);
+            for (int i = 0; i < pre; ++i) issue(seq + i, tile_begin + i);
+        }
+
+        // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
+        float2 Ox[R2], Oy[R2], Oz[R2], Dx[R2], Dy[R2], Dz[R2];
+        uint32_t best[2 * R2];
+        int32_t bidx[2 * R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+            float o[2][3], d[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = base + (2 * r + h) * kThreads + tid;
+                if (p < n_live) {
+                    const int slot = live ? live[p] : p;
+                    const float ax = sx[slot], ay = sy[slot], az = sz[slot];
+                    // dir_mode: the last three arrays hold the direction (end - start) itself,
+                    // the form the trace loop keeps between iterations (no cancellation error)
+                    d[h][0] = dir_mode ? ex[slot] : ex[slot] - ax;
+                    d[h][1] = dir_mode ? ey[slot] : ey[slot] - ay;
+                    d[h][2] = dir_mode ? ez[slot] : ez[slot] - az;
+                    // shift the origin by ray_start_eps along the ray:
+                    // t_shifted >= 0 <=> ray_u >= eps
+                    o[h][0] = fmaf(ray_start_eps, d[h][0], ax);
+                    o[h][1] = fmaf(ray_start_eps, d[h][1], ay);
+                    o[h][2] = fmaf(ray_start_eps, d[h][2], az);
+                } else {  // padding lane: zero direction => det == 0 => never a hit
+                    o[h][0] = o[h][1] = o[h][2] = 0.f;
+                    d[h][0] = d[h][1] = d[h][2] = 0.f;
+                }
+                best[2 * r + h] = TFRT_NOHIT_KEY;
+                bidx[2 * r + h] = 0;
+            }
+            Ox[r] = f2(o[0][0], o[1][0]); Oy[r] = f2(o[0][1], o[1][1]); Oz[r] = f2(o[0][2], o[1][2]);
+            Dx[r] = f2(d[0][0], d[1][0]); Dy[r] = f2(d[0][1], d[1][1]); Dz[r] = f2(d[0][2], d[1][2]);
+        }
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const uint32_t g = seq + it;
+            const int s = g % kStages;
+            mbar_wait(&sm.full[s], (g / kStages) & 1);
+            const float4 *__restrict__ tile = sm.tile[s];
+            const int tri0 = (tile_begin + it) * TFRT_TILE_TRIS;
 
 #pragma unroll kUnroll
-        for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
-            const float4 q0 = tile[j * 3 + 0];
-            const float4 q1 = tile[j * 3 + 1];
-            const float4 q2 = tile[j * 3 + 2];
-            // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
-            const float2 nx = f2(q0.x, q0.x), ny = f2(q0.y, q0.y), nz = f2(q0.z, q0.z),
-                         nd = f2(q0.w, q0.w);
-            const float2 ax = f2(q1.x, q1.x), ay = f2(q1.y, q1.y), az = f2(q1.z, q1.z),
-                         ad = f2(q1.w, q1.w);
-            const float2 bx = f2(q2.x, q2.x), by = f2(q2.y, q2.y), bz = f2(q2.z, q2.z),
-                         bd = f2(q2.w, q2.w);
-            const int tri = tri0 + j;
-            uint32_t key[2 * R2];
-            bool cand = false;
-#pragma unroll
-            for (int r = 0; r < R2; ++r) {
-                float2 det = __fmul2_rn(nx, Dx[r]);
-                det = __ffma2_rn(ny, Dy[r], det);
-                det = __ffma2_rn(nz, Dz[r], det);
-                float2 tq = __ffma2_rn(neg2(nx), Ox[r], nd);
-                tq = __ffma2_rn(neg2(ny), Oy[r], tq);
-                tq = __ffma2_rn(neg2(nz), Oz[r], tq);
-                float2 inv;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
-                const float2 t = __fmul2_rn(tq, inv);
-                const float2 px = __ffma2_rn(t, Dx[r], Ox[r]);
-                const float2 py = __ffma2_rn(t, Dy[r], Oy[r]);
-                const float2 pz = __ffma2_rn(t, Dz[r], Oz[r]);
-                float2 u = __ffma2_rn(ax, px, ad);
-                u = __ffma2_rn(ay, py, u);
-                u = __ffma2_rn(az, pz, u);
-                float2 v = __ffma2_rn(bx, px, bd);
-                v = __ffma2_rn(by, py, v);
-                v = __ffma2_rn(bz, pz, v);
-                float2 w = __fadd2_rn(one2, neg2(u));
-                w = __fadd2_rn(w, neg2(v));
-                // sign bit of (u|v|w) set <=> outside the (inflated) triangle; fold into the key
-                key[2 * r] = __float_as_uint(t.x) |
-                             ((__float_as_uint(u.x) | __float_as_uint(v.x) |
-                               __float_as_uint(w.x)) & 0x80000000u);
-                key[2 * r + 1] = __float_as_uint(t.y) |
-                                 ((__float_as_uint(u.y) | __float_as_uint(v.y) |
-                                   __float_as_uint(w.y)) & 0x80000000u);
-                cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
-            }
-            // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so the
-            // common case pays one vote instead of predicated selects per test.
-            if (__any_sync(0xffffffffu, cand)) {
+            for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
+                const float4 q0 = tile[j * 3 + 0];
+                const float4 q1 = tile[j * 3 + 1];
+                const float4 q2 = tile[j * 3 + 2];
+                // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
+                const float2 nx = f2(q0.x, q0.x), ny = f2(q0.y, q0.y), nz = f2(q0.z, q0.z),
+                             nd = f2(q0.w, q0.w);
+                const float2 ax = f2(q1.x, q1.x), ay = f2(q1.y, q1.y), az = f2(q1.z, q1.z),
+                             ad = f2(q1.w, q1.w);
+                const float2 bx = f2(q2.x, q2.x), by = f2(q2.y, q2.y), bz = f2(q2.z, q2.z),
+                             bd = f2(q2.w, q2.w);
+                const int tri = tri0 + j;
+                uint32_t key[2 * R2];
+                bool cand = false;
 #pragma unroll
                 for (int r = 0; r < R2; ++r) {
-                    // |det| >= intersect_eps is the reference's safe-denominator validity
-                    // (tfrt/geometry.py:306); det is re-derived here to keep it out of the
-                    // common path's live registers.
                     float2 det = __fmul2_rn(nx, Dx[r]);
                     det = __ffma2_rn(ny, Dy[r], det);
                     det = __ffma2_rn(nz, Dz[r], det);
-                    if (key[2 * r] < best[2 * r] && fabsf(det.x) >= intersect_eps) {
-                        best[2 * r] = key[2 * r];
-                        bidx[2 * r] = tri;
-                    }
-                    if (key[2 * r + 1] < best[2 * r + 1] && fabsf(det.y) >= intersect_eps) {
-                        best[2 * r + 1] = key[2 * r + 1];
-                        bidx[2 * r + 1] = tri;
+                    float2 tq = __ffma2_rn(neg2(nx), Ox[r], nd);
+                    tq = __ffma2_rn(neg2(ny), Oy[r], tq);
+                    tq = __ffma2_rn(neg2(nz), Oz[r], tq);
+                    float2 inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
+                    const float2 t = __fmul2_rn(tq, inv);
+                    const float2 px = __ffma2_rn(t, Dx[r], Ox[r]);
+                    const float2 py = __ffma2_rn(t, Dy[r], Oy[r]);
+                    const float2 pz = __ffma2_rn(t, Dz[r], Oz[r]);
+                    float2 u = __ffma2_rn(ax, px, ad);
+                    u = __ffma2_rn(ay, py, u);
+                    u = __ffma2_rn(az, pz, u);
+                    float2 v = __ffma2_rn(bx, px, bd);
+                    v = __ffma2_rn(by, py, v);
+                    v = __ffma2_rn(bz, pz, v);
+                    float2 w = __fadd2_rn(one2, neg2(u));
+                    w = __fadd2_rn(w, neg2(v));
+                    // sign bit of (u|v|w) set <=> outside the (inflated) triangle: fold into key
+                    key[2 * r] = __float_as_uint(t.x) |
+                                 ((__float_as_uint(u.x) | __float_as_uint(v.x) |
+                                   __float_as_uint(w.x)) & 0x80000000u);
+                    key[2 * r + 1] = __float_as_uint(t.y) |
+                                     ((__float_as_uint(u.y) | __float_as_uint(v.y) |
+                                       __float_as_uint(w.y)) & 0x80000000u);
+                    cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
+                }
+                // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so the
+                // common case pays one vote instead of predicated selects per test.
+                if (__any_sync(0xffffffffu, cand)) {
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) {
+                        // |det| >= intersect_eps is the reference's safe-denominator validity
+                        // (tfrt/geometry.py:306); det is re-derived here to keep it out of the
+                        // common path's live registers.
+                        float2 det = __fmul2_rn(nx, Dx[r]);
+                        det = __ffma2_rn(ny, Dy[r], det);
+                        det = __ffma2_rn(nz, Dz[r], det);
+                        if (key[2 * r] < best[2 * r] && fabsf(det.x) >= intersect_eps) {
+                            best[2 * r] = key[2 * r];
+                            bidx[2 * r] = tri;
+                        }
+                        if (key[2 * r + 1] < best[2 * r + 1] && fabsf(det.y) >= intersect_eps) {
+                            best[2 * r + 1] = key[2 * r + 1];
+                            bidx[2 * r + 1] = tri;
+                        }
                     }
                 }
             }
-        }
 
-        // release the stage; the producer refills it with tile it + kStages
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
-        if (tid == 0 && it + kStages < my_tiles) {
-            mbar_wait(&sm.empty[s], parity);
-            mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
-            bulk_g2s(sm.tile[s],
-                     packed + (size_t)(tile_begin + it + kStages) * TFRT_TILE_TRIS * 3,
-                     TFRT_TILE_BYTES, &sm.full[s]);
+            // release the stage; the producer refills it with tile it + kStages
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+            if (tid == 0 && it + kStages < my_tiles) issue(g + kStages, tile_begin + it + kStages);
         }
-        (void)warp;
-    }
+        seq += (uint32_t)my_tiles;
 
-    // ---- epilogue: (key, index) per live position
+        // ---- epilogue: (key, index) per live position
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
+        for (int r = 0; r < R2; ++r) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int p = base + (2 * r + h) * kThreads + tid;
-            if (p < n_live) {
-                const unsigned long long packed_hit =
-                    ((unsigned long long)best[2 * r + h] << 32) | (uint32_t)bidx[2 * r + h];
-                if (use_atomic)
-                    atomicMin(&hit[p], packed_hit);
-                else
-                    hit[p] = packed_hit;
+            for (int h = 0; h < 2; ++h) {
+                const int p = base + (2 * r + h) * kThreads + tid;
+                if (p < n_live) {
+                    const unsigned long long packed_hit =
+                        ((unsigned long long)best[2 * r + h] << 32) | (uint32_t)bidx[2 * r + h];
+                    if (use_atomic)
+                        atomicMin(&hit[p], packed_hit);
+                    else
+                        hit[p] = packed_hit;
+                }
             }
         }
     }
@@ -258,30 +270,34 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
         TFRT_CHECK_CUDA(cudaGetDevice(&dev));
         TFRT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // Grid shape: rays per thread (2*R2) and the number of triangle-range splits are chosen
-    // together so that the CTA count fills whole waves of resident CTAs (148 SMs x CTAs/SM):
-    // a 1 M-ray trace as 2 048 CTAs of 4 rays/thread is 3.46 waves (13 % idle tail), as
-    // 1 024 x 4 splits of 8 rays/thread it is 6.92 waves (1 %).  Score = wave efficiency x a
-    // per-shape factor (fewer rays per thread re-read the tile more often; every split repeats
-    // the ray load and ring prologue).
-    int r2 = 4, splits = 1;
+    // Work decomposition.  Items = ray blocks (kThreads * 2*R2 rays) x triangle splits, handed
+    // out dynamically to persistent CTAs, so the idle tail of a launch is about half an item per
+    // CTA.  Aim for >= 32 items per resident CTA (tail < 2 %) while an item keeps >= 4 tiles
+    // (its fixed cost -- ray gather, ring prologue, 64-bit atomicMin merge -- stays < 1 %).
+    // Prefer 8 rays per thread (one LDS.128 feeds 8 rays); fall back to 4 / 2 rays per thread
+    // only when the ray count cannot fill the machine otherwise.
+    int r2 = 1, splits = 1;
     {
         const int cand_r2[3] = {4, 2, 1};
         const int occ[3] = {4, 5, 6};                 // resident CTAs per SM (registers / smem)
-        const double shape[3] = {1.0, 0.96, 0.88};
-        double best_score = -1.0;
-        for (int c = 0; c < 3; ++c) {
-            const int rb = tfrt_div_up(n_upper, kThreads * 2 * cand_r2[c]);
-            const int max_splits = n_tiles < 16 ? n_tiles : 16;
-            for (int sp = 1; sp <= max_splits; ++sp) {
-                const int tps = tfrt_div_up(n_tiles, sp);
-                const int real = tfrt_div_up(n_tiles, tps);
-                if (real != sp) continue;
-                const double waves = (double)rb * sp / ((double)num_sms * occ[c]);
-                const double eff = waves / (double)(long long)(waves + 0.999999);
-                const double score = eff * shape[c] * ((double)tps / (tps + 0.35)) *
-                                     (sp > 1 ? 0.995 : 1.0);
-                if (score > best_score) { best_score = score; r2 = cand_r2[c]; splits = sp; }
+        static int items_per_cta = 0;                 // measured flat between 4 and 16
+        if (!items_per_cta) {
+            const char *e = getenv("TFRT_K1_ITEMS_PER_CTA");
+            items_per_cta = e ? atoi(e) : 8;
+            if (items_per_cta < 1) items_per_cta = 1;
+        }
+        bool done = false;
+        for (int min_tps = 4; min_tps >= 1 && !done; min_tps >>= 1) {   // small meshes: finer splits
+            const int max_splits = n_tiles / min_tps > 0 ? n_tiles / min_tps : 1;
+            for (int c = 0; c < 3 && !done; ++c) {
+                const long long rb = tfrt_div_up(n_upper, kThreads * 2 * cand_r2[c]);
+                const long long resident = (long long)num_sms * occ[c];
+                long long sp = ((long long)items_per_cta * resident + rb - 1) / rb;
+                if (sp > max_splits) sp = max_splits;
+                if (sp < 1) sp = 1;
+                r2 = cand_r2[c];
+                splits = (int)sp;
+                done = rb * sp >= 2 * resident;       // enough items to fill and balance
             }
         }
     }
@@ -295,8 +311,23 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     if (use_atomic)
         TFRT_CHECK_CUDA(cudaMemsetAsync(hit, 0xff, (size_t)n_upper * sizeof(uint64_t), stream));
 
+    // work counter of this launch: a rotating slot of a small device array, zeroed in stream
+    // order (launches of one stream never overlap; 64 slots cover concurrent streams)
+    static unsigned int *counters_of_device[64] = {nullptr};
+    static std::atomic<unsigned int> launch_seq{0};
+    int cur_dev = 0;
+    TFRT_CHECK_CUDA(cudaGetDevice(&cur_dev));
+    TFRT_REQUIRE(cur_dev >= 0 && cur_dev < 64, "tfrt_launch_intersect3d: device index %d", cur_dev);
+    if (!counters_of_device[cur_dev])
+        TFRT_CHECK_CUDA(cudaMalloc(&counters_of_device[cur_dev], 64 * sizeof(unsigned int)));
+    unsigned int *counter = counters_of_device[cur_dev] + (launch_seq.fetch_add(1) % 64u);
+    TFRT_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+
     const size_t smem = sizeof(IntersectSmem);
-    dim3 grid(ray_blocks, splits), block(kThreads);
+    const int occ_r2 = r2 >= 4 ? 4 : (r2 == 2 ? 5 : 6);
+    const long long total_upper = (long long)ray_blocks * splits;
+    const long long resident = (long long)num_sms * occ_r2;
+    dim3 grid((unsigned)(total_upper < resident ? total_upper : resident)), block(kThreads);
 #define TFRT_LAUNCH(R2)                                                                         \
     do {                                                                                        \
         static bool attr_set = false;                                                           \
@@ -308,9 +339,9 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
         }                                                                                       \
         k_intersect3d<R2><<<grid, block, smem, stream>>>(                                       \
             ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,          \
-            reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, intersect_eps,  \
-            ray_start_eps, 1.0f + 3.0f * size_eps, reinterpret_cast<unsigned long long *>(hit),       \
-            use_atomic, dir_mode);  \
+            reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, splits,         \
+            intersect_eps, ray_start_eps, 1.0f + 3.0f * size_eps,                               \
+            reinterpret_cast<unsigned long long *>(hit), use_atomic, dir_mode, counter);        \
     } while (0)
     const bool timed = tfrt_profile_begin(stream);
 #if TFRT_K1_FORCE_R2

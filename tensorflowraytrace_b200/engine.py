@@ -721,6 +721,16 @@ class OpticalEngine:
             dead_ray_length=self.dead_ray_length if bool(self.dead_ray_length) else None,
             compile=compile_sets, **kw)
         plan.packed = packed
+        # stop / target boundaries that do not require grad need no cotangents (merged order is
+        # optical -> stop -> target, so they are the tail of the triangle list)
+        def needs_grad(d):
+            return bool(d) and any(torch.is_tensor(v) and v.requires_grad for v in d.values())
+        if needs_grad(system._amalgamated_target):
+            plan.n_grad_tri = 0
+        elif needs_grad(system._amalgamated_stop):
+            plan.n_grad_tri = system._optical_count + system._stop_count
+        else:
+            plan.n_grad_tri = max(system._optical_count, 1)
         active, stopped, finished, dead = TraceFunction.apply(
             tri, None if system._norm_is_geometric else norm, src, plan)
         self.last_trace = plan.trace

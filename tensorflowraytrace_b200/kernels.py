@@ -239,7 +239,7 @@ class Trace3D:
                 ptr(it), _stream()), "tfrt_materialize3d")
         return rays, slot, it
 
-    def backward(self, g_hist, want_src_grad=False, dead_ray_length=None):
+    def backward(self, g_hist, want_src_grad=False, dead_ray_length=None, n_grad_tri=0):
         """b5 seam.  g_hist: dict which -> (6,n) f32 cotangents of `history(which)` rays (or
         None).  Returns (g_tri (9,T), g_norm (T,3), g_src (6,N) or None)."""
         dev = self.src.device
@@ -261,6 +261,7 @@ class Trace3D:
         g_norm = torch.empty((self.T, 3), dtype=torch.float32, device=dev)
         g_src = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev) if want_src_grad else None
         b.dead_ray_length = -1.0 if dead_ray_length is None else float(dead_ray_length)
+        b.n_grad_tri = int(n_grad_tri)
         b.g_acc, b.g_ray_ws = g_acc.data_ptr(), g_ray_ws.data_ptr()
         for i in range(9):
             b.g_tri_out[i] = g_tri[i].data_ptr()
