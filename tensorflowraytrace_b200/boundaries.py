@@ -56,6 +56,12 @@ def as_field(value, device=None):
     return t.to(device)
 
 
+def as_float_field(value, device=None):
+    """as_field for geometric data: integer input (e.g. the tuple (1, 0, 0)) becomes fp32."""
+    t = as_field(value, device)
+    return t if t.is_floating_point() else t.to(torch.float32)
+
+
 class TriangleMesh:
     """Minimal mesh container (stand-in for pyvista.PolyData): points (V,3), faces (F,3)."""
 
@@ -123,7 +129,7 @@ class SecondSurfaceVG(VectorGeneratorBase):
 
     @points.setter
     def points(self, val):
-        self._points = as_field(val)
+        self._points = as_float_field(val)
 
 
 class FromPointVG(VectorGeneratorBase):
@@ -141,7 +147,7 @@ class FromPointVG(VectorGeneratorBase):
 
     @point.setter
     def point(self, val):
-        self._point = as_field(val)
+        self._point = as_float_field(val)
 
 
 class FromVectorVG(VectorGeneratorBase):
@@ -159,7 +165,7 @@ class FromVectorVG(VectorGeneratorBase):
 
     @vector.setter
     def vector(self, val):
-        self._vector = as_field(val)
+        self._vector = as_float_field(val)
 
 
 class FromAxisVG(VectorGeneratorBase):
@@ -167,11 +173,11 @@ class FromAxisVG(VectorGeneratorBase):
     point plus a kwarg `point` (second point) or `direction`."""
 
     def __init__(self, first, **kwargs):
-        self.axis_point = as_field(first)
+        self.axis_point = as_float_field(first)
         if "point" in kwargs:
-            axis_vector = as_field(kwargs["point"]) - self.axis_point
+            axis_vector = as_float_field(kwargs["point"]) - self.axis_point
         elif "direction" in kwargs:
-            axis_vector = as_field(kwargs["direction"])
+            axis_vector = as_float_field(kwargs["direction"])
         else:
             raise ValueError(
                 "FromAxisVG: Must provide a kwarg 'point' or 'direction' to define the axis.")
@@ -183,6 +189,114 @@ class FromAxisVG(VectorGeneratorBase):
         d = torch.sum((zero - axis_point) * axis_vector, dim=1)
         closest_point = axis_point + axis_vector * d.reshape(-1, 1)
         return self.normalize(zero - closest_point)
+
+
+# =========================================================================================
+# constraints between parametric surfaces (tfrt/boundaries.py:17-235).  A constraint's make()
+# returns a handler that is appended to a surface's update_handles; it shifts or clips the
+# surface's `parameters` in place and is not differentiated (the reference uses assign_add
+# inside the tape).
+
+class Constraint(ABC):
+    """Base class.  `parent` selects what the constraint is relative to: "prev" (previous
+    surface of a multi-boundary, or zero for the first), "zero", "literal" (target and parent
+    passed to make() are the surfaces themselves) or an integer surface index."""
+
+    def __init__(self, parent="prev"):
+        if type(parent) is int:
+            if parent < 0:
+                raise ValueError("Constraint: integer parent must be >= 0")
+        elif type(parent) is str:
+            if parent not in {"zero", "prev", "literal"}:
+                raise ValueError("Constraint: string parent must be 'zero' or 'prev'.")
+        self._parent = parent
+
+    @property
+    def parent(self):
+        return self._parent
+
+    def interpret_params(self, target, parent):
+        """(target parameters, parent parameters) for the mode chosen at construction."""
+        if self._parent == "literal":
+            return target.parameters, parent.parameters
+        if self._parent == "zero":
+            return target.parameters, torch.zeros_like(target.parameters)
+        if self._parent == "prev":
+            mine = parent[target].parameters
+            if target == 0:
+                return mine, torch.zeros_like(mine)
+            return mine, parent[target - 1].parameters
+        return parent[target].parameters, parent[self._parent].parameters
+
+    @abstractmethod
+    def make(self, target, parent):
+        raise NotImplementedError
+
+
+class NoConstraint(Constraint):
+    def make(self, target, parent):
+        return lambda: None
+
+
+class PointConstraint(Constraint):
+    """Fixes the parameter-space distance between one vertex of the target surface and one
+    vertex of the parent surface (tfrt/boundaries.py:124-158)."""
+
+    def __init__(self, distance, target_vertex, parent_vertex=None, **kwargs):
+        super().__init__(**kwargs)
+        self.distance = distance
+        self.target_vertex = target_vertex
+        self.parent_vertex = parent_vertex or target_vertex
+
+    def make(self, target, parent):
+        def handler(target=target, parent=parent):
+            t, p = self.interpret_params(target, parent)
+            with torch.no_grad():
+                t.add_(p[self.parent_vertex] - t[self.target_vertex] + self.distance)
+        return handler
+
+
+class ThicknessConstraint(Constraint):
+    """Fixes the minimum ("min") or maximum ("max") parameter-space distance between the target
+    surface and its parent (tfrt/boundaries.py:162-215)."""
+
+    def __init__(self, distance, mode, **kwargs):
+        super().__init__(**kwargs)
+        self.distance = distance
+        self.mode = mode
+
+    @property
+    def mode(self):
+        return self._mode
+
+    @mode.setter
+    def mode(self, val):
+        if val not in {"min", "max"}:
+            raise ValueError("ThicknessConstraint: mode must be either 'min' or 'max'.")
+        self._mode = val
+        self._reduce = torch.max if val == "min" else torch.min
+
+    def make(self, target, parent):
+        def handler(target=target, parent=parent):
+            t, p = self.interpret_params(target, parent)
+            with torch.no_grad():
+                t.add_(self._reduce(p - t) + self.distance)
+        return handler
+
+
+class ClipConstraint:
+    """Clips a surface's parameters to [lower, upper] (tfrt/boundaries.py:219-235)."""
+
+    def __init__(self, lower, upper):
+        self.lower = lower
+        self.upper = upper
+        self.parent = "zero"
+
+    def make(self, target, _):
+        def handler(target=target):
+            with torch.no_grad():
+                target.parameters.clamp_(self.lower, self.upper)
+        return handler
 
 
 # =========================================================================================
@@ -474,3 +588,141 @@ class ParametricTriangleBoundary(TriangleBoundaryBase):
     def update_from_mesh(self):
         raise RuntimeError(
             "ParametricTriangleBoundary: update_from_mesh is disabled for parametric boundaries.")
+
+
+class ParametricMultiTriangleBoundary(TriangleBoundaryBase):
+    """Several parametric triangle surfaces over one set of zero points, tied together by
+    constraints (tfrt/boundaries.py:1233-1412).  `surfaces` is the list to hand to
+    OpticalSystem3D.optical; `parameters` the list of their parameter tensors."""
+
+    def __init__(self, zero_points, vector_generator, constraints, flip_norm,
+                 initial_parameters=0.0, validate_shape=True, parameters=None, material_list=(),
+                 **kwargs):
+        if isinstance(zero_points, str):
+            zero_points = _read_mesh(zero_points)
+        self.zero_points = zero_points
+        self.vector_generator = vector_generator
+        try:
+            self._surface_count = len(constraints)
+        except TypeError as e:
+            raise ValueError("ParametricMultiTriangleBoundary: constraints must be iterable.") from e
+
+        def per_surface(value, name, scalar_ok=True):
+            try:
+                if len(value) != self._surface_count:
+                    raise ValueError(f"ParametricMultiTriangleBoundary: constraints and {name} "
+                                     "must have the same size.")
+                return list(value)
+            except TypeError as e:
+                if scalar_ok:
+                    return [value] * self._surface_count
+                raise ValueError(f"ParametricMultiTriangleBoundary: {name} must be iterable.") from e
+
+        flip_norm = per_surface(flip_norm, "flip_norm", scalar_ok=False)
+        initial_parameters = per_surface(initial_parameters, "initial_parameters")
+        if parameters is not None:
+            parameters = per_surface(parameters, "parameters", scalar_ok=False)
+        material_list = list(material_list) if len(material_list) else [{}] * self._surface_count
+        if len(material_list) != self._surface_count:
+            raise ValueError("ParametricMultiTriangleBoundary: constraints and material_list "
+                             "must have the same size.")
+        vmap = kwargs.pop("vertex_update_map", None)
+        self._surfaces = [
+            ParametricTriangleBoundary(
+                self.zero_points, self.vector_generator, flip_norm=flip_norm[i],
+                initial_parameters=initial_parameters[i],
+                parameters=None if parameters is None else parameters[i],
+                material_dict=material_list[i], vertex_update_map=vmap, **kwargs)
+            for i in range(self._surface_count)]
+        self.constraints = list(constraints)
+        for i, (surface, constraint) in enumerate(zip(self._surfaces, self.constraints)):
+            if constraint.parent != "zero":
+                surface.update_handles.append(constraint.make(i, self._surfaces))
+            else:
+                surface.update_handles.append(constraint.make(surface, None))
+        self._name = kwargs.get("name")
+        self._fields = {}
+        self.material_dict = {}
+        RecursivelyUpdatable.__init__(self)
+
+    def _update(self):
+        from .engine import amalgamate
+        self._fields = amalgamate(self._surfaces)
+
+    def _generate_update_handles(self):
+        return [surface.update for surface in self._surfaces]
+
+    def update_materials(self):
+        pass
+
+    @property
+    def surface_count(self):
+        return self._surface_count
+
+    @property
+    def surfaces(self):
+        return self._surfaces
+
+    @property
+    def parameters(self):
+        return [surface.parameters for surface in self._surfaces]
+
+
+# ----------------------------------------------------------------------------------------- 2D
+
+class ParametricSegmentBoundary(BoundaryBase):
+    """A curve approximated by segments whose vertices slide along the lines from the points
+    of `zero_distribution` to those of `one_distribution`:
+    points = zero + parameters * (one - zero) (tfrt/boundaries.py:528-627).  The distributions
+    are objects with `.points` (n,2) (and optionally `.update`) or plain arrays."""
+
+    def __init__(self, zero_distribution, one_distribution, flip_norm=False,
+                 initial_parameters=0.0, validate_shape=True, parameters=None, **kwargs):
+        self._zero_distribution = zero_distribution
+        self._one_distribution = one_distribution
+        self.flip_norm = flip_norm
+        zero = self._points(zero_distribution)
+        if parameters is None:
+            init = torch.broadcast_to(torch.as_tensor(initial_parameters, dtype=torch.float32),
+                                      (zero.shape[0],)).clone().to(zero.device)
+            self.parameters = init.requires_grad_(True)
+        else:
+            self.parameters = parameters
+        super().__init__(**kwargs)
+
+    @staticmethod
+    def _points(dist):
+        return as_field(getattr(dist, "points", dist)).reshape(-1, 2)
+
+    @property
+    def dimension(self):
+        return 2
+
+    def update_materials(self):
+        if "x_start" in self._fields:
+            self._update_materials(self["x_start"].shape[0], self["x_start"].device)
+
+    def _generate_update_handles(self):
+        return [d.update for d in (self._zero_distribution, self._one_distribution)
+                if hasattr(d, "update")]
+
+    def _update(self):
+        zero, one = self._points(self._zero_distribution), self._points(self._one_distribution)
+        (self["x_start"], self["y_start"], self["x_end"], self["y_end"]) = self._update_internal(
+            zero, one, self.parameters, self.flip_norm)
+        self.update_materials()
+
+    @staticmethod
+    def _update_internal(zero, one, parameter, flip_norm):
+        points = zero + parameter.reshape(-1, 1) * (one - zero)
+        if flip_norm:
+            return points[1:, 0], points[1:, 1], points[:-1, 0], points[:-1, 1]
+        return points[:-1, 0], points[:-1, 1], points[1:, 0], points[1:, 1]
+
+    @property
+    def zero_distribution(self):
+        return self._zero_distribution
+
+    @property
+    def one_distribution(self):
+        return self._one_distribution

@@ -115,3 +115,165 @@ def plane_mesh(center, half_size, axis=0):
     if nrm[axis] < 0:
         faces = faces[:, ::-1].copy()
     return corners, faces
+
+
+# =============================================================================================
+# Graph tools for parametric meshes (tfrt/mesh_tools.py:221-331, 345-421): which corners a face
+# may move (`vertex_update_map`), the gradient accumulator and the parameter smoother.  The
+# reference builds dense V x V float64 matrices with O(V^2) Python set scans (5 GB at config 5's
+# 25 117 vertices); here everything is vectorised on a CSR vertex adjacency and the matrices are
+# scipy.sparse CSR (SGD_Optimizer and `smooth` accept them), identical in value.
+
+def _faces_of(mesh_or_faces):
+    faces = getattr(mesh_or_faces, "faces", mesh_or_faces)
+    f = np.asarray(faces).astype(np.int64)
+    if f.ndim == 1:
+        f = f.reshape(-1, 4)
+    if f.shape[1] == 4:
+        f = f[:, 1:]
+    return f
+
+
+def _points_of(mesh_or_points):
+    return np.asarray(getattr(mesh_or_points, "points", mesh_or_points), dtype=np.float64)
+
+
+def vertex_adjacency(faces, n_vertices):
+    """Symmetric boolean CSR adjacency: two vertices are neighbours when they share a face
+    (the reference's neighbors_from_faces, tfrt/mesh_tools.py:119-129)."""
+    import scipy.sparse as sp
+    i = np.concatenate([faces[:, 0], faces[:, 1], faces[:, 2], faces[:, 1], faces[:, 2], faces[:, 0]])
+    j = np.concatenate([faces[:, 1], faces[:, 2], faces[:, 0], faces[:, 0], faces[:, 1], faces[:, 2]])
+    a = sp.csr_matrix((np.ones(i.shape[0], dtype=np.int8), (i, j)), shape=(n_vertices, n_vertices))
+    a.data[:] = 1
+    return a
+
+
+def get_closest_point(mesh, point):
+    """Index of the mesh vertex nearest to `point` (tfrt/mesh_tools.py `get_closest_point`)."""
+    pts = _points_of(mesh)
+    return int(np.argmin(np.sum((pts - np.asarray(point, dtype=np.float64)) ** 2, axis=1)))
+
+
+def vertex_rings(mesh, top_parent):
+    """Breadth-first ring index of every vertex from `top_parent` over the face adjacency
+    (-1 for vertices that cannot be reached): the wave front the reference advances as
+    `active_edge` (tfrt/mesh_tools.py:241-272)."""
+    faces = _faces_of(mesh)
+    n = _points_of(mesh).shape[0]
+    adj = vertex_adjacency(faces, n)
+    ring = np.full(n, -1, dtype=np.int64)
+    frontier = np.array([top_parent], dtype=np.int64)
+    ring[frontier] = 0
+    k = 0
+    while frontier.size:
+        k += 1
+        reach = np.unique(adj[frontier].indices)
+        frontier = reach[ring[reach] < 0]
+        ring[frontier] = k
+    return ring, adj
+
+
+def mesh_parametrization_tools(mesh, top_parent, active_vertices=None, dense=False):
+    """vertex_update_map (F,3) bool and the gradient accumulator (V,V)
+    (tfrt/mesh_tools.py:221-331).
+
+    A face is visited when the wave front from `top_parent` first touches it and may move only
+    its vertices that lie ahead of the front (ring > the face's lowest ring); faces whose three
+    vertices share one ring would move nothing and are allowed all three ("orphaned faces",
+    tfrt/mesh_tools.py:471-480).  accumulator[i, j] = 1 when j == i or j is an ancestor of i,
+    a vertex's parents being its neighbours one ring closer to `top_parent`; left-multiplied
+    onto a gradient it moves a vertex together with everything downstream of it.
+    Returns a scipy.sparse CSR accumulator unless dense=True."""
+    import scipy.sparse as sp
+    faces = _faces_of(mesh)
+    n = _points_of(mesh).shape[0]
+    ring, adj = vertex_rings(mesh, top_parent)
+    missed = ring < 0
+    fring = np.where(ring[faces] < 0, np.iinfo(np.int64).max, ring[faces])
+    update_map = fring > fring.min(axis=1, keepdims=True)
+    update_map[~update_map.any(axis=1)] = True
+
+    # parents: neighbours one ring closer; unreachable vertices take their reachable neighbours
+    coo = adj.tocoo()
+    is_parent = (ring[coo.col] == ring[coo.row] - 1) & ~missed[coo.row] & ~missed[coo.col]
+    is_parent |= missed[coo.row] & ~missed[coo.col]
+    parents = sp.csr_matrix((np.ones(int(is_parent.sum()), dtype=np.float64),
+                             (coo.row[is_parent], coo.col[is_parent])), shape=(n, n))
+    # ancestors ring by ring: rows of ring k are final once rings < k are
+    order = [np.nonzero(ring == k)[0] for k in range(1, int(ring.max()) + 1)] + [np.nonzero(missed)[0]]
+    closure = sp.csr_matrix((n, n), dtype=np.float64)
+    eye = sp.identity(n, dtype=np.float64, format="csr")
+    for rows in order:
+        if rows.size == 0:
+            continue
+        block = parents[rows] @ (eye + closure)
+        block.data[:] = 1.0
+        sel = sp.csr_matrix((np.ones(rows.size), (rows, np.arange(rows.size))), shape=(n, rows.size))
+        closure = closure + sel @ block
+    accumulator = (closure + eye).tocsr()
+    if active_vertices is not None:
+        keep = np.array(sorted(set(int(v) for v in active_vertices)), dtype=np.int64)
+        accumulator = accumulator[keep][:, keep]
+    return update_map, (accumulator.toarray() if dense else accumulator)
+
+
+def gaussian_weights(sigma, count):
+    """Un-normalised gaussian weights per neighbour order (tfrt/mesh_tools.py:335-341)."""
+    x = np.arange(count) / sigma
+    return np.exp(-0.5 * x ** 2)
+
+
+def mesh_smoothing_tool(mesh, weights, active_vertices=None, dense=False):
+    """Smoother (V,V): left-multiplied onto the parameters, every vertex keeps weights[0]/sum of
+    itself and spreads weights[k]/sum evenly over its k-th order neighbours
+    (tfrt/mesh_tools.py:345-421)."""
+    import scipy.sparse as sp
+    faces = _faces_of(mesh)
+    n = _points_of(mesh).shape[0]
+    adj = vertex_adjacency(faces, n).astype(np.float64)
+    w = np.asarray(weights, dtype=np.float64)
+    w = w / w.sum()
+    eye = sp.identity(n, dtype=np.float64, format="csr")
+    taken, current = eye.copy(), eye.copy()
+    smoother = eye * w[0]
+    for order in range(1, w.shape[0]):
+        reach = current @ adj
+        reach.data[:] = 1.0
+        new = reach - reach.multiply(taken)          # not yet taken
+        new.eliminate_zeros()
+        counts = np.asarray(new.sum(axis=1)).ravel()
+        scale = sp.diags(np.where(counts > 0, w[order] / np.maximum(counts, 1.0), 0.0))
+        smoother = smoother + scale @ new
+        taken = taken + new
+        current = new
+    smoother = smoother.tocsr()
+    if active_vertices is not None:
+        keep = np.array(sorted(set(int(v) for v in active_vertices)), dtype=np.int64)
+        smoother = smoother[keep][:, keep]
+    return smoother.toarray() if dense else smoother
+
+
+def get_flat_initial(mesh, axis=0):
+    """Flatten one axis of `mesh.points` in place and return the removed coordinates, to be used
+    as initial parameters (tfrt/mesh_tools.py:425-456)."""
+    if axis not in (0, 1, 2):
+        raise ValueError("get_flat_initial: axis must be in {0, 1, 2}.")
+    initial = mesh.points[:, axis].copy()
+    mesh.points[:, axis] = 0.0
+    return initial
+
+
+def to_torch_sparse(matrix, device=None, dtype=None):
+    """scipy.sparse / dense matrix -> torch sparse CSR-compatible COO tensor for
+    SGD_Optimizer accumulators and smoothers."""
+    import scipy.sparse as sp
+    import torch
+    dtype = dtype or torch.float32
+    if sp.issparse(matrix):
+        coo = matrix.tocoo()
+        idx = torch.from_numpy(np.stack([coo.row, coo.col]).astype(np.int64))
+        t = torch.sparse_coo_tensor(idx, torch.from_numpy(coo.data).to(dtype), coo.shape).coalesce()
+    else:
+        t = torch.as_tensor(np.asarray(matrix), dtype=dtype)
+    return t.to(device) if device is not None else t
