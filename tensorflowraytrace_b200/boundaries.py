@@ -726,3 +726,160 @@ class ParametricSegmentBoundary(BoundaryBase):
     @property
     def one_distribution(self):
         return self._one_distribution
+
+
+class MasterSlaveParametricTriangleBoundary(ParametricTriangleBoundary):
+    """Parametric triangle boundary in which several vertices share one parameter
+    (tfrt/boundaries.py:1116-1229): `filter_masters` (callable on the (V,3) vertices returning a
+    boolean mask or index list, or the index list itself) names the vertices that own a
+    parameter; `attach_slaves(vertices, master, available_slaves)` returns the slave vertices
+    that follow each master.  parameters has one entry per master; the expansion to vertices is a
+    gather whose transpose (scatter-add) autograd applies to the vertex gradients."""
+
+    def __init__(self, filter_masters, attach_slaves, *args, **kwargs):
+        self._gather = None
+        super().__init__(*args, **kwargs)
+        verts = self._vertices.detach().cpu().numpy()
+        masters = filter_masters(verts) if callable(filter_masters) else filter_masters
+        masters = np.asarray(masters)
+        if masters.dtype == np.bool_:
+            masters = np.nonzero(masters)[0]
+        masters = [int(m) for m in masters]
+        master_index = {m: i for i, m in enumerate(masters)}
+        unclaimed = set(range(verts.shape[0])) - set(masters)
+        owner = dict(master_index)
+        for m in masters:
+            slaves = set(int(s) for s in attach_slaves(verts, m, unclaimed))
+            unclaimed -= slaves
+            for s in slaves:
+                owner[s] = master_index[m]
+        missing = [v for v in range(verts.shape[0]) if v not in owner]
+        if missing:
+            raise ValueError(f"MasterSlaveParametricTriangleBoundary: vertices {missing[:8]} "
+                             "were attached to no master.")
+        dev = self._zero_points.device
+        self._gather = torch.tensor([owner[v] for v in range(verts.shape[0])], dtype=torch.long,
+                                    device=dev)
+        self.masters = masters
+        self.parameters = self.parameters.detach()[torch.tensor(masters, device=dev)].clone() \
+            .requires_grad_(True)
+        self._update()
+
+    def _update(self):
+        if self._gather is None:       # base-class constructor, before the gather exists
+            return super()._update()
+        self._vertices = self._update_internal(self._zero_points, self._vectors,
+                                               self.parameters[self._gather])
+        if self.auto_update_mesh:
+            self.update_mesh_from_vertices()
+        self.update_fields_from_vertices()
+
+
+class ParametricCylindricalGuide(TriangleBoundaryBase):
+    """A closed cylinder-like light guide whose radius varies along (and optionally around) its
+    axis (tfrt/boundaries.py:1416-1717): vertices = cylinder of `minimum_radius` + parameters *
+    radial unit vectors, parameters >= 0 with min(parameters) pinned to 0 on every update.
+    rotationally_symmetric=True: one parameter per axial layer (z_res), else one per side vertex
+    (z_res * theta_res).  Cap vertices (on the axis) never move.  The class builds its own mesh
+    (mesh_tools.cylindrical_mesh), vertex_update_map and accumulator
+    (mesh_tools.mesh_parametrization_tools)."""
+
+    def __init__(self, start, end, minimum_radius, theta_res=6, z_res=8, start_cap=True,
+                 end_cap=True, rotationally_symmetric=False, initial_parameters=0.0,
+                 initial_taper=None, auto_update_mesh=False, use_vertex_update_map=True,
+                 **kwargs):
+        from . import mesh_tools as mt
+        pts, faces = mt.cylindrical_mesh(start, end, radius=minimum_radius, theta_res=theta_res,
+                                         z_res=z_res, start_cap=start_cap, end_cap=end_cap)
+        self._mesh = TriangleMesh(pts, faces)
+        self._zero_points_mesh = self._mesh.copy()
+        self._zero_points = as_float_field(pts)
+        self._vertices = self._zero_points
+        self._faces = torch.from_numpy(faces).to(dtype=torch.int32, device=self._zero_points.device)
+        self._n_side = theta_res * z_res
+        self._n_caps = int(bool(start_cap)) + int(bool(end_cap))
+        self._theta_res, self._z_res = theta_res, z_res
+        self._guide_map, self._accumulator = mt.mesh_parametrization_tools(
+            self._mesh, mt.get_closest_point(self._mesh, start),
+            active_vertices=range(self._n_side))
+        self._vertex_update_map = None
+        self._update_map_dev = None
+        self.use_vertex_update_map = use_vertex_update_map
+        self.vector_generator = FromAxisVG(start, point=end)
+        self.auto_update_mesh = auto_update_mesh
+        self._rotationally_symmetric = rotationally_symmetric
+        self.reparametrize(self._zero_points)
+        dev = self._zero_points.device
+        size = z_res if rotationally_symmetric else self._n_side
+        if initial_taper is not None:
+            try:
+                t0, t1 = float(initial_taper[0]), float(initial_taper[1])
+            except (IndexError, TypeError) as e:
+                raise ValueError(
+                    "ParametricCylindricalGuide: initial_taper must be None or a 2-tuple.") from e
+            init = torch.linspace(t0, t1, z_res, device=dev)
+            if not rotationally_symmetric:
+                init = init.repeat_interleave(theta_res)
+        else:
+            init = torch.broadcast_to(torch.as_tensor(initial_parameters, dtype=torch.float32),
+                                      (size,)).clone().to(dev)
+        self.parameters = init.to(torch.float32).requires_grad_(True)
+        BoundaryBase.__init__(self, **kwargs)
+        if not self.auto_update_mesh:
+            self.update_mesh_from_vertices()
+
+    def _generate_update_handles(self):
+        return []
+
+    def _constraint(self):
+        with torch.no_grad():
+            self.parameters.sub_(self.parameters.min())
+
+    def _update(self):
+        self._constraint()
+        p = self.parameters
+        if self._rotationally_symmetric:
+            p = p.repeat_interleave(self._theta_res)
+        p = torch.nn.functional.pad(p, (0, self._n_caps))       # cap vertices stay on the axis
+        self._vertices = self._zero_points + p.reshape(-1, 1) * self._vectors
+        if self.auto_update_mesh:
+            self.update_mesh_from_vertices()
+        self.update_fields_from_vertices()
+
+    def reparametrize(self, zero_points):
+        v = self.vector_generator.generate(self._zero_points)
+        # the cap vertices lie on the axis: no radial direction (the generator yields 0/0)
+        self._vectors = torch.where(torch.isfinite(v), v, torch.zeros_like(v))
+
+    @property
+    def zero_points(self):
+        return self._zero_points_mesh
+
+    @property
+    def vectors(self):
+        return self._vectors
+
+    @property
+    def use_vertex_update_map(self):
+        return self._use_vertex_update_map
+
+    @use_vertex_update_map.setter
+    def use_vertex_update_map(self, val):
+        self._use_vertex_update_map = bool(val)
+        self.vertex_update_map = self._guide_map if val else None
+
+    @property
+    def accumulator(self):
+        return self._accumulator
+
+    @property
+    def rotationally_symmetric(self):
+        return self._rotationally_symmetric
+
+    def update_vertices_from_mesh(self):
+        raise RuntimeError("ParametricCylindricalGuide: update_vertices_from_mesh is disabled "
+                           "for parametric boundaries.")
+
+    def update_from_mesh(self):
+        raise RuntimeError("ParametricCylindricalGuide: update_from_mesh is disabled for "
+                           "parametric boundaries.")
