@@ -17,33 +17,21 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tensorflowraytrace_b200 import (boundaries, engine, materials, mesh_tools, operation,  # noqa: E402
-                                     optimizer, scenes, sources)
+from tensorflowraytrace_b200 import (boundaries, distributions, engine, materials,  # noqa: E402
+                                     mesh_tools, operation, optimizer, scenes, sources)
 
 SOURCE_DISTANCE, MAGNIFICATION, OBJECT_SIZE = 4.0, 2.0, 0.2
-GOLDEN = math.pi * (1.0 + 5.0 ** 0.5)
 
 
 def build(ray_count=20000, rings=12, seed=0, device="cuda", grad_clip=1e-3):
-    gen = torch.Generator(device=device).manual_seed(seed)
-
-    # random source, regenerated on the device at every system.update()
-    state = {}
-
-    def base_points():
-        yz = (torch.rand((ray_count, 2), generator=gen, device=device) * 2 - 1) * OBJECT_SIZE
-        state["rank"] = yz / OBJECT_SIZE
-        return torch.cat([torch.full((ray_count, 1), -SOURCE_DISTANCE, device=device), yz], 1)
-
-    def directions():   # RandomUniformSphere(pi/16), tfrt/distributions.py:1756-1774
-        lo = math.cos(math.pi / 16.0)
-        phi = torch.acos(lo + (1 - lo) * torch.rand(ray_count, generator=gen, device=device))
-        theta = torch.remainder(GOLDEN * torch.rand(ray_count, generator=gen, device=device), 2 * math.pi)
-        return torch.stack([torch.cos(phi), torch.sin(phi) * torch.cos(theta),
-                            torch.sin(phi) * torch.sin(theta)], 1)
-
-    source = sources.AngularSource(3, base_points, directions, [scenes.YELLOW], dense=False,
-                                   ranks=lambda: state["rank"])
+    # random source (dev/simple_3d_optimize.py:29-43): re-sampled on the device at every update
+    distributions.seed_all(seed)
+    side = max(int(round(ray_count ** 0.5)), 1)
+    base_points = distributions.RandomUniformSquare(OBJECT_SIZE, side)
+    angles = distributions.RandomUniformSphere(math.pi / 16.0, side * side)
+    source = sources.AngularSource(
+        3, (-SOURCE_DISTANCE, 0.0, 0.0), (1.0, 0.0, 0.0), angles, base_points, [scenes.YELLOW],
+        dense=False, extra_fields={"rank": ("base_point", base_points, "ranks")})
 
     # zero points: a hexagonal disk in the y-z plane
     pts, faces = mesh_tools.hexagonal_mesh(1.0, rings)

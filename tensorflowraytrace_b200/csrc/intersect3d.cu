@@ -272,28 +272,35 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     }
     // Work decomposition.  Items = ray blocks (kThreads * 2*R2 rays) x triangle splits, handed
     // out dynamically to persistent CTAs, so the idle tail of a launch is about half an item per
-    // CTA.  Aim for >= 32 items per resident CTA (tail < 2 %) while an item keeps >= 4 tiles
-    // (its fixed cost -- ray gather, ring prologue, 64-bit atomicMin merge -- stays < 1 %).
+    // CTA.  Long items are cheap to cut (an item's fixed cost -- ray gather, ring prologue,
+    // 64-bit atomicMin merge -- is a few microseconds): aim for up to 64 items per resident CTA
+    // while an item keeps >= 16 tiles, but never fewer than 8 items per CTA while it keeps >= 4
+    // (measured flat between 4 and 16 items per CTA at 5-tile items, profiles/r1_k1_tuning.md).
     // Prefer 8 rays per thread (one LDS.128 feeds 8 rays); fall back to 4 / 2 rays per thread
-    // only when the ray count cannot fill the machine otherwise.
+    // and finer splits only when the ray count cannot fill the machine otherwise.
     int r2 = 1, splits = 1;
     {
         const int cand_r2[3] = {4, 2, 1};
         const int occ[3] = {4, 5, 6};                 // resident CTAs per SM (registers / smem)
-        static int items_per_cta = 0;                 // measured flat between 4 and 16
-        if (!items_per_cta) {
+        static int items_lo = 0, items_hi = 0;
+        if (!items_lo) {
             const char *e = getenv("TFRT_K1_ITEMS_PER_CTA");
-            items_per_cta = e ? atoi(e) : 8;
-            if (items_per_cta < 1) items_per_cta = 1;
+            items_lo = e ? atoi(e) : 8;
+            if (items_lo < 1) items_lo = 1;
+            items_hi = e ? items_lo : 64;
         }
         bool done = false;
         for (int min_tps = 4; min_tps >= 1 && !done; min_tps >>= 1) {   // small meshes: finer splits
-            const int max_splits = n_tiles / min_tps > 0 ? n_tiles / min_tps : 1;
             for (int c = 0; c < 3 && !done; ++c) {
                 const long long rb = tfrt_div_up(n_upper, kThreads * 2 * cand_r2[c]);
                 const long long resident = (long long)num_sms * occ[c];
-                long long sp = ((long long)items_per_cta * resident + rb - 1) / rb;
-                if (sp > max_splits) sp = max_splits;
+                const long long cap_lo = n_tiles / min_tps > 0 ? n_tiles / min_tps : 1;
+                const long long cap_hi = n_tiles / (4 * min_tps) > 0 ? n_tiles / (4 * min_tps) : 1;
+                long long sp_hi = (items_hi * resident + rb - 1) / rb;
+                long long sp_lo = (items_lo * resident + rb - 1) / rb;
+                if (sp_hi > cap_hi) sp_hi = cap_hi;
+                if (sp_lo > cap_lo) sp_lo = cap_lo;
+                long long sp = sp_hi > sp_lo ? sp_hi : sp_lo;
                 if (sp < 1) sp = 1;
                 r2 = cand_r2[c];
                 splits = (int)sp;

@@ -1,40 +1,178 @@
 """
-Sources: ray-set field dicts feeding the trace hot path (tfrt/sources.py).
+Sources: ray-set field dicts feeding the trace hot path (tfrt/sources.py), generated on the GPU.
 
-The hot path only consumes the *field layout* of a source: 1-D, equal-length tensors
-`x_start, y_start, (z_start,) x_end, y_end, (z_end,) wavelength` plus any extra per-ray
-fields that ray operations declare or `simple_ray_inheritance` names (tfrt/sources.py:72-359;
-tfrt/engine.py:2242-2257).  Ray generation itself (distributions, quaternion rotations) is
-outside the hot path ("next" rank 2); the generic container and the two
-closed-form sources the BASELINE configs use are provided here.
+The hot path consumes only the *field layout* of a source: 1-D, equal-length fp32 tensors
+`x_start, y_start, (z_start,) x_end, y_end, (z_end,) wavelength` plus any extra per-ray fields
+(tfrt/sources.py:72-359; tfrt/engine.py:2242-2257).  The classes below keep the reference's
+constructors and its dense / undense "domain" semantics, but build the fields with torch ops on
+the field device, so a source re-sampled at every `system.update()` stays in HBM.
 
-  SourceBase      common container + update protocol     tfrt/sources.py:72-359
-  ManualSource    filled by indexing                      tfrt/sources.py:363-382
-  PointSource     rays from one point along given unit vectors   tfrt/sources.py:464-674
-                  (end = start + ray_length * direction, :598-603)
-  AngularSource   base points x directions, dense or undense     tfrt/sources.py:678-914
+  SourceBase       domains, dense expansion, extra fields        tfrt/sources.py:72-359
+  ManualSource     filled by indexing                            tfrt/sources.py:363-382
+  RotationBase     central_angle handling (2D angle, 3D vector or quaternion)   :386-460
+  PointSource      rays from one point                           tfrt/sources.py:464-674
+  AngularSource    base points x angles                          tfrt/sources.py:678-914
+  AperatureSource  start points -> end points                    tfrt/sources.py:918-1095
+
+Dense sources take the cross product of their domains in the reference's order: the domain
+index arrays are `tf.meshgrid(*ranges)` (default 'xy' indexing) flattened row-major
+(tfrt/sources.py:283-292), i.e. for domains (d0, d1, d2, ...) the flattened order has d1
+slowest, then d0, then d2 ... fastest.  Undense sources pair their variables element-wise.
+`PrecompiledSource` (pickled ray sets, :1099-1358) is out of scope.
 """
 
 import itertools
+import math
 
 import numpy as np
 import torch
 
-from .boundaries import as_field
+from .boundaries import as_field, as_float_field, default_device
 from .update import RecursivelyUpdatable
 
 COUNTER = itertools.count(0)
 
 
 class SourceBase(RecursivelyUpdatable):
-    def __init__(self, dimension, extra_fields=None, name=None, **kwargs):
+    """Base class of sources (tfrt/sources.py:72-359).
+
+    extra_fields : dict field -> (domain, value) or (domain, object, attribute).  The value (a
+        tensor, array, scalar or zero-argument callable) is expanded like the source's own
+        variables of that domain and published as a ray field (e.g. ranks).
+    dense : cross every domain with every other (True) or pair them element-wise (False).
+    """
+
+    def __init__(self, extra_fields=None, standard_domains=frozenset(), dense=True,
+                 always_resize=False, name=None, **kwargs):
+        self.extra_fields = {} if extra_fields is None else extra_fields
+        self._standard_domains = set(standard_domains) | {"whole", "wavelength"}
+        self.dense = dense
+        self._fields = {}
+        self._domain_gathers = {}
+        self._domain_sizes = {}
+        self._needs_resize = True
+        self.always_resize = always_resize
+        self._name = name or f"{type(self).__name__}-{next(COUNTER)}"
+        super().__init__(**kwargs)
+
+    def _set_dimension(self, dimension):
         if dimension not in {2, 3}:
             raise ValueError("Source: dimension must be 2 or 3")
         self._dimension = dimension
-        self._fields = {}
-        self.extra_fields = {} if extra_fields is None else extra_fields
-        self._name = name or f"{type(self).__name__}-{next(COUNTER)}"
-        super().__init__(**kwargs)
+
+    @staticmethod
+    def validate_extra_fields(extra_fields):
+        for field, args in extra_fields.items():
+            if type(field) is not str:
+                raise ValueError("Source extra fields: keys must be strings.")
+            if len(args) not in (2, 3):
+                raise ValueError(
+                    "Source extra fields: every entry must be either a 2-tuple of "
+                    "(domain, value), or a 3-tuple of (domain, object, attribute).")
+
+    # ------------------------------------------------------------------ domain machinery
+    @staticmethod
+    def _resolve(items):
+        if len(items) == 2:
+            domain, value = items
+        else:
+            domain, obj, attr = items
+            try:
+                value = obj[attr]
+            except (TypeError, KeyError, IndexError):
+                value = getattr(obj, attr)
+        if callable(value):
+            value = value()
+        return domain, value
+
+    def resize(self):
+        self._needs_resize = True
+
+    def _resize(self):
+        """Work out the size of every domain and, for dense sources, the gather index arrays
+        (tfrt/sources.py:206-315)."""
+        self._needs_resize = False
+        sizes = {}
+        entries = list(self._internal_vars().values()) + \
+            [self._resolve(items) for items in self._extra_fields.values()]
+        for domain, value in entries:
+            t = torch.as_tensor(value) if not torch.is_tensor(value) else value
+            sizes.setdefault(domain, []).append(t.shape[0] if t.dim() > 0 else 1)
+        self._domain_sizes = {}
+        for domain, found in sizes.items():
+            distinct = set(found) - {1}
+            if len(distinct) > 1:
+                raise ValueError("Source resize: found incompatible shapes in the same domain.")
+            self._domain_sizes[domain] = distinct.pop() if distinct else 1
+        if self.dense:
+            domains = [d for d in self._domain_sizes if d != "whole"]
+            dev = default_device()
+            ranges = [torch.arange(self._domain_sizes[d], device=dev) for d in domains]
+            grids = torch.meshgrid(*ranges, indexing="xy") if len(ranges) > 1 else ranges
+            self._domain_gathers = {d: g.reshape(-1) for d, g in zip(domains, grids)}
+            self._domain_sizes["whole"] = int(np.prod([self._domain_sizes[d] for d in domains]))
+        else:
+            self._domain_gathers = {}
+            whole = 1
+            for size in self._domain_sizes.values():
+                if size == 1:
+                    continue
+                if whole == 1:
+                    whole = size
+                if whole != size:
+                    raise ValueError("Source resize: found incompatibly sized variables with "
+                                     "an undense source.")
+            self._domain_sizes["whole"] = whole
+
+    def _expand(self, domain, value):
+        t = as_field(value)
+        if self.dense and domain != "whole":
+            if t.dim() == 0:
+                t = t.reshape(1)
+            return t[self._domain_gathers[domain].to(t.device)]
+        if t.dim() < 2:
+            return torch.broadcast_to(t, (self._domain_sizes["whole"],)).clone() \
+                if t.dim() == 0 or t.shape[0] == 1 else t
+        return t
+
+    def make_vars(self, internal_vars):
+        return {name: self._expand(domain, value) for name, (domain, value) in internal_vars.items()}
+
+    def publish_extra_fields(self):
+        for field, items in self._extra_fields.items():
+            domain, value = self._resolve(items)
+            self[field] = self._expand(domain, value)
+
+    def _update(self):
+        if self._needs_resize or self.always_resize:
+            self._resize()
+        self._internal_update(self.make_vars(self._internal_vars()))
+        self.publish_extra_fields()
+
+    def _internal_vars(self):
+        return {}
+
+    def _internal_update(self, expanded_vars):
+        pass
+
+    def snapshot(self, do_update=True):
+        if do_update:
+            self.update()
+        return {field: data.clone() for field, data in self.items()}
+
+    # ------------------------------------------------------------------ dict protocol
+    @property
+    def extra_fields(self):
+        return self._extra_fields
+
+    @extra_fields.setter
+    def extra_fields(self, val):
+        self.validate_extra_fields(val)
+        self._extra_fields = val
+
+    @property
+    def standard_domains(self):
+        return self._standard_domains
 
     @property
     def name(self):
@@ -61,19 +199,6 @@ class SourceBase(RecursivelyUpdatable):
     def items(self):
         return self._fields.items
 
-    def snapshot(self, do_update=True):
-        if do_update:
-            self.update()
-        return dict(self._fields)
-
-    def _publish_extra_fields(self, count):
-        for field, value in self.extra_fields.items():
-            value = value() if callable(value) else value
-            t = as_field(value)
-            if t.dim() < 1:
-                t = torch.broadcast_to(t, (count,)).clone()
-            self[field] = t
-
     def _generate_update_handles(self):
         return []
 
@@ -83,7 +208,8 @@ class ManualSource(SourceBase):
     functions in `update_handles` / `post_update_handles` to regenerate it on update()."""
 
     def __init__(self, dimension, **kwargs):
-        super().__init__(dimension, **kwargs)
+        self._set_dimension(dimension)
+        super().__init__(**kwargs)
 
     def _update(self):
         pass
@@ -95,81 +221,232 @@ class ManualSource(SourceBase):
         return self
 
 
-class PointSource(SourceBase):
-    """Rays leaving `center` along unit vectors `directions` (N,dim), one wavelength per ray or
-    a list of wavelengths crossed with the directions when dense (tfrt/sources.py:464-674).
-    end = start + ray_length * direction (tfrt/sources.py:598-603)."""
+# =============================================================================================
+# rotations (tfrt/sources.py:386-460; the reference delegates to tfquaternion)
 
-    def __init__(self, dimension, center, directions, wavelengths, ray_length=1.0, dense=True,
-                 **kwargs):
-        self.center = center
-        self.directions = directions
-        self.wavelengths = wavelengths
-        self.ray_length = ray_length
-        self.dense = dense
-        super().__init__(dimension, **kwargs)
+def quaternion_from_x_to(v):
+    """Unit quaternion (w, x, y, z) of the shortest rotation taking +x onto `v`."""
+    v = np.asarray(v, dtype=np.float64)
+    v = v / np.linalg.norm(v)
+    w = 1.0 + v[0]
+    if w < 1e-12:                                   # antiparallel: half a turn about z
+        return np.array([0.0, 0.0, 0.0, 1.0])
+    q = np.array([w, 0.0, -v[2], v[1]])            # (1 + x.v, x cross v)
+    return q / np.linalg.norm(q)
 
-    def _update(self):
-        d = as_field(self.directions() if callable(self.directions) else self.directions)
-        d = d.reshape(-1, self.dimension)
-        wl = as_field(np.atleast_1d(np.asarray(self.wavelengths, dtype=np.float64))).to(d.device)
-        if self.dense:   # every direction x every wavelength, direction index fastest
-            n_d, n_w = d.shape[0], wl.shape[0]
-            d = d.repeat(n_w, 1)
-            wl = wl.repeat_interleave(n_d)
+
+def rotate_by_quaternion(q, vectors):
+    """Rotate (n,3) vectors by the unit quaternion q = (w, x, y, z): v' = v + 2 r x (r x v + w v)."""
+    q = torch.as_tensor(np.asarray(q, dtype=np.float64), dtype=vectors.dtype, device=vectors.device)
+    w, r = q[0], q[1:].reshape(1, 3)
+    t = torch.linalg.cross(r.expand_as(vectors), vectors, dim=1) + w * vectors
+    return vectors + 2.0 * torch.linalg.cross(r.expand_as(vectors), t, dim=1)
+
+
+class RotationBase:
+    """central_angle handling shared by PointSource and AngularSource.  2D: a scalar angle.
+    3D: angle_type "vector" (the direction the source faces; the shortest rotation from +x) or
+    "quaternion" ((w, x, y, z) given directly)."""
+
+    def __init__(self, central_angle, angle_type):
+        if angle_type not in ("vector", "quaternion"):
+            raise ValueError("Source: angle_type must be 'vector' or 'quaternion'.")
+        self._angle_type = angle_type
+        self.central_angle = central_angle
+
+    @property
+    def central_angle(self):
+        return self._central_angle
+
+    @central_angle.setter
+    def central_angle(self, val):
+        val = np.asarray(val, dtype=np.float64)
+        if self.dimension == 2:
+            if val.shape != ():
+                raise ValueError("Source: central_angle must be scalar.")
+            self._central_angle = float(val)
+        elif self._angle_type == "vector":
+            if val.shape != (3,):
+                raise ValueError("Source: central_angle must be size (3,).")
+            self._central_angle = quaternion_from_x_to(val)
         else:
-            wl = torch.broadcast_to(wl, (d.shape[0],)).clone()
-        c = as_field(np.asarray(self.center, dtype=np.float64)).to(d.device).reshape(1, -1)
-        start = torch.broadcast_to(c, d.shape)
-        end = start + self.ray_length * d
-        names = ("x", "y", "z")[: self.dimension]
-        for i, ax in enumerate(names):
+            if val.shape != (4,):
+                raise ValueError("Source: central_angle must be size (4,).")
+            self._central_angle = val / np.linalg.norm(val)
+
+    def _rotate_angles(self, angles):
+        if self._dimension == 2:
+            return angles + self._central_angle
+        return rotate_by_quaternion(self._central_angle, angles)
+
+    def _rotate_points(self, points):
+        if self._dimension == 2:
+            c, s = math.cos(self._central_angle), math.sin(self._central_angle)
+            return torch.stack([c * points[:, 0] - s * points[:, 1],
+                                s * points[:, 0] + c * points[:, 1]], dim=1)
+        if points.shape[1] == 2:     # 2D base points live in the y-z plane
+            points = torch.cat([torch.zeros_like(points[:, :1]), points], dim=1)
+        return rotate_by_quaternion(self._central_angle, points)
+
+
+def _center(val, dimension, who):
+    t = np.asarray(val, dtype=np.float64)
+    if t.shape != (dimension,):
+        raise ValueError(f"{who}: center must be size ({dimension},).")
+    return as_float_field(t)
+
+
+class _DirectedSource(SourceBase, RotationBase):
+    """Common tail of PointSource / AngularSource: write the ray fields from start points and
+    unit directions (or 2D angles)."""
+
+    def _publish(self, start, angles, forward, expanded_vars):
+        if self._dimension == 2:
+            end = start + self.ray_length * torch.stack([torch.cos(angles), torch.sin(angles)], 1)
+        else:
+            end = start + self.ray_length * angles
+        first, second = (start, end) if forward else (end, start)
+        for i, ax in enumerate(("x", "y", "z")[: self._dimension]):
+            self._fields[f"{ax}_start"] = first[:, i].contiguous()
+            self._fields[f"{ax}_end"] = second[:, i].contiguous()
+        if "wavelengths" in expanded_vars:
+            self._fields["wavelength"] = expanded_vars["wavelengths"]
+
+    def _angle_var(self):
+        dist = self._angular_distribution
+        return dist.angles if getattr(dist, "angles", None) is not None else dist.points
+
+
+class PointSource(_DirectedSource):
+    """Rays that all start at `center` (tfrt/sources.py:464-674).  In 2D the angular
+    distribution provides angles (rad, relative to central_angle); in 3D unit vectors about +x
+    (a sphere distribution's `points`) that are rotated onto `central_angle`.
+    end = start + ray_length * direction (:598-603); start_on_center=False swaps the ends."""
+
+    def __init__(self, dimension, center, central_angle, angular_distribution, wavelengths,
+                 start_on_center=True, ray_length=1.0, angle_type="vector", **kwargs):
+        self._set_dimension(dimension)
+        RotationBase.__init__(self, central_angle, angle_type)
+        self.center = center
+        self._angular_distribution = angular_distribution
+        self._wavelengths = None if wavelengths is None else as_float_field(wavelengths)
+        self.start_on_center = start_on_center
+        self.ray_length = ray_length
+        SourceBase.__init__(self, standard_domains={"angle"}, **kwargs)
+
+    def _internal_vars(self):
+        out = {"angles": ("angle", self._angle_var())}
+        if self._wavelengths is not None:
+            out["wavelengths"] = ("wavelength", self._wavelengths)
+        return out
+
+    def _internal_update(self, expanded_vars):
+        angles = self._rotate_angles(expanded_vars["angles"])
+        start = torch.broadcast_to(self._center.to(angles.device).reshape(1, -1),
+                                   (angles.shape[0], self._dimension))
+        self._publish(start, angles, self.start_on_center, expanded_vars)
+
+    def _generate_update_handles(self):
+        return [self._angular_distribution.update]
+
+    @property
+    def center(self):
+        return self._center
+
+    @center.setter
+    def center(self, val):
+        self._center = _center(val, self.dimension, "PointSource")
+
+    @property
+    def angular_distribution(self):
+        return self._angular_distribution
+
+
+class AngularSource(_DirectedSource):
+    """Rays that start on base points (rotated by central_angle, then offset by `center`) and
+    leave along the angular distribution (tfrt/sources.py:678-914).  dense=True crosses base
+    points, angles and wavelengths; dense=False pairs them element-wise."""
+
+    def __init__(self, dimension, center, central_angle, angular_distribution,
+                 base_point_distribution, wavelengths, start_on_base=True, ray_length=1.0,
+                 angle_type="vector", **kwargs):
+        self._set_dimension(dimension)
+        RotationBase.__init__(self, central_angle, angle_type)
+        self.center = center
+        self._angular_distribution = angular_distribution
+        self._base_point_distribution = base_point_distribution
+        self._wavelengths = None if wavelengths is None else as_float_field(wavelengths)
+        self.start_on_base = start_on_base
+        self.ray_length = ray_length
+        SourceBase.__init__(self, standard_domains={"base_point", "angle"}, **kwargs)
+
+    def _internal_vars(self):
+        out = {"angles": ("angle", self._angle_var()),
+               "base_points": ("base_point", self._base_point_distribution.points)}
+        if self._wavelengths is not None:
+            out["wavelengths"] = ("wavelength", self._wavelengths)
+        return out
+
+    def _internal_update(self, expanded_vars):
+        angles = self._rotate_angles(expanded_vars["angles"])
+        base = self._rotate_points(expanded_vars["base_points"])
+        start = self._center.to(base.device).reshape(1, -1) + base
+        self._publish(start, angles, self.start_on_base, expanded_vars)
+
+    def _generate_update_handles(self):
+        return [self._angular_distribution.update, self._base_point_distribution.update]
+
+    @property
+    def center(self):
+        return self._center
+
+    @center.setter
+    def center(self, val):
+        self._center = _center(val, self.dimension, "AngularSource")
+
+    @property
+    def angular_distribution(self):
+        return self._angular_distribution
+
+    @property
+    def base_point_distribution(self):
+        return self._base_point_distribution
+
+
+class AperatureSource(SourceBase):
+    """Rays from the points of one distribution to the points of another
+    (tfrt/sources.py:918-1095)."""
+
+    def __init__(self, dimension, start_point_distribution, end_point_distribution, wavelengths,
+                 **kwargs):
+        self._set_dimension(dimension)
+        self._start_point_distribution = start_point_distribution
+        self._end_point_distribution = end_point_distribution
+        self._wavelengths = None if wavelengths is None else as_float_field(wavelengths)
+        super().__init__(standard_domains={"start_point", "end_point"}, **kwargs)
+
+    def _internal_vars(self):
+        out = {"start_points": ("start_point", self._start_point_distribution.points),
+               "end_points": ("end_point", self._end_point_distribution.points)}
+        if self._wavelengths is not None:
+            out["wavelengths"] = ("wavelength", self._wavelengths)
+        return out
+
+    def _internal_update(self, expanded_vars):
+        start, end = expanded_vars["start_points"], expanded_vars["end_points"]
+        for i, ax in enumerate(("x", "y", "z")[: self._dimension]):
             self._fields[f"{ax}_start"] = start[:, i].contiguous()
             self._fields[f"{ax}_end"] = end[:, i].contiguous()
-        self._fields["wavelength"] = wl
-        self._publish_extra_fields(d.shape[0])
+        if "wavelengths" in expanded_vars:
+            self._fields["wavelength"] = expanded_vars["wavelengths"]
 
+    def _generate_update_handles(self):
+        return [self._start_point_distribution.update, self._end_point_distribution.update]
 
-class AngularSource(SourceBase):
-    """Base points x directions (tfrt/sources.py:678-914).  dense=True crosses every base point
-    with every direction (and wavelength); dense=False pairs them element-wise.  The optional
-    `ranks` (N, dim-1) of the base points is published as the field `rank`, the quantity the
-    reference's imaging losses use (dev/simple_3d_optimize.py:136-137)."""
+    @property
+    def start_point_distribution(self):
+        return self._start_point_distribution
 
-    def __init__(self, dimension, base_points, directions, wavelengths, ray_length=1.0,
-                 dense=False, ranks=None, **kwargs):
-        self.base_points = base_points
-        self.directions = directions
-        self.wavelengths = wavelengths
-        self.ray_length = ray_length
-        self.dense = dense
-        self.ranks = ranks
-        super().__init__(dimension, **kwargs)
-
-    def _update(self):
-        get = lambda v: as_field(v() if callable(v) else v)  # noqa: E731
-        b = get(self.base_points).reshape(-1, self.dimension)
-        d = get(self.directions).reshape(-1, self.dimension)
-        wl = as_field(np.atleast_1d(np.asarray(self.wavelengths, dtype=np.float64))).to(b.device)
-        rank = None if self.ranks is None else get(self.ranks)
-        if self.dense:
-            n_b, n_d, n_w = b.shape[0], d.shape[0], wl.shape[0]
-            b = b.repeat(n_d * n_w, 1)
-            if rank is not None:
-                rank = rank.repeat(n_d * n_w, *([1] * (rank.dim() - 1)))
-            d = d.repeat_interleave(n_b, dim=0).repeat(n_w, 1)
-            wl = wl.repeat_interleave(n_b * n_d)
-        else:
-            if b.shape[0] != d.shape[0]:
-                raise ValueError(
-                    "Source resize: found incompatibly sized variables with an undense source.")
-            wl = torch.broadcast_to(wl, (b.shape[0],)).clone()
-        end = b + self.ray_length * d
-        names = ("x", "y", "z")[: self.dimension]
-        for i, ax in enumerate(names):
-            self._fields[f"{ax}_start"] = b[:, i].contiguous()
-            self._fields[f"{ax}_end"] = end[:, i].contiguous()
-        self._fields["wavelength"] = wl
-        if rank is not None:
-            self._fields["rank"] = rank
-        self._publish_extra_fields(b.shape[0])
+    @property
+    def end_point_distribution(self):
+        return self._end_point_distribution
