@@ -423,12 +423,27 @@ def run_ours(args):
         }
     elif scene["dimension"] == 2:
         # the 2D path is one launch per trace: launch-latency bound, no roofline fraction
+        tr2 = engine.last_trace
+        reps = 50
+        tr2.forward()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            tr2.forward()
+        e1.record()
+        torch.cuda.synchronize()
         line["roofline"] = {
             "kernel": "k_trace2d_forward", "bound": "latency", "achieved": None, "peak": None,
             "unit": "us/trace", "frac": None, "traffic": None,
             "us_per_trace": 1e6 * fwd_seconds / args.steps,
+            "us_per_trace_kernel_only": 1e3 * e0.elapsed_time(e1) / reps,
             "note": "config 1 (1 000 rays x 3 segments x 3 iterations) is launch-latency bound "
-                    "(SURVEY.md 8(d)): one kernel launch per trace, fp64 arithmetic"}
+                    "(SURVEY.md 8(d)): one kernel launch per trace, fp64 arithmetic; "
+                    "us_per_trace is the public-API call (system.update + ray_trace, host "
+                    "bookkeeping included), us_per_trace_kernel_only the C-ABI launch alone "
+                    "(status memset + k_trace2d_forward)"}
     if backward:
         # the backward leg (loss + K2 + K3 backward + all-reduce) timed on its own with CUDA
         # events around autograd, forward outside the timed span

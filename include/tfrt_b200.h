@@ -10,7 +10,9 @@
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in `_host`.
  *   - All work is enqueued on the given stream (a cudaStream_t passed as void*); no hidden
- *     synchronisation, no allocation: the caller owns every buffer, including workspaces.
+ *     synchronisation; the caller owns every buffer, including workspaces.  The only memory
+ *     the library allocates itself is a 256-byte per-device array of work counters for the
+ *     persistent search kernel (first call) and the 4-byte sink of tfrt_fp32_peak.
  *   - Return value 0 = success; nonzero = error, message in tfrt_last_error() (thread local).
  *   - Rays are structure-of-arrays fp32, "slot" indexed: slot i is source ray i for the whole
  *     trace (rays never split: StandardReaction emits exactly one child per active ray,
