@@ -407,3 +407,54 @@ def test_full_size_cfg5_subsample_parity():
     assert cmp["iterations"] == 3
     assert cmp["max_rel"] < POINT_TOL, cmp
     assert cmp["mismatches"] <= 6                        # near ties only (others raise)
+
+
+def test_full_size_cfg4_subsample_parity():
+    """BASELINE config 4 at full size (4 194 304 rays x 50 002 triangles x 16 iterations of TIR
+    bounces, six wavelengths, decaying live set): a random subsample of the same rays traced by
+    the oracle must agree slot for slot at every iteration."""
+    from types import SimpleNamespace
+    scene = scenes.config4()
+    engine, _, _ = scenes.build_engine(scene, eps=helpers.EPS, compile_active_rays=False)
+    engine.ray_trace(16)
+    tr = engine.last_trace
+    assert tr.N == 4194304 and tr.T == 50002
+    live = tr.live_counts()
+    assert live[0] == tr.N and live[-1] < live[0]
+    rng = np.random.default_rng(7)
+    idx = np.sort(rng.choice(tr.N, size=1024, replace=False))
+    didx = torch.from_numpy(idx).to(DEV)
+    sub = SimpleNamespace(last_trace=SimpleNamespace(
+        K=tr.K, tape_tri=tr.tape_tri[:, didx], tape_status=tr.tape_status[:, didx],
+        tape_f=tr.tape_f[:, :, didx]))
+    oracle, _ = helpers.oracle_from_scene(scene, ray_slice=idx)
+    oracle.ray_trace(16)
+    cmp = helpers.compare_trace(sub, oracle)
+    assert cmp["iterations"] >= 8
+    assert cmp["max_rel"] < POINT_TOL, cmp
+
+
+def test_full_size_cfg3_subsample_gradient():
+    """Backward at BASELINE config 3's launch shape (1 048 576 rays): the gradient of the loss
+    restricted to a random subsample of rays equals the oracle's gradient for those rays."""
+    scene = scenes.config3()
+    engine, params, _ = scenes.build_engine(scene, eps=helpers.EPS, compile_active_rays=False)
+    engine.ray_trace(3)
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.choice(1048576, size=4096, replace=False))
+    chosen = torch.zeros(1048576, dtype=torch.bool, device=DEV)
+    chosen[torch.from_numpy(idx).to(DEV)] = True
+    err = scenes.imaging_error(scene)(engine)
+    mask = chosen[engine.last_history_slots["finished"].long()]
+    grads = torch.autograd.grad(err[mask].sum(), params)
+    oracle, oparams = helpers.oracle_from_scene(scene, ray_slice=idx, requires_grad=True)
+    oracle.ray_trace(3)
+    ofin = oracle.finished_rays
+    goal = scene["goal_scale"] * ofin["rank"]
+    oerr = (ofin["y_end"] - goal[:, 0]) ** 2 + (ofin["z_end"] - goal[:, 1]) ** 2
+    assert int(mask.sum()) == oerr.shape[0]
+    assert abs(float(err[mask].sum().detach()) - float(oerr.sum().detach())) < 1e-4 * float(oerr.sum().detach())
+    ograds = torch.autograd.grad(oerr.sum(), oparams)
+    for g, og_ in zip(grads, ograds):
+        assert float(og_.abs().max()) > 0
+        assert helpers.rel_err(g.cpu().numpy(), og_.numpy()) < GRAD_TOL
