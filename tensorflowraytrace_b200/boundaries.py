@@ -883,3 +883,77 @@ class ParametricCylindricalGuide(TriangleBoundaryBase):
     def update_from_mesh(self):
         raise RuntimeError("ParametricCylindricalGuide: update_from_mesh is disabled for "
                            "parametric boundaries.")
+
+
+class ParametricMultiSegmentBoundary(BoundaryBase):
+    """Several parametric segment curves over one pair of base-point distributions, tied
+    together by constraints (tfrt/boundaries.py:631-826); the 2D sibling of
+    ParametricMultiTriangleBoundary.  `surfaces` is the list for OpticalSystem2D.optical_segments."""
+
+    def __init__(self, zero_distribution, one_distribution, constraints, flip_norm,
+                 initial_parameters=0.0, validate_shape=True, parameters=None, material_list=(),
+                 **kwargs):
+        self._zero_distribution = zero_distribution
+        self._one_distribution = one_distribution
+        try:
+            self._surface_count = len(constraints)
+        except TypeError as e:
+            raise ValueError("ParametricMultiSegmentBoundary: constraints must be iterable.") from e
+
+        def per_surface(value, name, scalar_ok=True):
+            try:
+                if len(value) != self._surface_count:
+                    raise ValueError(f"ParametricMultiSegmentBoundary: constraints and {name} "
+                                     "must have the same size.")
+                return list(value)
+            except TypeError as e:
+                if scalar_ok:
+                    return [value] * self._surface_count
+                raise ValueError(f"ParametricMultiSegmentBoundary: {name} must be iterable.") from e
+
+        self.flip_norm = per_surface(flip_norm, "flip_norm", scalar_ok=False)
+        initial_parameters = per_surface(initial_parameters, "initial_parameters")
+        if parameters is not None:
+            parameters = per_surface(parameters, "parameters", scalar_ok=False)
+        material_list = list(material_list) if len(material_list) else [{}] * self._surface_count
+        if len(material_list) != self._surface_count:
+            raise ValueError("ParametricMultiSegmentBoundary: constraints and material_list "
+                             "must have the same size.")
+        self.surfaces = [
+            ParametricSegmentBoundary(
+                zero_distribution, one_distribution, flip_norm=self.flip_norm[i],
+                initial_parameters=initial_parameters[i],
+                parameters=None if parameters is None else parameters[i],
+                material_dict=material_list[i])
+            for i in range(self._surface_count)]
+        self.constraints = list(constraints)
+        for i, (surface, constraint) in enumerate(zip(self.surfaces, self.constraints)):
+            if constraint.parent != "zero":
+                surface.update_handles.append(constraint.make(i, self.surfaces))
+            else:
+                surface.update_handles.append(constraint.make(surface, None))
+        super().__init__(**kwargs)
+
+    @property
+    def dimension(self):
+        return 2
+
+    def update_materials(self):
+        pass
+
+    def _update(self):
+        from .engine import amalgamate
+        self._fields = amalgamate(self.surfaces)
+
+    def _generate_update_handles(self):
+        handles = [d.update for d in (self._zero_distribution, self._one_distribution)
+                   if hasattr(d, "update")]
+        return handles + [surface.update for surface in self.surfaces]
+
+    @property
+    def surface_count(self):
+        return self._surface_count
+
+    @property
+    def parameters(self):
+        return [surface.parameters for surface in self.surfaces]

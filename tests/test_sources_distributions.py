@@ -144,3 +144,35 @@ def test_aperature_source():
     gs, ge = np.meshgrid(np.arange(4), np.arange(3))
     assert np.allclose(npy(src["y_start"]), np.linspace(-1, 1, 4)[gs.reshape(-1)], atol=1e-6)
     assert np.allclose(npy(src["y_end"]), np.linspace(-2, 2, 3)[ge.reshape(-1)], atol=1e-6)
+
+
+def test_parametric_segment_boundaries_and_constraints():
+    """2D parametric curves: points = zero + p (one - zero), consecutive points make segments,
+    flip_norm reverses them; a multi-boundary keeps its thickness constraint on update."""
+    from tensorflowraytrace_b200 import boundaries as B
+    zero = D.StaticUniformAperaturePoints((0.0, -1.0), (0.0, 1.0), 5)
+    one = D.StaticUniformAperaturePoints((1.0, -1.0), (1.0, 1.0), 5)
+    init = [0.0, 0.1, 0.2, 0.1, 0.0]
+    seg = B.ParametricSegmentBoundary(zero, one, initial_parameters=init)
+    assert seg["x_start"].shape == (4,) and seg.dimension == 2
+    assert np.allclose(npy(seg["x_start"]), init[:-1], atol=1e-7)
+    assert np.allclose(npy(seg["x_end"]), init[1:], atol=1e-7)
+    assert np.allclose(npy(seg["y_start"]), np.linspace(-1, 1, 5)[:-1], atol=1e-7)
+    flipped = B.ParametricSegmentBoundary(zero, one, flip_norm=True, initial_parameters=init)
+    assert np.allclose(npy(flipped["x_start"]), init[1:], atol=1e-7)
+    (g,) = torch.autograd.grad(seg["x_end"].sum() + seg["x_start"].sum(), [seg.parameters])
+    assert np.allclose(npy(g), [1, 2, 2, 2, 1])
+    multi = B.ParametricMultiSegmentBoundary(
+        zero, one, [B.ThicknessConstraint(0.0, "min"), B.ThicknessConstraint(0.3, "min")],
+        [True, False], initial_parameters=[init, 0.0],
+        material_list=[{"mat_in": np.int64(1), "mat_out": np.int64(0)}] * 2)
+    p0, p1 = multi.parameters
+    assert abs(float((0.0 - p0).max().detach())) < 1e-7           # first surface touches zero
+    assert abs(float((p0 - p1).max().detach()) + 0.3) < 1e-6      # min gap 0.3 to the second
+    assert multi["x_start"].shape == (8,) and len(multi.surfaces) == 2
+    with torch.no_grad():
+        p1.add_(0.5)
+    multi.update()
+    assert abs(float((p0 - p1).max().detach()) + 0.3) < 1e-6
+    with pytest.raises(ValueError):
+        B.ParametricMultiSegmentBoundary(zero, one, [B.NoConstraint()], [True, False])
