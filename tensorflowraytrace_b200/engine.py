@@ -83,17 +83,22 @@ def annotation_helper(parent, field, value, valid_shape_field, dtype=None):
     """Keep `parent[field]` annotated on every update (tfrt/engine.py:103-142): `value` is
     broadcast to the shape of `parent[valid_shape_field]` (or, if callable, called with that
     shape and `dtype`) by a post-update handle, e.g. to apply materials to a boundary."""
+    cache = {}
+
     def f():
         ref = parent[valid_shape_field]
         if callable(value):
             parent[field] = value(ref.shape, dtype)
-        else:
+            return
+        key = (tuple(ref.shape), ref.device)
+        if cache.get("key") != key:      # constant annotation: rebuilt only when the shape changes
             t = torch.as_tensor(value, device=ref.device)
             if dtype is not None:
                 t = t.to(dtype)
             elif t.is_floating_point():
                 t = t.to(torch.float32)
-            parent[field] = torch.broadcast_to(t, ref.shape).clone()
+            cache["key"], cache["tensor"] = key, torch.broadcast_to(t, ref.shape).clone()
+        parent[field] = cache["tensor"]
     parent.post_update_handles.append(f)
     f()
 
@@ -178,6 +183,14 @@ class OpticalSystemBase(RecursivelyUpdatable):
                 [descriptor_of(m) for m in self._materials], device)
         return self._material_table
 
+    def _category_tensor(self, cat, like):
+        """Constant int64 category labels, cached per (category, count, device)."""
+        cache = self.__dict__.setdefault("_category_cache", {})
+        key = (cat, like.shape[0], like.device)
+        if key not in cache:
+            cache[key] = torch.full((like.shape[0],), cat, dtype=torch.int64, device=like.device)
+        return cache[key]
+
     @abstractmethod
     def intersect(self, rays):
         raise NotImplementedError
@@ -261,7 +274,7 @@ class OpticalSystem3D(OpticalSystemBase):
         for cat, d in ((OPTICAL, self._amalgamated_optical), (STOP, self._amalgamated_stop),
                        (TARGET, self._amalgamated_target)):
             if bool(d):
-                d["catagory"] = torch.full_like(d["xp"], cat, dtype=torch.int64)
+                d["catagory"] = self._category_tensor(cat, d["xp"])
                 counts.append(d["xp"].shape[0])
             else:
                 counts.append(0)
@@ -408,7 +421,7 @@ class OpticalSystem2D(OpticalSystemBase):
             for cat, name in ((OPTICAL, "optical"), (STOP, "stop"), (TARGET, "target")):
                 d = getattr(self, f"_amalgamated_{name}_{suffix}")
                 if bool(d):
-                    d["catagory"] = torch.full_like(d[key], cat, dtype=torch.int64)
+                    d["catagory"] = self._category_tensor(cat, d[key])
                     counts.append(d[key].shape[0])
                 else:
                     counts.append(0)
@@ -865,24 +878,31 @@ class OpticalEngine:
 
         inherit = [f for f in src_fields if f not in kernels.RAY_FIELDS_2D]
         self.last_history_slots, self.last_history_iterations = {}, {}
-        for name, flag, store in (("active", self.compile_active_rays, self._active_rays),
-                                  ("finished", self.compile_finished_rays, self._finished_rays),
-                                  ("stopped", self.compile_stopped_rays, self._stopped_rays),
-                                  ("dead", self.compile_dead_rays, self._dead_rays)):
-            if not flag:
-                continue
-            it, slot = sets[name]
-            rays = tape[it, :, slot]                              # (n_set, 4)
+        wanted = [(name, store) for name, flag, store in (
+            ("active", self.compile_active_rays, self._active_rays),
+            ("finished", self.compile_finished_rays, self._finished_rays),
+            ("stopped", self.compile_stopped_rays, self._stopped_rays),
+            ("dead", self.compile_dead_rays, self._dead_rays)) if flag]
+        # one gather for all compiled sets (latency matters here), then per-set views
+        sizes = [int(sets[name][0].shape[0]) for name, _ in wanted]
+        it_all = torch.cat([sets[name][0] for name, _ in wanted]) if wanted else None
+        slot_all = torch.cat([sets[name][1] for name, _ in wanted]) if wanted else None
+        rays_all = tape[it_all, :, slot_all] if wanted else None          # (n_total, 4)
+        inherited = {f: src_fields[f][slot_all] for f in inherit} if wanted else {}
+        off = 0
+        for (name, store), size in zip(wanted, sizes):
+            rays = rays_all[off:off + size]
             out = {k: rays[:, i] for i, k in enumerate(kernels.RAY_FIELDS_2D)}
             if name == "dead" and bool(self.dead_ray_length):
                 for c in "xy":
                     out[c + "_end"] = out[c + "_start"] + self.dead_ray_length * (
                         out[c + "_end"] - out[c + "_start"])
             for f in inherit:
-                out[f] = src_fields[f][slot]
+                out[f] = inherited[f][off:off + size]
             store.append(out)
-            self.last_history_slots[name] = slot
-            self.last_history_iterations[name] = it
+            self.last_history_slots[name] = slot_all[off:off + size]
+            self.last_history_iterations[name] = it_all[off:off + size]
+            off += size
         self.last_projection_result = {}
 
     # ------------------------------------------------------------------ unfused single pass
