@@ -1,0 +1,356 @@
+"""Generate golden vectors from the REFERENCE'S OWN SOURCE (tests/golden/ref_*.npz).
+
+The reference (`/root/reference/tfrt`, pure Python on TensorFlow) cannot be imported as is: TensorFlow,
+tfquaternion and pyvista are absent from this image.  This script puts a stand-in `tensorflow` module
+on `sys.path` (tests/golden/tf_shim/, ~70 tf ops mapped onto the IEEE-equivalent torch float64 ops, with
+`tf.GradientTape` served by torch autograd) and then imports and runs the reference's unmodified
+`tfrt.geometry / engine / operation / materials / boundaries / sources / optimizer` code:
+
+  * function level: `line_triangle_intersect`, `snells_law_3D`, `line_intersect`,
+    `line_circle_intersect`, `snells_law_2D`, `angle_in_interval`, every material;
+  * engine level: `OpticalSystem3D/2D` + `OpticalEngine([StandardReaction()]).ray_trace` on small
+    versions of the BASELINE scenes (lens, light guide, 2D wedge, 2D arc lens), with the history sets
+    in the reference's order and a `slot` field (source-ray id) carried through `simple_ray_inheritance`;
+  * gradient level: the `tf.GradientTape` block of `dev/simple_3d_optimize.py:122-140` (same loss) to the
+    two `ParametricTriangleBoundary.parameters` Variables.
+
+What this pins and what it does not: every line of reference Python on the path executes as written
+(broadcast orientation, where / safe-value structure, inf fill + argmin, merge and compaction order,
+Snell branches, material formulas, vertices -> fields map, the tape); the arithmetic of each individual tf
+op is torch's float64 implementation of the same IEEE operation, not TensorFlow's Eigen kernel.
+
+Runs only in the build container (needs /root/reference); the .npz files are committed and travel.
+
+    python tests/golden/make_reference_golden.py
+"""
+import math
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get("TFRT_REFERENCE", "/root/reference")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# fp32-appropriate epsilons shared with the CUDA parity tests (tests/helpers.py EPS)
+EPS = dict(intersect_epsilion=1e-10, size_epsilion=1e-5, ray_start_epsilion=1e-4)
+RAYS3 = ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")
+RAYS2 = ("x_start", "y_start", "x_end", "y_end")
+
+
+def f32_round(x):
+    return np.asarray(x, dtype=np.float32).astype(np.float64)
+
+
+def import_reference():
+    """Returns the reference's modules, imported from REFERENCE with the tf stand-in."""
+    for p in (REFERENCE, os.path.join(HERE, "tf_shim")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import tensorflow as tf  # the stand-in
+    assert tf.__version__ == "2.shim", "a real tensorflow is importable: use it instead of the shim"
+    import tfrt.boundaries as boundaries
+    import tfrt.engine as engine
+    import tfrt.geometry as geometry
+    import tfrt.materials as materials
+    import tfrt.operation as operation
+    import tfrt.sources as sources
+    import pyvista as pv
+    assert os.path.abspath(engine.__file__).startswith(os.path.abspath(REFERENCE))
+
+    class Ref:
+        pass
+    ref = Ref()
+    ref.tf, ref.pv = tf, pv
+    ref.boundaries, ref.engine, ref.geometry = boundaries, engine, geometry
+    ref.materials, ref.operation, ref.sources = materials, operation, sources
+    return ref
+
+
+def golden_scenes():
+    for p in (ROOT,):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from tensorflowraytrace_b200 import scenes
+    return {
+        "ref_lens3d": scenes.lens_optimize_config(ray_count=192, step_count=3, name="golden"),
+        "ref_guide3d": scenes.config4(ray_count=150, theta_res=8, z_res=5, max_iterations=6),
+        "ref_wedge2d": scenes.config1(ray_count=64),
+        "ref_arclens2d": scenes.arc_lens_2d(ray_count=90),
+    }
+
+
+# ------------------------------------------------------------------------------- engine level
+
+def _polydata(ref, vertices, faces):
+    faces = np.asarray(faces, dtype=np.int64)
+    packed = np.concatenate([np.full((faces.shape[0], 1), 3, dtype=np.int64), faces], axis=1)
+    return ref.pv.PolyData(f32_round(vertices), packed.reshape(-1))
+
+
+def _materials(ref, names):
+    return [{"n": getattr(ref.materials, n)} for n in names]
+
+
+def _manual_source(ref, scene, dimension):
+    src = ref.sources.ManualSource(dimension)
+    n = None
+    for k, v in scene["sources"].items():
+        src[k] = torch.from_numpy(np.ascontiguousarray(f32_round(v)))
+        n = v.shape[0]
+    src["slot"] = torch.arange(n, dtype=torch.float64)
+    return src
+
+
+def reference_engine_3d(ref, scene):
+    """tfrt objects for a 3D scene: parametric surfaces as `ParametricTriangleBoundary` along
+    `FromVectorVG` (pattern of dev/simple_3d_optimize.py:69-81; flip already applied to the scene's
+    faces), static surfaces (zero vectors) and targets as `ManualTriangleBoundary`."""
+    tf = ref.tf
+    optical, params = [], []
+    for s in scene["surfaces"]:
+        mat = {"mat_in": tf.constant(s["mat_in"], dtype=tf.int64),
+               "mat_out": tf.constant(s["mat_out"], dtype=tf.int64)}
+        if np.any(s["vectors"] != 0.0):
+            vec = f32_round(s["vectors"])
+            assert np.allclose(vec, vec[0]) and abs(np.linalg.norm(vec[0]) - 1.0) < 1e-12
+            surf = ref.boundaries.ParametricTriangleBoundary(
+                _polydata(ref, s["zero_points"], s["faces"]),
+                ref.boundaries.FromVectorVG(tuple(vec[0])),
+                initial_parameters=torch.from_numpy(f32_round(s["parameters"])),
+                material_dict=mat)
+            params.append(surf.parameters)
+        else:
+            verts = s["zero_points"] + s["parameters"][:, None] * s["vectors"]
+            surf = ref.boundaries.ManualTriangleBoundary(
+                mesh=_polydata(ref, verts, s["faces"]), material_dict=mat)
+        optical.append(surf)
+    targets = [ref.boundaries.ManualTriangleBoundary(mesh=_polydata(ref, m["vertices"], m["faces"]))
+               for m in scene["targets"]]
+    system = ref.engine.OpticalSystem3D(**EPS)
+    system.optical = optical
+    system.targets = targets
+    system.sources = [_manual_source(ref, scene, 3)]
+    system.materials = _materials(ref, scene["materials"])
+    system.update()
+    inherit = {k for k in scene["sources"] if k not in RAYS3} | {"slot"}
+    eng = ref.engine.OpticalEngine(3, [ref.operation.StandardReaction()], compile_dead_rays=True,
+                                   compile_stopped_rays=True, simple_ray_inheritance=inherit)
+    eng.optical_system = system
+    eng.validate_system()
+    return eng, system, params
+
+
+def reference_engine_2d(ref, scene):
+    tf = ref.tf
+
+    def segs(items, with_mat):
+        out = []
+        for it in items:
+            b = ref.boundaries.ManualSegmentBoundary()
+            b.feed_segments(f32_round(it["segments"]))
+            if with_mat:
+                ref.engine.annotation_helper(b, "mat_in", it["mat_in"], "x_start", dtype=tf.int64)
+                ref.engine.annotation_helper(b, "mat_out", it["mat_out"], "x_start", dtype=tf.int64)
+            out.append(b)
+        return out
+
+    def arcs(items, with_mat):
+        out = []
+        for it in items:
+            b = ref.boundaries.ManualArcBoundary()
+            a = f32_round(it["arcs"])
+            for i, name in enumerate(("x_center", "y_center", "angle_start", "angle_end", "radius")):
+                b[name] = torch.from_numpy(np.ascontiguousarray(a[:, i]))
+            if with_mat:
+                ref.engine.annotation_helper(b, "mat_in", it["mat_in"], "x_center", dtype=tf.int64)
+                ref.engine.annotation_helper(b, "mat_out", it["mat_out"], "x_center", dtype=tf.int64)
+            out.append(b)
+        return out
+
+    system = ref.engine.OpticalSystem2D(**EPS)
+    if scene["optical_segments"]:
+        system.optical_segments = segs(scene["optical_segments"], True)
+    if scene["optical_arcs"]:
+        system.optical_arcs = arcs(scene["optical_arcs"], True)
+    if scene["stop_segments"]:
+        system.stop_segments = segs(scene["stop_segments"], False)
+    if scene["stop_arcs"]:
+        system.stop_arcs = arcs(scene["stop_arcs"], False)
+    if scene["target_segments"]:
+        system.target_segments = segs(scene["target_segments"], False)
+    if scene["target_arcs"]:
+        system.target_arcs = arcs(scene["target_arcs"], False)
+    system.sources = [_manual_source(ref, scene, 2)]
+    system.materials = _materials(ref, scene["materials"])
+    system.update()
+    eng = ref.engine.OpticalEngine(2, [ref.operation.StandardReaction()], compile_dead_rays=True,
+                                   compile_stopped_rays=True,
+                                   simple_ray_inheritance={"wavelength", "slot"})
+    eng.optical_system = system
+    eng.validate_system()
+    return eng, system
+
+
+def _record_sets(out, eng, fields):
+    for set_name in ("active", "finished", "stopped", "dead"):
+        s = getattr(eng, set_name + "_rays")
+        try:
+            slot = s["slot"]
+        except KeyError:
+            continue
+        if slot.shape[0] == 0:
+            continue
+        out[f"{set_name}_slot"] = slot.numpy().astype(np.int64)
+        for f in fields:
+            out[f"{set_name}_{f}"] = s[f].numpy().astype(np.float64)
+        if set_name == "finished":
+            out["finished_wavelength"] = s["wavelength"].numpy().astype(np.float64)
+
+
+def run_reference(ref, name, scene):
+    tf = ref.tf
+    out = {}
+    if scene["dimension"] == 3:
+        eng, system, params = reference_engine_3d(ref, scene)
+        if "goal_scale" in scene:
+            # the tape block of dev/simple_3d_optimize.py:128-140, verbatim structure
+            with tf.GradientTape() as tape:
+                eng.optical_system.update()
+                eng.clear_ray_history()
+                eng.ray_trace(scene["max_iterations"])
+                output = tf.stack([eng.finished_rays["y_end"], eng.finished_rays["z_end"]], axis=1)
+                goal = eng.finished_rays["rank"]
+                goal = goal * scene["goal_scale"]
+                error = tf.math.squared_difference(output, goal)
+                grads = tape.gradient(error, params)
+            for i, g in enumerate(grads):
+                out[f"grad_{i}"] = g.numpy()
+            out["loss"] = np.array(float(error.sum()))
+        else:
+            eng.ray_trace(scene["max_iterations"])
+        _record_sets(out, eng, RAYS3)
+        # merged triangle fields as the reference built them (vertices -> fields map)
+        for f in ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2", "norm"):
+            out[f"merged_{f}"] = system._merged[f].numpy().astype(np.float64)
+        out["merged_catagory"] = system._merged["catagory"].numpy().astype(np.int64)
+    else:
+        eng, system = reference_engine_2d(ref, scene)
+        eng.ray_trace(scene["max_iterations"])
+        _record_sets(out, eng, RAYS2)
+    return out
+
+
+# ------------------------------------------------------------------------------- function level
+
+def function_vectors(ref):
+    """Random-input known answers straight out of tfrt/geometry.py and tfrt/materials.py."""
+    tf, g = ref.tf, ref.geometry
+    rng = np.random.default_rng(20261018)
+    out = {}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+
+    # 3D: line_triangle_intersect (geometry.py:191-320): N rays x M triangles -> (M, N)
+    n, m = 40, 25
+    rs = rng.normal(size=(n, 3)) * 0.5 + np.array([-3.0, 0.0, 0.0])
+    re = rs + rng.normal(size=(n, 3)) * 0.3 + np.array([1.0, 0.0, 0.0])
+    p0 = rng.normal(size=(m, 3))
+    p1 = p0 + rng.normal(size=(m, 3))
+    p2 = p0 + rng.normal(size=(m, 3))
+    p1[0] = p0[0] + (p2[0] - p0[0]) * 2.0            # a degenerate (zero-area) triangle
+    re[1] = rs[1] + (p1[3] - p0[3])                  # a ray parallel to triangle 3's plane
+    args = [T(rs[:, i]) for i in range(3)] + [T(re[:, i]) for i in range(3)]
+    for p in (p0, p1, p2):
+        args += [T(p[:, i]) for i in range(3)]
+    res = g.line_triangle_intersect(*args, 1e-10)
+    out["tri_in_rays"] = np.concatenate([rs, re], axis=1)
+    out["tri_in_tris"] = np.concatenate([p0, p1, p2], axis=1)
+    for key, val in zip(("x", "y", "z", "valid", "ray_u", "trig_u", "trig_v"), res):
+        out[f"tri_{key}"] = val.numpy()
+
+    # 3D: snells_law_3D (geometry.py:671-753): refraction both ways, TIR, mirror, zero indices
+    k = 64
+    s = rng.normal(size=(k, 3))
+    e = s + rng.normal(size=(k, 3))
+    nrm = rng.normal(size=(k, 3))
+    n_in = rng.choice([1.0, 1.33, 1.5, 2.4, 0.0], size=k, p=[0.2, 0.2, 0.3, 0.2, 0.1])
+    n_out = rng.choice([1.0, 1.33, 1.5, 0.0], size=k, p=[0.5, 0.2, 0.2, 0.1])
+    res = g.snells_law_3D(*[T(s[:, i]) for i in range(3)], *[T(e[:, i]) for i in range(3)],
+                          T(nrm), T(n_in), T(n_out), tf.constant(1.5, dtype=tf.float64))
+    out["snell3_in"] = np.concatenate([s, e, nrm, n_in[:, None], n_out[:, None]], axis=1)
+    out["snell3_out"] = np.stack([r.numpy() for r in res], axis=1)
+
+    # 2D: line_intersect (geometry.py:27-167) -> (M, N), incl. a parallel pair
+    n, m = 30, 12
+    a = rng.normal(size=(n, 4))
+    b = rng.normal(size=(m, 4))
+    b[2, 2:] = b[2, :2] + (a[4, 2:] - a[4, :2]) * 1.7
+    res = g.line_intersect(*[T(a[:, i]) for i in range(4)], *[T(b[:, i]) for i in range(4)], 1e-10)
+    out["seg_in_first"], out["seg_in_second"] = a, b
+    for key, val in zip(("x", "y", "valid", "u", "v"), res):
+        out[f"seg_{key}"] = val.numpy()
+
+    # 2D: line_circle_intersect (geometry.py:338-547): both roots, incl. misses and a tangent
+    n, m = 30, 9
+    a = rng.normal(size=(n, 4)) * 1.5
+    c = np.concatenate([rng.normal(size=(m, 2)), rng.uniform(0.3, 2.0, size=(m, 1))], axis=1)
+    a[0] = [-5.0, c[0, 1] + c[0, 2], 5.0, c[0, 1] + c[0, 2]]        # tangent to circle 0
+    res = g.line_circle_intersect(*[T(a[:, i]) for i in range(4)], *[T(c[:, i]) for i in range(3)],
+                                  1e-10)
+    out["circ_in_lines"], out["circ_in_circles"] = a, c
+    plus, minus = res
+    for tag, d in (("plus", plus), ("minus", minus)):
+        for key in ("x", "y", "valid", "u", "v"):
+            out[f"circ_{tag}_{key}"] = d[key].numpy()
+
+    # 2D: snells_law_2D (geometry.py:565-653), norms as angles
+    k = 64
+    s = rng.normal(size=(k, 2))
+    e = s + rng.normal(size=(k, 2))
+    ang = rng.uniform(-math.pi, math.pi, size=k)
+    n_in = rng.choice([1.0, 1.33, 1.5, 2.4, 0.0], size=k, p=[0.2, 0.2, 0.3, 0.2, 0.1])
+    n_out = rng.choice([1.0, 1.33, 1.5, 0.0], size=k, p=[0.5, 0.2, 0.2, 0.1])
+    res = g.snells_law_2D(T(s[:, 0]), T(s[:, 1]), T(e[:, 0]), T(e[:, 1]), T(ang), T(n_in), T(n_out),
+                          tf.constant(0.75, dtype=tf.float64))
+    out["snell2_in"] = np.concatenate([s, e, ang[:, None], n_in[:, None], n_out[:, None]], axis=1)
+    out["snell2_out"] = np.stack([r.numpy() for r in res], axis=1)
+
+    # angle_in_interval (geometry.py:766-802), wrap-around windows included
+    k = 200
+    ang = rng.uniform(-2 * math.pi, 2 * math.pi, size=k)
+    a1 = rng.uniform(-math.pi, 2 * math.pi, size=k)
+    a2 = rng.uniform(-math.pi, 2 * math.pi, size=k)
+    out["angle_in"] = np.stack([ang, a1, a2], axis=1)
+    out["angle_out"] = g.angle_in_interval(T(ang), T(a1), T(a2)).numpy()
+
+    # materials (materials.py:25-104), wavelength in nm
+    wl = np.linspace(380.0, 780.0, 41)
+    out["mat_wavelength"] = wl
+    for name in ("vacuum", "acrylic", "crown_glass", "flint_glass", "fused_silica", "polycarbonate",
+                 "soda_lime", "reflective"):
+        out[f"mat_{name}"] = np.broadcast_to(
+            np.asarray(getattr(ref.materials, name)(T(wl)), dtype=np.float64), wl.shape).copy()
+    out["mat_constant_1p7"] = np.asarray(ref.materials.build_constant_material(1.7)(T(wl)),
+                                         dtype=np.float64)
+    return out
+
+
+def main():
+    ref = import_reference()
+    data = function_vectors(ref)
+    path = os.path.join(HERE, "ref_functions.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    for name, scene in golden_scenes().items():
+        data = run_reference(ref, name, scene)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **data)
+        sizes = {k: v.shape for k, v in data.items() if k.endswith("_slot")}
+        print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes, sets {sizes}")
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ def f32_round(x):
 
 
 def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round_inputs=True,
-                      **engine_kwargs):
+                      fp32_vertices=True, **engine_kwargs):
     """Returns (engine, parameters list).  Inputs are rounded through fp32 (vertices are formed in
     fp64 from fp32-rounded zero points / vectors / parameters, then the *fields* are what they
     are: the kernel computes vertices in fp32, see `round_vertices`)."""
@@ -39,7 +39,7 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
         zero = torch.from_numpy(rnd(s["zero_points"]))
         vec = torch.from_numpy(rnd(s["vectors"]))
         verts = ob.parametric_vertices(zero, vec, p)
-        if round_inputs:
+        if round_inputs and fp32_vertices:
             # The CUDA path stores vertices as fp32 fields, formed in fp32 (one multiply, one
             # add, no contraction).  Give the oracle exactly those values -- with a
             # straight-through gradient, so autograd still reaches the parameters.

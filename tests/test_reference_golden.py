@@ -1,0 +1,205 @@
+"""Pins against the REFERENCE'S OWN CODE.
+
+tests/golden/ref_*.npz were produced by tests/golden/make_reference_golden.py, which imports the
+unmodified reference (`tfrt.geometry / engine / operation / materials / boundaries / sources`) in the
+build container with a stand-in `tensorflow` module (tests/golden/tf_shim: each tf op mapped to the
+IEEE-equivalent torch float64 op, GradientTape -> torch autograd).  So every line of reference Python
+on the hot path ran as written to make these vectors.
+
+CPU (`not gpu`): the oracle restatement reproduces them to float64 rounding -- functions, whole traces
+(history sets in reference order), the vertices -> fields map, and the GradientTape gradients of
+dev/simple_3d_optimize.py's loss.  GPU: the CUDA path reproduces them through the public API within
+the north-star tolerances (hit membership exact, points / directions 1e-5, gradients 1e-4)."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import geometry as og
+from oracle import materials as om
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_reference_golden as mrg  # noqa: E402  (imports neither the shim nor the reference)
+
+SCENES = mrg.golden_scenes()
+SETS = ("active", "finished", "stopped", "dead")
+
+
+def load(name):
+    return dict(np.load(os.path.join(HERE, "golden", f"{name}.npz")))
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def close(a, b, tol=1e-12):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return bool(np.all(np.abs(a - b) <= tol * (1.0 + np.abs(b))))
+
+
+# ------------------------------------------------------------------------------------ functions
+
+def test_functions_line_triangle_intersect():
+    ref = load("ref_functions")
+    r, t = ref["tri_in_rays"], ref["tri_in_tris"]
+    args = [T(r[:, i]) for i in range(6)] + [T(t[:, i]) for i in range(9)]
+    got = og.line_triangle_intersect(*args, 1e-10)
+    valid = ref["tri_valid"]
+    assert np.array_equal(got[3].numpy(), valid)
+    assert valid.shape == (t.shape[0], r.shape[0])          # (triangles, rays): geometry.py:238-251
+    assert not valid[0].any() and not valid[3, 1]            # the degenerate / parallel cases
+    for i, key in enumerate(("x", "y", "z", "valid", "ray_u", "trig_u", "trig_v")):
+        assert close(got[i].numpy(), ref[f"tri_{key}"]), key    # garbage-where-invalid included
+
+
+def test_functions_snells_law_3d():
+    ref = load("ref_functions")
+    a = ref["snell3_in"]
+    got = og.snells_law_3D(*[T(a[:, i]) for i in range(6)], T(a[:, 6:9]), T(a[:, 9]), T(a[:, 10]),
+                           torch.tensor(1.5, dtype=torch.float64))
+    assert close(np.stack([g.numpy() for g in got], axis=1), ref["snell3_out"])
+
+
+def test_functions_2d():
+    ref = load("ref_functions")
+    a, b = ref["seg_in_first"], ref["seg_in_second"]
+    got = og.line_intersect(*[T(a[:, i]) for i in range(4)], *[T(b[:, i]) for i in range(4)], 1e-10)
+    for i, key in enumerate(("x", "y", "valid", "u", "v")):
+        assert close(got[i].numpy(), ref[f"seg_{key}"]), key
+    a, c = ref["circ_in_lines"], ref["circ_in_circles"]
+    plus, minus = og.line_circle_intersect(*[T(a[:, i]) for i in range(4)],
+                                           *[T(c[:, i]) for i in range(3)], 1e-10)
+    for tag, d in (("plus", plus), ("minus", minus)):
+        for key in ("x", "y", "valid", "u", "v"):
+            assert close(d[key].numpy(), ref[f"circ_{tag}_{key}"], 1e-10), (tag, key)
+    a = ref["snell2_in"]
+    got = og.snells_law_2D(*[T(a[:, i]) for i in range(7)], torch.tensor(0.75, dtype=torch.float64))
+    assert close(np.stack([g.numpy() for g in got], axis=1), ref["snell2_out"], 1e-11)
+    a = ref["angle_in"]
+    assert np.array_equal(og.angle_in_interval(T(a[:, 0]), T(a[:, 1]), T(a[:, 2])).numpy(),
+                          ref["angle_out"])
+
+
+def test_functions_materials():
+    ref = load("ref_functions")
+    wl = T(ref["mat_wavelength"])
+    for name in ("vacuum", "acrylic", "crown_glass", "flint_glass", "fused_silica", "polycarbonate",
+                 "soda_lime", "reflective"):
+        got = np.broadcast_to(np.asarray(om.BY_NAME[name](wl), dtype=np.float64), wl.shape)
+        assert close(got, ref[f"mat_{name}"], 1e-14), name
+    assert close(np.asarray(om.build_constant_material(1.7)(wl)), ref["mat_constant_1p7"])
+
+
+# ------------------------------------------------------------------------------------ traces (CPU)
+
+def _oracle_trace(name):
+    scene = SCENES[name]
+    if scene["dimension"] == 3:
+        grad = "goal_scale" in scene
+        eng, params = helpers.oracle_from_scene(scene, requires_grad=grad, fp32_vertices=False,
+                                                compile_dead_rays=True, compile_stopped_rays=True)
+        fields = helpers.RAY_FIELDS
+    else:
+        eng, params = helpers.oracle2d_from_scene(scene, compile_dead_rays=True,
+                                                  compile_stopped_rays=True)
+        fields = helpers.RAY_FIELDS_2D
+    eng.ray_trace(scene["max_iterations"])
+    return scene, eng, params, fields
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_oracle_matches_reference_trace(name):
+    want = load(name)
+    scene, eng, params, fields = _oracle_trace(name)
+    seen = 0
+    for set_name in SETS:
+        s = getattr(eng, set_name + "_rays")
+        n = int(s["slot"].shape[0]) if bool(s) else 0
+        if f"{set_name}_slot" not in want:
+            assert n == 0, set_name
+            continue
+        # same membership in the same (reference) order
+        assert np.array_equal(s["slot"].detach().numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
+        for f in fields:
+            assert close(s[f].detach().numpy(), want[f"{set_name}_{f}"], 1e-10), (set_name, f)
+        seen += n
+    assert seen > 0
+    if "merged_xp" in want:
+        merged = eng.optical_system._merged if hasattr(eng.optical_system, "_merged") else None
+        if merged is not None:
+            for f in ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2", "norm"):
+                assert close(merged[f].detach().numpy(), want[f"merged_{f}"], 1e-13), f
+            assert np.array_equal(merged["catagory"].numpy(), want["merged_catagory"])
+    if "grad_0" in want:
+        fin = eng.finished_rays
+        goal = scene["goal_scale"] * fin["rank"]
+        err = (fin["y_end"] - goal[:, 0]) ** 2 + (fin["z_end"] - goal[:, 1]) ** 2
+        assert abs(float(err.sum().detach()) - float(want["loss"])) < 1e-11 * abs(float(want["loss"]))
+        for i, g in enumerate(torch.autograd.grad(err.sum(), params)):
+            assert helpers.rel_err(g.numpy(), want[f"grad_{i}"]) < 1e-9, i
+
+
+# ------------------------------------------------------------------------------------ traces (GPU)
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_cuda_path_matches_reference_trace(name):
+    from tensorflowraytrace_b200 import scenes
+    scene, want = SCENES[name], load(name)
+    if scene["dimension"] == 3:
+        engine, params, _ = scenes.build_engine(scene, eps=helpers.EPS, compile_dead_rays=True,
+                                                compile_stopped_rays=True)
+        fields = helpers.RAY_FIELDS
+    else:
+        engine, params, _ = scenes.build_engine_2d(scene, eps=helpers.EPS, compile_dead_rays=True,
+                                                   compile_stopped_rays=True)
+        fields = helpers.RAY_FIELDS_2D
+    engine.ray_trace(scene["max_iterations"])
+    for set_name in SETS:
+        got = getattr(engine, set_name + "_rays")
+        if f"{set_name}_slot" not in want:
+            assert not bool(got) or got["x_start"].shape[0] == 0, set_name
+            continue
+        slot = engine.last_history_slots[set_name].cpu().numpy().astype(np.int64)
+        assert np.array_equal(slot, want[f"{set_name}_slot"]), set_name      # bit-exact membership / order
+        for f in fields:
+            assert helpers.rel_err(got[f].detach().cpu().numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+    if "grad_0" in want:
+        err = scenes.imaging_error(scene)(engine)
+        grads = torch.autograd.grad(err.sum(), params)
+        assert abs(float(err.sum().detach()) - float(want["loss"])) < 1e-5 * abs(float(want["loss"]))
+        for i, g in enumerate(grads):
+            assert helpers.rel_err(g.cpu().numpy(), want[f"grad_{i}"]) < 1e-4, i
+
+
+@pytest.mark.gpu
+def test_cuda_intersection_seam_matches_reference_function():
+    """`OpticalSystem3D._intersection` on the reference's own line_triangle_intersect
+    vectors: same winner per ray as argmin over the reference's (M, N) ray_u, same hit point."""
+    from tensorflowraytrace_b200 import engine as eng
+    ref = load("ref_functions")
+    r, t = ref["tri_in_rays"], ref["tri_in_tris"]
+    valid = ref["tri_valid"] & (ref["tri_trig_u"] >= -1e-5) & (ref["tri_trig_v"] >= -1e-5) \
+        & (ref["tri_trig_u"] + ref["tri_trig_v"] <= 1 + 1e-5) & (ref["tri_ray_u"] >= 1e-4)
+    u = np.where(valid, ref["tri_ray_u"], np.inf)
+    want_tri = np.where(valid.any(axis=0), u.argmin(axis=0), -1)
+    dev = torch.device("cuda:0")
+    args = [torch.tensor(r[:, i], dtype=torch.float32, device=dev) for i in range(6)] + \
+           [torch.tensor(t[:, i], dtype=torch.float32, device=dev) for i in range(9)]
+    x, y, z, ok, ray_u, trig_u, trig_v, gather_ray, gather_trig = eng.OpticalSystem3D._intersection(
+        *args, 1e-10, 1e-5, 1e-4)
+    ok = ok.cpu().numpy()
+    got_tri = np.where(ok, gather_trig.cpu().numpy(), -1)
+    assert np.array_equal(got_tri, want_tri)
+    hit = ok.nonzero()[0]
+    assert hit.size > 3
+    for name, arr in (("x", x), ("y", y), ("z", z), ("ray_u", ray_u)):
+        want = ref[f"tri_{name}"][want_tri[hit], hit]
+        assert helpers.rel_err(arr.cpu().numpy()[hit], want) < 1e-5, name
