@@ -198,6 +198,40 @@ def config4(ray_count=4194304, theta_res=100, z_res=250, seed=4321, max_iteratio
     }
 
 
+
+def mirror_stop_3d(ray_count=256, step_count=3, seed=99):
+    """Every 3D category and reaction branch in one small scene: the imaging lens of
+    `lens_optimize_config` (refraction in and out, six wavelengths through dispersive crown glass),
+    a square aperture stop that clips part of the beam behind the lens, a tilted flat mirror
+    (`reflective`, n = 0 => reflection, tfrt/geometry.py:747-749) folding the beam towards -y, and
+    a target plane at y = -6; rays that leave the lens rim or miss the mirror die."""
+    rng = np.random.default_rng(seed)
+    base, rank = random_uniform_square(0.2, ray_count, rng)
+    dirs = random_uniform_sphere(math.pi / 14.0, ray_count, rng)
+    starts = np.stack([np.full(ray_count, -4.0), base[:, 0], base[:, 1]], axis=1)
+    wl = np.asarray(RAINBOW_6, dtype=np.float64)[np.arange(ray_count) % 6]
+    sources = make_rays(starts, dirs, wl, extra={"rank": rank})
+    surfaces = lens_surfaces(step_count)
+    # mirror: square of half-size 1.5 centred at (3, 0, 0), plane rotated 45 degrees about z
+    mv, mf = mesh_tools.plane_mesh((0.0, 0.0, 0.0), 1.5, axis=0)
+    c, s_ = math.cos(math.pi / 4), math.sin(math.pi / 4)
+    mv = np.stack([c * mv[:, 0] - s_ * mv[:, 1], s_ * mv[:, 0] + c * mv[:, 1], mv[:, 2]], axis=1)
+    mv[:, 0] += 3.0
+    mirror = {"zero_points": mv, "vectors": np.zeros_like(mv), "parameters": np.zeros(mv.shape[0]),
+              "faces": mf[:, ::-1].copy(), "mat_in": 2, "mat_out": 0}
+    sv, sf = mesh_tools.plane_mesh((1.5, 0.55, 0.0), 0.45, axis=0)
+    tv, tf_ = mesh_tools.plane_mesh((3.0, -6.0, 0.0), 20.0, axis=1)
+    return {
+        "name": f"mirror_stop_3d_{ray_count}rays_hex{step_count}",
+        "dimension": 3,
+        "sources": sources,
+        "surfaces": surfaces + [mirror],
+        "targets": [static_mesh(tv, tf_)],
+        "stops": [static_mesh(sv, sf)],
+        "materials": ["vacuum", "crown_glass", "reflective"],
+        "max_iterations": 5,
+    }
+
 # ----------------------------------------------------------------------------- 2D configs
 
 def rays_2d(starts, angles, wavelengths, ray_length=1.0):

@@ -78,6 +78,7 @@ def golden_scenes():
     return {
         "ref_lens3d": scenes.lens_optimize_config(ray_count=192, step_count=3, name="golden"),
         "ref_guide3d": scenes.config4(ray_count=150, theta_res=8, z_res=5, max_iterations=6),
+        "ref_mirror_stop3d": scenes.mirror_stop_3d(),
         "ref_wedge2d": scenes.config1(ray_count=64),
         "ref_arclens2d": scenes.arc_lens_2d(ray_count=90),
     }
@@ -132,6 +133,9 @@ def reference_engine_3d(ref, scene):
                for m in scene["targets"]]
     system = ref.engine.OpticalSystem3D(**EPS)
     system.optical = optical
+    if scene["stops"]:
+        system.stops = [ref.boundaries.ManualTriangleBoundary(
+            mesh=_polydata(ref, m["vertices"], m["faces"])) for m in scene["stops"]]
     system.targets = targets
     system.sources = [_manual_source(ref, scene, 3)]
     system.materials = _materials(ref, scene["materials"])
@@ -338,12 +342,131 @@ def function_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- sources (8(f) rank 2)
+
+def source_cases():
+    """name -> (kind, constructor arguments) shared by the generator (reference classes) and the test
+    (tensorflowraytrace_b200 classes).  Only deterministic (Static*) distributions.  2D Point /
+    AngularSource cannot be built in the reference at HEAD (`center` setter rejects vectors,
+    tfrt/sources.py:657-666, :889-898) and are therefore absent."""
+    PI = math.pi
+    return {
+        "dist_uniform_angular": ("StaticUniformAngularDistribution", (-0.2, 0.3, 7), {}),
+        "dist_lambertian_angular": ("StaticLambertianAngularDistribution", (-1.0, 0.5, 9), {}),
+        "dist_beam": ("StaticUniformBeam", (-1.5, 1.5, 6), {}),
+        "dist_beam_rotated": ("StaticUniformBeam", (-1.0, 3.0, 5), {"central_angle": PI / 2}),
+        "dist_aperature": ("StaticUniformAperaturePoints", ((0.0, -1.0), (2.0, 1.0), 5), {}),
+        "dist_square": ("StaticUniformSquare", (2.0, 3, 1.0, 4), {}),
+        "dist_circle": ("StaticUniformCircle", (50,), {"radius": 2.0}),
+        "dist_sphere": ("StaticUniformSphere", (PI / 8, 40), {}),
+        "dist_lambertian_sphere": ("StaticLambertianSphere", (PI / 3, 40), {}),
+        "src_point3d": ("PointSource", (3, (-1.0, 0.0, 0.0), (1.0, 0.0, 0.0),
+                                        ("StaticUniformSphere", (PI / 8, 12), {}), [575.0, 450.0]), {}),
+        "src_point3d_rotated": ("PointSource", (3, (-1.0, 0.5, 0.25), (1.0, 1.0, 0.0),
+                                                ("StaticUniformSphere", (PI / 8, 12), {}), [575.0]),
+                                {"ray_length": 2.5}),
+        "src_angular3d_dense": ("AngularSource", (3, (-4.0, 0.0, 0.0), (1.0, 0.0, 0.0),
+                                                  ("StaticUniformSphere", (PI / 16, 5), {}),
+                                                  ("StaticUniformSquare", (0.2, 3), {}), [575.0, 680.0]), {}),
+        "src_angular3d_undense": ("AngularSource", (3, (-4.0, 0.1, 0.0), (1.0, 0.0, 0.0),
+                                                    ("StaticUniformSphere", (PI / 16, 9), {}),
+                                                    ("StaticUniformSquare", (0.2, 3), {}), [575.0] * 9),
+                                  {"dense": False}),
+        "src_aperature2d": ("AperatureSource", (2, ("StaticUniformAperaturePoints", ((0.0, -1.0), (0.0, 1.0), 3), {}),
+                                                ("StaticUniformAperaturePoints", ((2.0, -1.0), (2.0, 1.0), 4), {}),
+                                                [575.0, 450.0]), {}),
+    }
+
+
+def build_case(dist_mod, src_mod, spec):
+    """Instantiate a case from `source_cases()` with the given distributions / sources modules."""
+    kind, args, kwargs = spec
+
+    def arg(a):
+        if isinstance(a, tuple) and len(a) == 3 and isinstance(a[0], str) and isinstance(a[2], dict):
+            return build_case(dist_mod, src_mod, a)
+        return a
+    cls = getattr(src_mod, kind, None) or getattr(dist_mod, kind)
+    return cls(*[arg(a) for a in args], **kwargs)
+
+
+def source_vectors(ref):
+    import tfrt.distributions as rd
+    out = {}
+    for name, spec in source_cases().items():
+        obj = build_case(rd, ref.sources, spec)
+        if name.startswith("dist_"):
+            for attr in ("angles", "points", "ranks"):
+                if hasattr(obj, attr) and getattr(obj, attr) is not None:
+                    out[f"{name}__{attr}"] = np.asarray(getattr(obj, attr), dtype=np.float64)
+        else:
+            for key in sorted(obj.keys()):
+                out[f"{name}__{key}"] = np.asarray(obj[key], dtype=np.float64)
+    return out
+
+
+# ------------------------------------------------------------------------------- optimiser (8(f) rank 1)
+
+OPT_STEPS = ((1.0, 0.0), (1.0, 0.6), (0.5, 0.6), (0.5, 0.3))     # (lr_scale, momentum) per step
+OPT_KW = dict(learning_rate=0.004, individual_lr=[1.0, 0.5])
+
+
+def optimizer_scene():
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import scenes
+    return scenes.lens_optimize_config(ray_count=160, step_count=3, seed=77, name="golden_opt")
+
+
+def optimizer_accumulators(scene):
+    """A synthetic dense accumulator for the first surface (the reference only requires a (V, V)
+    matrix, tfrt/optimizer.py:251-256), none for the second."""
+    v = scene["surfaces"][0]["parameters"].shape[0]
+    rng = np.random.default_rng(5)
+    acc = (rng.uniform(size=(v, v)) < 0.15).astype(np.float64) + np.eye(v)
+    return [acc, None]
+
+
+def optimizer_vectors(ref):
+    """`tfrt.optimizer.SGD_Optimizer.single_step` (Keras SGD(nesterov=True) at its default 0.01 step,
+    tfrt/optimizer.py:103, :284-320) driving the reference engine: parameter trajectories."""
+    import tfrt.optimizer as ropt
+    tf = ref.tf
+    scene = optimizer_scene()
+    eng, system, params = reference_engine_3d(ref, scene)
+    goal_scale = scene["goal_scale"]
+
+    def error_function(engine):
+        output = tf.stack([engine.finished_rays["y_end"], engine.finished_rays["z_end"]], axis=1)
+        return tf.math.squared_difference(output, engine.finished_rays["rank"] * goal_scale)
+
+    opt = ropt.SGD_Optimizer(eng, params, error_function, scene["max_iterations"], **OPT_KW)
+    accs = [None if a is None else torch.from_numpy(a) for a in optimizer_accumulators(scene)]
+    out = {"initial_0": params[0].numpy().copy(), "initial_1": params[1].numpy().copy()}
+    grads, err = opt.process_gradient(accs)
+    out["processed_0"], out["processed_1"] = grads[0].numpy(), grads[1].numpy()
+    out["mean_error_0"] = np.array(float(err))
+    errors = []
+    for k, (lr_scale, momentum) in enumerate(OPT_STEPS):
+        errors.append(float(opt.single_step(accs, lr_scale=lr_scale, momentum=momentum)))
+        out[f"step{k}_0"], out[f"step{k}_1"] = params[0].numpy().copy(), params[1].numpy().copy()
+    out["errors"] = np.array(errors)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
     path = os.path.join(HERE, "ref_functions.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = source_vectors(ref)
+    path = os.path.join(HERE, "ref_sources.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = optimizer_vectors(ref)
+    path = os.path.join(HERE, "ref_optimizer.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, errors {data['errors']}")
     for name, scene in golden_scenes().items():
         data = run_reference(ref, name, scene)
         path = os.path.join(HERE, f"{name}.npz")

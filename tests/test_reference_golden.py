@@ -203,3 +203,68 @@ def test_cuda_intersection_seam_matches_reference_function():
     for name, arr in (("x", x), ("y", y), ("z", z), ("ray_u", ray_u)):
         want = ref[f"tri_{name}"][want_tri[hit], hit]
         assert helpers.rel_err(arr.cpu().numpy()[hit], want) < 1e-5, name
+
+
+# ------------------------------------------------------------------------------------ sources
+
+SOURCE_CASES = mrg.source_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SOURCE_CASES))
+def test_sources_and_distributions_match_reference(name):
+    """8(f) rank 2: our distributions / sources (fp32 fields) against the arrays the reference's own
+    classes produced for the same constructor arguments (tfrt/distributions.py, tfrt/sources.py)."""
+    from tensorflowraytrace_b200 import distributions as D
+    from tensorflowraytrace_b200 import sources as S
+    ref = load("ref_sources")
+    obj = mrg.build_case(D, S, SOURCE_CASES[name])
+    checked = 0
+    for key, want in ref.items():
+        case, attr = key.split("__")
+        if case != name:
+            continue
+        got = getattr(obj, attr) if name.startswith("dist_") else obj[attr]
+        got = got.detach().cpu().numpy().astype(np.float64)
+        assert got.shape == want.shape, (key, got.shape, want.shape)
+        assert np.allclose(got, want, rtol=2e-6, atol=2e-6), (key, np.abs(got - want).max())
+        checked += 1
+    assert checked >= 2
+
+
+# ------------------------------------------------------------------------------------ optimiser
+
+@pytest.mark.gpu
+def test_optimizer_trajectory_matches_reference():
+    """8(f) rank 1: `SGD_Optimizer.process_gradient / single_step` (lr scaling, common clip, dense vs
+    sparse accumulator, Keras SGD(nesterov=True) at its default 0.01 step, momentum schedule) on the
+    CUDA path against the parameter trajectory of the reference's own `tfrt.optimizer.SGD_Optimizer`
+    driving the reference engine."""
+    import scipy.sparse as sp
+    from tensorflowraytrace_b200 import mesh_tools, optimizer, scenes
+    want = load("ref_optimizer")
+    scene = mrg.optimizer_scene()
+    engine, params, _ = scenes.build_engine(scene, eps=helpers.EPS)
+    goal_scale = float(scene["goal_scale"])
+
+    def error_function(eng):
+        fin = eng.finished_rays
+        output = torch.stack([fin["y_end"], fin["z_end"]], dim=1)
+        return (output - fin["rank"] * goal_scale) ** 2
+
+    opt = optimizer.SGD_Optimizer(engine, params, error_function, scene["max_iterations"], **mrg.OPT_KW)
+    acc0, _ = mrg.optimizer_accumulators(scene)
+    accs = [mesh_tools.to_torch_sparse(sp.csr_matrix(acc0), "cuda"), None]
+    for i in range(2):
+        assert helpers.rel_err(params[i].detach().cpu().numpy(), want[f"initial_{i}"]) < 1e-6
+    grads, err = opt.process_gradient(accs)
+    assert abs(float(err) - float(want["mean_error_0"])) < 1e-5 * float(want["mean_error_0"])
+    for i in range(2):
+        assert helpers.rel_err(grads[i].cpu().numpy(), want[f"processed_{i}"]) < 1e-4, i
+    assert float(np.abs(want["processed_1"]).max()) == pytest.approx(10 * mrg.OPT_KW["learning_rate"])  # clip hit
+    for k, (lr_scale, momentum) in enumerate(mrg.OPT_STEPS):
+        e = opt.single_step(accs, lr_scale=lr_scale, momentum=momentum)
+        assert abs(float(e) - float(want["errors"][k])) < 1e-4 * float(want["errors"][k]), k
+        for i in range(2):
+            moved = np.abs(want[f"step{k}_{i}"] - want[f"initial_{i}"]).max()
+            diff = np.abs(params[i].detach().cpu().numpy() - want[f"step{k}_{i}"]).max()
+            assert diff < 2e-4 * moved + 1e-7, (k, i, diff, moved)
