@@ -47,16 +47,26 @@ constexpr int kThreads = TFRT_K1_THREADS;
 constexpr int kStages = TFRT_K1_STAGES;
 constexpr int kUnroll = TFRT_K1_UNROLL;
 
+constexpr int kItemQueue = 8;   // published work items in flight (the producer is at most
+                                // kStages + 1 items ahead of the slowest consumer warp)
+
 struct __align__(16) IntersectSmem {
     float4 tile[kStages][TFRT_TILE_TRIS * 3];
     uint64_t full[kStages];
     uint64_t empty[kStages];
+    uint64_t item_ready[kItemQueue];
+    int32_t item[kItemQueue];
+    // producer state, touched by thread 0 only (kept out of every thread's registers)
+    uint32_t p_g;          // next tile sequence number to issue
+    int32_t p_items;       // items published so far
+    int32_t p_tile, p_tiles, p_tile_begin;
+    int32_t p_done;
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
-template <int R2>
+template <int R2, bool kQueue>
 __global__ void __launch_bounds__(kThreads, (R2 >= 4 ? TFRT_K1_MINBLOCKS : 1))
 k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const float *__restrict__ sz, const float *__restrict__ ex,
@@ -68,12 +78,19 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               unsigned int *__restrict__ work_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IntersectSmem &sm = *reinterpret_cast<IntersectSmem *>(smem_raw);
-    __shared__ int s_item;
 
     // Persistent CTAs pull work items (ray block x triangle split) from a global counter, so
     // the tail of a launch is one item, not one wave, whatever the live count turns out to be
     // (it is only known on the device).  Consecutive items are different ray blocks of the
     // same split: neighbouring CTAs stream the same triangle tiles out of L2.
+    //
+    // kQueue (long items, 8 rays per thread): no CTA-wide barrier separates items.  The elected
+    // producer thread fetches the next item when its tile stream reaches it, publishes the id
+    // through a small mbarrier-guarded queue and keeps the TMA ring kStages tiles ahead ACROSS
+    // item boundaries; each warp crosses into the next item on its own (its rays, its epilogue),
+    // so warps only ever wait for tiles.  The price is that a CTA claims items up to kStages
+    // tiles before it starts them, which unbalances launches made of few, short items.
+    // !kQueue (short items): one item at a time, fetched between two __syncthreads.
     const int n_live = n_live_ptr ? *n_live_ptr : n_live_static;
     const int rays_per_cta = kThreads * 2 * R2;
     const int ray_blocks = (n_live + rays_per_cta - 1) / rays_per_cta;
@@ -86,11 +103,41 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], kThreads / 32);
         }
+        if constexpr (kQueue) {
+#pragma unroll
+            for (int q = 0; q < kItemQueue; ++q) mbar_init(&sm.item_ready[q], 1);
+            sm.p_g = 0; sm.p_items = 0; sm.p_tile = 0; sm.p_tiles = 0; sm.p_tile_begin = 0;
+            sm.p_done = 0;
+        }
         mbar_fence_init();
     }
-    uint32_t seq = 0;   // tiles this CTA has pushed through the ring so far (stage / parity)
+    if constexpr (kQueue) __syncthreads();
 
-    // producer: tile `g` of the CTA's running sequence <- global tile `tile`
+    // ---- producer, kQueue (thread 0 only): issue the next tile of the stream, fetching items
+    // as the stream reaches them
+    auto produce_one = [&]() {
+        if (sm.p_done) return;
+        if (sm.p_tile == sm.p_tiles) {
+            const int it = (int)atomicAdd(work_counter, 1u);
+            const int q = sm.p_items % kItemQueue;
+            sm.item[q] = it;
+            mbar_arrive(&sm.item_ready[q]);          // release: publishes sm.item[q]
+            ++sm.p_items;
+            if (it >= total_items) { sm.p_done = 1; return; }
+            sm.p_tile_begin = (it / ray_blocks) * tiles_per_split;
+            sm.p_tiles = min(n_tiles, sm.p_tile_begin + tiles_per_split) - sm.p_tile_begin;
+            sm.p_tile = 0;
+        }
+        const uint32_t g = sm.p_g;
+        const int s = g % kStages;
+        if (g >= (uint32_t)kStages) mbar_wait(&sm.empty[s], ((g / kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
+        bulk_g2s(sm.tile[s], packed + (size_t)(sm.p_tile_begin + sm.p_tile) * TFRT_TILE_TRIS * 3,
+                 TFRT_TILE_BYTES, &sm.full[s]);
+        ++sm.p_tile;
+        sm.p_g = g + 1;
+    };
+    // ---- producer, !kQueue: tile `g` of the CTA's running sequence <- global tile `tile`
     auto issue = [&](uint32_t g, int tile) {
         const int s = g % kStages;
         if (g >= (uint32_t)kStages) mbar_wait(&sm.empty[s], ((g / kStages) - 1) & 1);
@@ -98,22 +145,34 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         bulk_g2s(sm.tile[s], packed + (size_t)tile * TFRT_TILE_TRIS * 3, TFRT_TILE_BYTES,
                  &sm.full[s]);
     };
+    if constexpr (kQueue) {
+        if (tid == 0)
+            for (int i = 0; i < kStages; ++i) produce_one();   // fill the ring
+    }
 
     const float2 one2 = f2(w_one, w_one);   // 1 + 3*size_eps (eps is folded into ad, bd)
-
-    for (;;) {
-        __syncthreads();                    // previous item done; barriers initialised
-        if (tid == 0) s_item = (int)atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const int item = s_item;
+    uint32_t seq = 0;                       // tiles this warp (CTA) has consumed so far
+    for (int item_seq = 0;; ++item_seq) {
+        int item;
+        if constexpr (kQueue) {
+            const int q = item_seq % kItemQueue;
+            mbar_wait(&sm.item_ready[q], (uint32_t)((item_seq / kItemQueue) & 1));
+            item = sm.item[q];
+        } else {
+            __syncthreads();                // previous item done; barriers initialised
+            if (tid == 0) sm.item[0] = (int)atomicAdd(work_counter, 1u);
+            __syncthreads();
+            item = sm.item[0];
+        }
         if (item >= total_items) break;
         const int base = (item % ray_blocks) * rays_per_cta;
         const int tile_begin = (item / ray_blocks) * tiles_per_split;
         const int my_tiles = min(n_tiles, tile_begin + tiles_per_split) - tile_begin;
-
-        if (tid == 0) {                     // producer prologue: fill the ring
-            const int pre = min(kStages, my_tiles);
-            for (int i = 0; i < pre; ++i) issue(seq + i, tile_begin + i);
+        if constexpr (!kQueue) {
+            if (tid == 0) {                 // producer prologue: fill the ring
+                const int pre = min(kStages, my_tiles);
+                for (int i = 0; i < pre; ++i) issue(seq + i, tile_begin + i);
+            }
         }
 
         // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
@@ -227,10 +286,15 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                 }
             }
 
-            // release the stage; the producer refills it with tile it + kStages
+            // release the stage; the producer keeps the stream kStages tiles ahead
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
-            if (tid == 0 && it + kStages < my_tiles) issue(g + kStages, tile_begin + it + kStages);
+            if constexpr (kQueue) {
+                if (tid == 0) produce_one();
+            } else {
+                if (tid == 0 && it + kStages < my_tiles)
+                    issue(g + kStages, tile_begin + it + kStages);
+            }
         }
         seq += (uint32_t)my_tiles;
 
@@ -335,16 +399,25 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     const long long total_upper = (long long)ray_blocks * splits;
     const long long resident = (long long)num_sms * occ_r2;
     dim3 grid((unsigned)(total_upper < resident ? total_upper : resident)), block(kThreads);
-#define TFRT_LAUNCH(R2)                                                                         \
+    // Barrier-free item crossing pays for itself on long, heavy items (8 rays per thread, >= 4
+    // tiles: +1 % at 16 M rays x 99 k triangles, +4 % at 1 M x 20 k, +8 % at 1 M x 2 k); launches
+    // made of short items keep the one-item-at-a-time loop (profiles/r1_k1_tuning.md section 5).
+    static int queue_mode = -1;
+    if (queue_mode < 0) {
+        const char *e = getenv("TFRT_K1_QUEUE");     // 0 = never, 1 = auto (default), 2 = always
+        queue_mode = e ? atoi(e) : 1;
+    }
+    const bool use_queue = queue_mode == 2 || (queue_mode == 1 && r2 == 4 && tiles_per_split >= 4);
+#define TFRT_LAUNCH(R2, Q)                                                                      \
     do {                                                                                        \
         static bool attr_set = false;                                                           \
         if (!attr_set) {                                                                        \
-            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_intersect3d<R2>,                             \
+            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_intersect3d<R2, Q>,                          \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                                  (int)smem));                                   \
             attr_set = true;                                                                    \
         }                                                                                       \
-        k_intersect3d<R2><<<grid, block, smem, stream>>>(                                       \
+        k_intersect3d<R2, Q><<<grid, block, smem, stream>>>(                                    \
             ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,          \
             reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, splits,         \
             intersect_eps, ray_start_eps, 1.0f + 3.0f * size_eps,                               \
@@ -352,11 +425,15 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     } while (0)
     const bool timed = tfrt_profile_begin(stream);
 #if TFRT_K1_FORCE_R2
-    TFRT_LAUNCH(TFRT_K1_FORCE_R2);
+    if (use_queue) TFRT_LAUNCH(TFRT_K1_FORCE_R2, true);
+    else TFRT_LAUNCH(TFRT_K1_FORCE_R2, false);
 #else
-    if (r2 == 4) TFRT_LAUNCH(4);
-    else if (r2 == 2) TFRT_LAUNCH(2);
-    else TFRT_LAUNCH(1);
+    if (r2 == 4 && use_queue) TFRT_LAUNCH(4, true);
+    else if (r2 == 4) TFRT_LAUNCH(4, false);
+    else if (r2 == 2 && use_queue) TFRT_LAUNCH(2, true);
+    else if (r2 == 2) TFRT_LAUNCH(2, false);
+    else if (use_queue) TFRT_LAUNCH(1, true);
+    else TFRT_LAUNCH(1, false);
 #endif
 #undef TFRT_LAUNCH
     if (timed) tfrt_profile_end(stream);
