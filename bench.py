@@ -177,6 +177,43 @@ def size_cpu_sample(scene, backward, threads, target_s):
     return n
 
 
+def reference_source_leg(scene, backward, threads, target_s=8.0, mem_bytes=6e9):
+    """The reference's OWN Python (`tfrt`, pip-installed under baseline/_ref) executed on the stand-in
+    tensorflow of oracle/tf_shim (torch float64 CPU ops): timed beside the oracle port.  The sample is
+    bounded by memory: the reference materialises ~150 (triangles x rays) float64 tensors per
+    iteration, all of them retained by the GradientTape.  Returns a dict or None (3D configs only;
+    absent install -> None)."""
+    if scene["dimension"] != 3:
+        return None
+    try:
+        import torch
+        from oracle import reference_runner as rr
+        if rr.find_reference(installed_only=True) is None:
+            return None
+        torch.set_num_threads(threads)
+        ref = rr.import_reference(installed_only=True)
+        T = scene_triangles(scene)
+        per_ray = T * 8.0 * 150 * (scene["max_iterations"] if backward else 1)
+        n = int(max(8, min(mem_bytes / per_ray, 4096, scene["sources"]["x_start"].shape[0])))
+        dt, tests, live = rr.timed_reference_step(ref, scene, n, backward)        # warm-up / probe
+        reps = int(max(1, min(5, target_s / max(dt, 1e-3))))
+        total_s = total_tests = 0.0
+        for _ in range(reps):
+            dt, tests, live = rr.timed_reference_step(ref, scene, n, backward)
+            total_s += dt
+            total_tests += tests
+        return {"value": total_tests / total_s, "unit": UNIT, "cores": threads,
+                "kind": "reference source on a stand-in tensorflow",
+                "sample": f"first {n} of {scene['sources']['x_start'].shape[0]} rays x {T} triangles x "
+                          f"{scene['max_iterations']} iterations, {'fwd+bwd (GradientTape)' if backward else 'fwd'}, "
+                          f"{reps} step(s) of {total_s / reps:.2f} s; unmodified tfrt.engine / geometry / "
+                          f"operation / boundaries from baseline/_ref, every tf op served by torch float64 "
+                          f"CPU (oracle/tf_shim), un-chunked dense (triangles x rays) tensors as the "
+                          f"reference builds them"}
+    except Exception as e:  # the leg is informative: never fail the bench line over it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement timed on the host cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -210,9 +247,14 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "TensorFlow is not installable in this image, so the reference's own code cannot "
-                "run; this is its algorithm restated op-for-op (oracle/).",
+        "note": "TensorFlow is not installable in this image, so the reference cannot run as "
+                "shipped; `value` is its algorithm restated op-for-op (oracle/, cache-chunked: the "
+                "fastest CPU form we found); `reference_source` times the reference's own Python "
+                "on a stand-in tensorflow when baseline/_ref holds the pip-installed package.",
     }
+    src_leg = reference_source_leg(scene, backward, threads)
+    if src_leg is not None:
+        line["reference_source"] = src_leg
     print(json.dumps(line), flush=True)
 
 
@@ -491,6 +533,9 @@ def run_ours(args):
             "sample": f"first {n} of {n_total} rays x {T} triangles x {K} iterations, "
                       f"{'fwd+bwd' if backward else 'fwd'}, float64 dense restatement of the "
                       f"reference (oracle/), torch CPU, {dt:.1f} s"}
+        src_leg = reference_source_leg(scene, backward, threads, target_s=4.0)
+        if src_leg is not None:
+            line["cpu_baseline"]["reference_source"] = src_leg
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

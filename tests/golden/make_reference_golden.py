@@ -2,7 +2,7 @@
 
 The reference (`/root/reference/tfrt`, pure Python on TensorFlow) cannot be imported as is: TensorFlow,
 tfquaternion and pyvista are absent from this image.  This script puts a stand-in `tensorflow` module
-on `sys.path` (tests/golden/tf_shim/, ~70 tf ops mapped onto the IEEE-equivalent torch float64 ops, with
+on `sys.path` (oracle/tf_shim/, loaded by oracle/reference_runner.py; ~70 tf ops mapped onto the IEEE-equivalent torch float64 ops, with
 `tf.GradientTape` served by torch autograd) and then imports and runs the reference's unmodified
 `tfrt.geometry / engine / operation / materials / boundaries / sources / optimizer` code:
 
@@ -30,44 +30,14 @@ import sys
 sys.dont_write_bytecode = True
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-REFERENCE = os.environ.get("TFRT_REFERENCE", "/root/reference")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# fp32-appropriate epsilons shared with the CUDA parity tests (tests/helpers.py EPS)
-EPS = dict(intersect_epsilion=1e-10, size_epsilion=1e-5, ray_start_epsilion=1e-4)
-RAYS3 = ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")
-RAYS2 = ("x_start", "y_start", "x_end", "y_end")
-
-
-def f32_round(x):
-    return np.asarray(x, dtype=np.float32).astype(np.float64)
-
-
-def import_reference():
-    """Returns the reference's modules, imported from REFERENCE with the tf stand-in."""
-    for p in (REFERENCE, os.path.join(HERE, "tf_shim")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import tensorflow as tf  # the stand-in
-    assert tf.__version__ == "2.shim", "a real tensorflow is importable: use it instead of the shim"
-    import tfrt.boundaries as boundaries
-    import tfrt.engine as engine
-    import tfrt.geometry as geometry
-    import tfrt.materials as materials
-    import tfrt.operation as operation
-    import tfrt.sources as sources
-    import pyvista as pv
-    assert os.path.abspath(engine.__file__).startswith(os.path.abspath(REFERENCE))
-
-    class Ref:
-        pass
-    ref = Ref()
-    ref.tf, ref.pv = tf, pv
-    ref.boundaries, ref.engine, ref.geometry = boundaries, engine, geometry
-    ref.materials, ref.operation, ref.sources = materials, operation, sources
-    return ref
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle.reference_runner import (EPS, RAYS2, RAYS3, f32_round, import_reference,  # noqa: E402
+                                     reference_engine_2d, reference_engine_3d)
 
 
 def golden_scenes():
@@ -82,121 +52,6 @@ def golden_scenes():
         "ref_wedge2d": scenes.config1(ray_count=64),
         "ref_arclens2d": scenes.arc_lens_2d(ray_count=90),
     }
-
-
-# ------------------------------------------------------------------------------- engine level
-
-def _polydata(ref, vertices, faces):
-    faces = np.asarray(faces, dtype=np.int64)
-    packed = np.concatenate([np.full((faces.shape[0], 1), 3, dtype=np.int64), faces], axis=1)
-    return ref.pv.PolyData(f32_round(vertices), packed.reshape(-1))
-
-
-def _materials(ref, names):
-    return [{"n": getattr(ref.materials, n)} for n in names]
-
-
-def _manual_source(ref, scene, dimension):
-    src = ref.sources.ManualSource(dimension)
-    n = None
-    for k, v in scene["sources"].items():
-        src[k] = torch.from_numpy(np.ascontiguousarray(f32_round(v)))
-        n = v.shape[0]
-    src["slot"] = torch.arange(n, dtype=torch.float64)
-    return src
-
-
-def reference_engine_3d(ref, scene):
-    """tfrt objects for a 3D scene: parametric surfaces as `ParametricTriangleBoundary` along
-    `FromVectorVG` (pattern of dev/simple_3d_optimize.py:69-81; flip already applied to the scene's
-    faces), static surfaces (zero vectors) and targets as `ManualTriangleBoundary`."""
-    tf = ref.tf
-    optical, params = [], []
-    for s in scene["surfaces"]:
-        mat = {"mat_in": tf.constant(s["mat_in"], dtype=tf.int64),
-               "mat_out": tf.constant(s["mat_out"], dtype=tf.int64)}
-        if np.any(s["vectors"] != 0.0):
-            vec = f32_round(s["vectors"])
-            assert np.allclose(vec, vec[0]) and abs(np.linalg.norm(vec[0]) - 1.0) < 1e-12
-            surf = ref.boundaries.ParametricTriangleBoundary(
-                _polydata(ref, s["zero_points"], s["faces"]),
-                ref.boundaries.FromVectorVG(tuple(vec[0])),
-                initial_parameters=torch.from_numpy(f32_round(s["parameters"])),
-                material_dict=mat)
-            params.append(surf.parameters)
-        else:
-            verts = s["zero_points"] + s["parameters"][:, None] * s["vectors"]
-            surf = ref.boundaries.ManualTriangleBoundary(
-                mesh=_polydata(ref, verts, s["faces"]), material_dict=mat)
-        optical.append(surf)
-    targets = [ref.boundaries.ManualTriangleBoundary(mesh=_polydata(ref, m["vertices"], m["faces"]))
-               for m in scene["targets"]]
-    system = ref.engine.OpticalSystem3D(**EPS)
-    system.optical = optical
-    if scene["stops"]:
-        system.stops = [ref.boundaries.ManualTriangleBoundary(
-            mesh=_polydata(ref, m["vertices"], m["faces"])) for m in scene["stops"]]
-    system.targets = targets
-    system.sources = [_manual_source(ref, scene, 3)]
-    system.materials = _materials(ref, scene["materials"])
-    system.update()
-    inherit = {k for k in scene["sources"] if k not in RAYS3} | {"slot"}
-    eng = ref.engine.OpticalEngine(3, [ref.operation.StandardReaction()], compile_dead_rays=True,
-                                   compile_stopped_rays=True, simple_ray_inheritance=inherit)
-    eng.optical_system = system
-    eng.validate_system()
-    return eng, system, params
-
-
-def reference_engine_2d(ref, scene):
-    tf = ref.tf
-
-    def segs(items, with_mat):
-        out = []
-        for it in items:
-            b = ref.boundaries.ManualSegmentBoundary()
-            b.feed_segments(f32_round(it["segments"]))
-            if with_mat:
-                ref.engine.annotation_helper(b, "mat_in", it["mat_in"], "x_start", dtype=tf.int64)
-                ref.engine.annotation_helper(b, "mat_out", it["mat_out"], "x_start", dtype=tf.int64)
-            out.append(b)
-        return out
-
-    def arcs(items, with_mat):
-        out = []
-        for it in items:
-            b = ref.boundaries.ManualArcBoundary()
-            a = f32_round(it["arcs"])
-            for i, name in enumerate(("x_center", "y_center", "angle_start", "angle_end", "radius")):
-                b[name] = torch.from_numpy(np.ascontiguousarray(a[:, i]))
-            if with_mat:
-                ref.engine.annotation_helper(b, "mat_in", it["mat_in"], "x_center", dtype=tf.int64)
-                ref.engine.annotation_helper(b, "mat_out", it["mat_out"], "x_center", dtype=tf.int64)
-            out.append(b)
-        return out
-
-    system = ref.engine.OpticalSystem2D(**EPS)
-    if scene["optical_segments"]:
-        system.optical_segments = segs(scene["optical_segments"], True)
-    if scene["optical_arcs"]:
-        system.optical_arcs = arcs(scene["optical_arcs"], True)
-    if scene["stop_segments"]:
-        system.stop_segments = segs(scene["stop_segments"], False)
-    if scene["stop_arcs"]:
-        system.stop_arcs = arcs(scene["stop_arcs"], False)
-    if scene["target_segments"]:
-        system.target_segments = segs(scene["target_segments"], False)
-    if scene["target_arcs"]:
-        system.target_arcs = arcs(scene["target_arcs"], False)
-    system.sources = [_manual_source(ref, scene, 2)]
-    system.materials = _materials(ref, scene["materials"])
-    system.update()
-    eng = ref.engine.OpticalEngine(2, [ref.operation.StandardReaction()], compile_dead_rays=True,
-                                   compile_stopped_rays=True,
-                                   simple_ray_inheritance={"wavelength", "slot"})
-    eng.optical_system = system
-    eng.validate_system()
-    return eng, system
 
 
 def _record_sets(out, eng, fields):
