@@ -64,6 +64,26 @@ struct __align__(16) IntersectSmem {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+// packed f32x2 arithmetic (SASS FFMA2 / FMUL2 / FADD2); TFRT_K1_SCALAR=1 builds the same kernel from
+// scalar FFMA / FMUL / FADD for the tuning study (profiles/r1_k1_tuning.md)
+#ifndef TFRT_K1_SCALAR
+#define TFRT_K1_SCALAR 0
+#endif
+#if TFRT_K1_SCALAR
+__device__ __forceinline__ float2 k_fma2(float2 a, float2 b, float2 c) {
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+}
+__device__ __forceinline__ float2 k_mul2(float2 a, float2 b) {
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+}
+__device__ __forceinline__ float2 k_add2(float2 a, float2 b) {
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+#else
+__device__ __forceinline__ float2 k_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 k_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 k_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#endif
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 template <int R2, bool kQueue>
@@ -233,27 +253,27 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                 bool cand = false;
 #pragma unroll
                 for (int r = 0; r < R2; ++r) {
-                    float2 det = __fmul2_rn(nx, Dx[r]);
-                    det = __ffma2_rn(ny, Dy[r], det);
-                    det = __ffma2_rn(nz, Dz[r], det);
-                    float2 tq = __ffma2_rn(neg2(nx), Ox[r], nd);
-                    tq = __ffma2_rn(neg2(ny), Oy[r], tq);
-                    tq = __ffma2_rn(neg2(nz), Oz[r], tq);
+                    float2 det = k_mul2(nx, Dx[r]);
+                    det = k_fma2(ny, Dy[r], det);
+                    det = k_fma2(nz, Dz[r], det);
+                    float2 tq = k_fma2(neg2(nx), Ox[r], nd);
+                    tq = k_fma2(neg2(ny), Oy[r], tq);
+                    tq = k_fma2(neg2(nz), Oz[r], tq);
                     float2 inv;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
-                    const float2 t = __fmul2_rn(tq, inv);
-                    const float2 px = __ffma2_rn(t, Dx[r], Ox[r]);
-                    const float2 py = __ffma2_rn(t, Dy[r], Oy[r]);
-                    const float2 pz = __ffma2_rn(t, Dz[r], Oz[r]);
-                    float2 u = __ffma2_rn(ax, px, ad);
-                    u = __ffma2_rn(ay, py, u);
-                    u = __ffma2_rn(az, pz, u);
-                    float2 v = __ffma2_rn(bx, px, bd);
-                    v = __ffma2_rn(by, py, v);
-                    v = __ffma2_rn(bz, pz, v);
-                    float2 w = __fadd2_rn(one2, neg2(u));
-                    w = __fadd2_rn(w, neg2(v));
+                    const float2 t = k_mul2(tq, inv);
+                    const float2 px = k_fma2(t, Dx[r], Ox[r]);
+                    const float2 py = k_fma2(t, Dy[r], Oy[r]);
+                    const float2 pz = k_fma2(t, Dz[r], Oz[r]);
+                    float2 u = k_fma2(ax, px, ad);
+                    u = k_fma2(ay, py, u);
+                    u = k_fma2(az, pz, u);
+                    float2 v = k_fma2(bx, px, bd);
+                    v = k_fma2(by, py, v);
+                    v = k_fma2(bz, pz, v);
+                    float2 w = k_add2(one2, neg2(u));
+                    w = k_add2(w, neg2(v));
                     // sign bit of (u|v|w) set <=> outside the (inflated) triangle: fold into key
                     key[2 * r] = __float_as_uint(t.x) |
                                  ((__float_as_uint(u.x) | __float_as_uint(v.x) |
@@ -271,9 +291,9 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                         // |det| >= intersect_eps is the reference's safe-denominator validity
                         // (tfrt/geometry.py:306); det is re-derived here to keep it out of the
                         // common path's live registers.
-                        float2 det = __fmul2_rn(nx, Dx[r]);
-                        det = __ffma2_rn(ny, Dy[r], det);
-                        det = __ffma2_rn(nz, Dz[r], det);
+                        float2 det = k_mul2(nx, Dx[r]);
+                        det = k_fma2(ny, Dy[r], det);
+                        det = k_fma2(nz, Dz[r], det);
                         if (key[2 * r] < best[2 * r] && fabsf(det.x) >= intersect_eps) {
                             best[2 * r] = key[2 * r];
                             bidx[2 * r] = tri;
