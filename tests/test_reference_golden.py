@@ -2,7 +2,7 @@
 
 tests/golden/ref_*.npz were produced by tests/golden/make_reference_golden.py, which imports the
 unmodified reference (`tfrt.geometry / engine / operation / materials / boundaries / sources`) in the
-build container with a stand-in `tensorflow` module (tests/golden/tf_shim: each tf op mapped to the
+build container with a stand-in `tensorflow` module (oracle/tf_shim: each tf op mapped to the
 IEEE-equivalent torch float64 op, GradientTape -> torch autograd).  So every line of reference Python
 on the hot path ran as written to make these vectors.
 
