@@ -453,10 +453,11 @@ def run_ours(args):
             "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
             "share_of_step": k_ms * 1e-3 / seconds,
             "flop_per_test": FLOP_PER_TEST,
-            # the kernel's plane form issues 14 FFMA + 2 FMUL + 2 FADD (as 9 packed f32x2
-            # instructions per ray pair) + 1 MUFU.RCP per test: 18 FMA-pipe lane-slots
-            "fma_pipe_slots_per_test": 18.0,
-            "fma_pipe_utilisation": 18.0 * tests_per_launch / (k_ms / k_n * 1e-3)
+            # the kernel's projected plane form issues 10 FFMA + 1 FMUL + 3 FADD (as 14 packed
+            # f32x2 instructions per ray pair) + 1 MUFU.RCP per test: 14 FMA-pipe lane-slots, i.e.
+            # fewer than the algorithmic 45-FLOP Moller-Trumbore count the roofline is quoted on
+            "fma_pipe_slots_per_test": 14.0,
+            "fma_pipe_utilisation": 14.0 * tests_per_launch / (k_ms / k_n * 1e-3)
                                     / (fp32_peak / 2.0),
             "peak_source": "measured in this run by tfrt_fp32_peak (register-only FFMA loop on "
                            "all SMs); MEASURED_PEAKS.json carries no fp32 figure. Nominal "

@@ -43,12 +43,19 @@ static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 
 // ---------------------------------------------------------------------------------------------
 // packed triangle layout
 //
-// One triangle = 12 floats = three float4 (one broadcast LDS.128 each):
-//   q0 = (nx, ny, nz, d )      plane:   det = n.D, t' = d - n.O
-//   q1 = (ax, ay, az, ad)      u-plane: u = a.P + ad   (+size_eps)
-//   q2 = (bx, by, bz, bd)      v-plane: v = b.P + bd   (+size_eps)
-// with n = e1 x e2 (un-normalised, so |det| is the reference's |denominator|,
-// tfrt/geometry.py:300), d = n.A, a = (e2 x n)/|n|^2, b = (n x e1)/|n|^2.
+// One triangle = 12 floats = three float4 (one broadcast LDS.128 each), in the projected form of
+// Wald's ray-triangle test: k = dominant axis of the normal n = e1 x e2, (k1, k2) = (k+1, k+2) mod 3,
+// the plane scaled so that its k-coefficient is 1:
+//   q0 = (m1, m2, dd, index)    det = D[k] + m1 D[k1] + m2 D[k2],  t' = dd - O[k] - m1 O[k1] - m2 O[k2]
+//   q1 = (a1, a2, a0, n[k])     u = a1 P[k1] + a2 P[k2] + a0     (+size_eps folded into a0)
+//   q2 = (b1, b2, b0, header)   v = b1 P[k1] + b2 P[k2] + b0     (+size_eps folded into b0)
+// with m = n/n[k], dd = m.A, and (a, a0), (b, b0) the barycentric planes u = a3.P + ad,
+// a3 = (e2 x n)/|n|^2, v = b3.P + bd, b3 = (n x e1)/|n|^2, with P[k] eliminated through the plane
+// equation (exact for points on the plane): 14 FMA-pipe lane-ops per test instead of 18.
+// det * n[k] is the reference's denominator (tfrt/geometry.py:300) up to sign.
+// Inside a tile the records are grouped by k (stable: index order inside a group) so that the
+// kernel runs three specialised loops without a per-triangle branch; `index` is the triangle's
+// position in the merged set, `header` of record 0 = (size of group 0) | (size of group 1) << 16.
 // FFMA2 takes a 32-bit register broadcast to both halves (SASS operand `R.F32`), so a
 // coefficient multiplies the two rays of a pair without being stored twice.
 #define TFRT_TRI_FLOATS 12

@@ -8,17 +8,28 @@
 //  * a thread owns 2*R2 rays kept in registers as R2 f32x2 pairs (origin, direction);
 //  * triangles stream through shared memory in tiles of TFRT_TILE_TRIS, copied by one elected
 //    thread with cp.async.bulk (TMA 1-D) into a 3-stage mbarrier ring;
-//  * per (ray, triangle) the precomputed-plane test costs 18 fp32 ops issued as 9 FFMA2/FADD2
-//    (two rays per instruction) + 1 MUFU.RCP + 4 integer ops:
-//        det = n.D            t' = d - n.O           t = t'/det   (origin pre-shifted by
-//        P   = O + t D        u  = a.P + ad          v = b.P + bd  ray_start_eps so t>=0 <=> valid)
+//  * per (ray, triangle) the projected precomputed-plane test (Wald's projection onto the
+//    dominant axis k of the normal, plane scaled to a unit k-coefficient; record layout in
+//    common.cuh) costs 14 fp32 ops issued as 7 FFMA2/FADD2/FMUL2 per ray (two rays per
+//    instruction) + 1 MUFU.RCP + 3 integer ops:
+//        det = D[k] + m1 D[k1] + m2 D[k2]      t' = dd - O[k] - m1 O[k1] - m2 O[k2]
+//        t   = t'/det     (origin pre-shifted by ray_start_eps so t >= 0 <=> valid)
+//        P1  = O[k1] + t D[k1]                 P2 = O[k2] + t D[k2]
+//        u   = a1 P1 + a2 P2 + a0              v  = b1 P1 + b2 P2 + b0
 //        w   = (1+3 eps) - u - v
 //    valid & nearer  <=>  (bits(t) | signbit(u|v|w))  <  best   as unsigned integers;
-//  * the running best is (key, triangle index); ascending scan + strict '<' gives the lowest
-//    index on exact ties (the behaviour of argmin in the reference's CPU kernels);
+//    the triangles of a tile are grouped by k, so three specialised loops run back to back
+//    with the roles of the ray components fixed at compile time;
+//  * the running best is (key, triangle index); the scan is in index order inside an axis
+//    group and strict '<' keeps the first, so exact ties between triangles of one group (e.g.
+//    the coplanar halves of a flat target) go to the lowest index, the behaviour of argmin in
+//    the reference's CPU kernels; an exact tie between triangles of different dominant axes of
+//    one tile goes to the lower axis (a bit-equal t from two different planes: a near tie by
+//    the north star's rule);
 //  * optional split of the triangle range over blockIdx.y, merged with a 64-bit atomicMin on
 //    (key << 32 | index) -- same tie rule -- so small ray counts still fill 148 SMs.
 #include <atomic>
+#include <type_traits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -196,7 +207,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         }
 
         // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
-        float2 Ox[R2], Oy[R2], Oz[R2], Dx[R2], Dy[R2], Dz[R2];
+        float2 O[3][R2], D[3][R2];
         uint32_t best[2 * R2];
         int32_t bidx[2 * R2];
 #pragma unroll
@@ -225,8 +236,11 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                 best[2 * r + h] = TFRT_NOHIT_KEY;
                 bidx[2 * r + h] = 0;
             }
-            Ox[r] = f2(o[0][0], o[1][0]); Oy[r] = f2(o[0][1], o[1][1]); Oz[r] = f2(o[0][2], o[1][2]);
-            Dx[r] = f2(d[0][0], d[1][0]); Dy[r] = f2(d[0][1], d[1][1]); Dz[r] = f2(d[0][2], d[1][2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                O[c][r] = f2(o[0][c], o[1][c]);
+                D[c][r] = f2(d[0][c], d[1][c]);
+            }
         }
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -234,77 +248,80 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             const int s = g % kStages;
             mbar_wait(&sm.full[s], (g / kStages) & 1);
             const float4 *__restrict__ tile = sm.tile[s];
-            const int tri0 = (tile_begin + it) * TFRT_TILE_TRIS;
 
+            // One specialised loop per dominant axis K of the tile's three triangle groups: the
+            // ray components taking the roles (k, k1, k2) are fixed at compile time.
+            auto run_group = [&](auto kc, int j0, int j1) {
+                constexpr int K = decltype(kc)::value, K1 = (K + 1) % 3, K2 = (K + 2) % 3;
 #pragma unroll kUnroll
-            for (int j = 0; j < TFRT_TILE_TRIS; ++j) {
-                const float4 q0 = tile[j * 3 + 0];
-                const float4 q1 = tile[j * 3 + 1];
-                const float4 q2 = tile[j * 3 + 2];
-                // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
-                const float2 nx = f2(q0.x, q0.x), ny = f2(q0.y, q0.y), nz = f2(q0.z, q0.z),
-                             nd = f2(q0.w, q0.w);
-                const float2 ax = f2(q1.x, q1.x), ay = f2(q1.y, q1.y), az = f2(q1.z, q1.z),
-                             ad = f2(q1.w, q1.w);
-                const float2 bx = f2(q2.x, q2.x), by = f2(q2.y, q2.y), bz = f2(q2.z, q2.z),
-                             bd = f2(q2.w, q2.w);
-                const int tri = tri0 + j;
-                uint32_t key[2 * R2];
-                bool cand = false;
-#pragma unroll
-                for (int r = 0; r < R2; ++r) {
-                    float2 det = k_mul2(nx, Dx[r]);
-                    det = k_fma2(ny, Dy[r], det);
-                    det = k_fma2(nz, Dz[r], det);
-                    float2 tq = k_fma2(neg2(nx), Ox[r], nd);
-                    tq = k_fma2(neg2(ny), Oy[r], tq);
-                    tq = k_fma2(neg2(nz), Oz[r], tq);
-                    float2 inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
-                    const float2 t = k_mul2(tq, inv);
-                    const float2 px = k_fma2(t, Dx[r], Ox[r]);
-                    const float2 py = k_fma2(t, Dy[r], Oy[r]);
-                    const float2 pz = k_fma2(t, Dz[r], Oz[r]);
-                    float2 u = k_fma2(ax, px, ad);
-                    u = k_fma2(ay, py, u);
-                    u = k_fma2(az, pz, u);
-                    float2 v = k_fma2(bx, px, bd);
-                    v = k_fma2(by, py, v);
-                    v = k_fma2(bz, pz, v);
-                    float2 w = k_add2(one2, neg2(u));
-                    w = k_add2(w, neg2(v));
-                    // sign bit of (u|v|w) set <=> outside the (inflated) triangle: fold into key
-                    key[2 * r] = __float_as_uint(t.x) |
-                                 ((__float_as_uint(u.x) | __float_as_uint(v.x) |
-                                   __float_as_uint(w.x)) & 0x80000000u);
-                    key[2 * r + 1] = __float_as_uint(t.y) |
-                                     ((__float_as_uint(u.y) | __float_as_uint(v.y) |
-                                       __float_as_uint(w.y)) & 0x80000000u);
-                    cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
-                }
-                // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so the
-                // common case pays one vote instead of predicated selects per test.
-                if (__any_sync(0xffffffffu, cand)) {
+                for (int j = j0; j < j1; ++j) {
+                    const float4 q0 = tile[j * 3 + 0];
+                    const float4 q1 = tile[j * 3 + 1];
+                    const float4 q2 = tile[j * 3 + 2];
+                    // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
+                    const float2 m1 = f2(q0.x, q0.x), m2 = f2(q0.y, q0.y), dd = f2(q0.z, q0.z);
+                    const float2 a1 = f2(q1.x, q1.x), a2 = f2(q1.y, q1.y), a0 = f2(q1.z, q1.z);
+                    const float2 b1 = f2(q2.x, q2.x), b2 = f2(q2.y, q2.y), b0 = f2(q2.z, q2.z);
+                    uint32_t key[2 * R2];
+                    float2 dets[R2];
+                    bool cand = false;
 #pragma unroll
                     for (int r = 0; r < R2; ++r) {
-                        // |det| >= intersect_eps is the reference's safe-denominator validity
-                        // (tfrt/geometry.py:306); det is re-derived here to keep it out of the
-                        // common path's live registers.
-                        float2 det = k_mul2(nx, Dx[r]);
-                        det = k_fma2(ny, Dy[r], det);
-                        det = k_fma2(nz, Dz[r], det);
-                        if (key[2 * r] < best[2 * r] && fabsf(det.x) >= intersect_eps) {
-                            best[2 * r] = key[2 * r];
-                            bidx[2 * r] = tri;
-                        }
-                        if (key[2 * r + 1] < best[2 * r + 1] && fabsf(det.y) >= intersect_eps) {
-                            best[2 * r + 1] = key[2 * r + 1];
-                            bidx[2 * r + 1] = tri;
+                        float2 det = k_fma2(m1, D[K1][r], D[K][r]);
+                        det = k_fma2(m2, D[K2][r], det);
+                        float2 tq = k_add2(dd, neg2(O[K][r]));
+                        tq = k_fma2(neg2(m1), O[K1][r], tq);
+                        tq = k_fma2(neg2(m2), O[K2][r], tq);
+                        float2 inv;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
+                        const float2 t = k_mul2(tq, inv);
+                        const float2 p1 = k_fma2(t, D[K1][r], O[K1][r]);
+                        const float2 p2 = k_fma2(t, D[K2][r], O[K2][r]);
+                        float2 u = k_fma2(a1, p1, a0);
+                        u = k_fma2(a2, p2, u);
+                        float2 v = k_fma2(b1, p1, b0);
+                        v = k_fma2(b2, p2, v);
+                        float2 w = k_add2(one2, neg2(u));
+                        w = k_add2(w, neg2(v));
+                        // sign bit of (u|v|w) set <=> outside the (inflated) triangle: fold into key
+                        key[2 * r] = __float_as_uint(t.x) |
+                                     ((__float_as_uint(u.x) | __float_as_uint(v.x) |
+                                       __float_as_uint(w.x)) & 0x80000000u);
+                        key[2 * r + 1] = __float_as_uint(t.y) |
+                                         ((__float_as_uint(u.y) | __float_as_uint(v.y) |
+                                           __float_as_uint(w.y)) & 0x80000000u);
+                        cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
+                        dets[r] = det;
+                    }
+                    // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so
+                    // the common case pays one vote instead of predicated selects per test.
+                    if (__any_sync(0xffffffffu, cand)) {
+                        const int tri = __float_as_int(q0.w);
+                        // |det * n[k]| >= intersect_eps is the reference's safe-denominator
+                        // validity (tfrt/geometry.py:306)
+                        const float nk = q1.w;
+#pragma unroll
+                        for (int r = 0; r < R2; ++r) {
+                            if (key[2 * r] < best[2 * r] &&
+                                fabsf(dets[r].x * nk) >= intersect_eps) {
+                                best[2 * r] = key[2 * r];
+                                bidx[2 * r] = tri;
+                            }
+                            if (key[2 * r + 1] < best[2 * r + 1] &&
+                                fabsf(dets[r].y * nk) >= intersect_eps) {
+                                best[2 * r + 1] = key[2 * r + 1];
+                                bidx[2 * r + 1] = tri;
+                            }
                         }
                     }
                 }
-            }
+            };
+            const int header = __float_as_int(tile[2].w);
+            const int c0 = header & 0xffff, c1 = c0 + (header >> 16);
+            run_group(std::integral_constant<int, 0>{}, 0, c0);
+            run_group(std::integral_constant<int, 1>{}, c0, c1);
+            run_group(std::integral_constant<int, 2>{}, c1, TFRT_TILE_TRIS);
 
             // release the stage; the producer keeps the stream kStages tiles ahead
             __syncwarp();
@@ -337,6 +354,24 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
     }
 }
 
+// Resident CTAs per SM of the three ray-count variants {R2 = 4, 2, 1}, asked from the runtime once
+// (the persistent grid is sized from it).
+const int *occupancy_table() {
+    static int occ[3] = {0, 0, 0};
+    if (!occ[0]) {
+        const int smem = (int)sizeof(IntersectSmem);
+        int v[3] = {4, 4, 6};
+        cudaFuncSetAttribute(k_intersect3d<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_intersect3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_intersect3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[0], k_intersect3d<4, false>, kThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[1], k_intersect3d<2, false>, kThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[2], k_intersect3d<1, false>, kThreads, smem);
+        for (int i = 0; i < 3; ++i) occ[i] = v[i] > 0 ? v[i] : 1;
+    }
+    return occ;
+}
+
 }  // namespace
 
 // host launcher -------------------------------------------------------------------------------
@@ -365,7 +400,7 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     int r2 = 1, splits = 1;
     {
         const int cand_r2[3] = {4, 2, 1};
-        const int occ[3] = {4, 5, 6};                 // resident CTAs per SM (registers / smem)
+        const int *occ = occupancy_table();           // resident CTAs per SM (registers / smem)
         static int items_lo = 0, items_hi = 0;
         if (!items_lo) {
             const char *e = getenv("TFRT_K1_ITEMS_PER_CTA");
@@ -415,7 +450,7 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     TFRT_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
 
     const size_t smem = sizeof(IntersectSmem);
-    const int occ_r2 = r2 >= 4 ? 4 : (r2 == 2 ? 5 : 6);
+    const int occ_r2 = occupancy_table()[r2 >= 4 ? 0 : (r2 == 2 ? 1 : 2)];
     const long long total_upper = (long long)ray_blocks * splits;
     const long long resident = (long long)num_sms * occ_r2;
     dim3 grid((unsigned)(total_upper < resident ? total_upper : resident)), block(kThreads);

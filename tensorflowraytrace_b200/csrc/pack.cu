@@ -4,18 +4,24 @@
 
 namespace {
 
-// One thread per (padded) triangle: writes the 12-float record described in common.cuh.
-__global__ void k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
-                                 const float *__restrict__ zp, const float *__restrict__ x1,
-                                 const float *__restrict__ y1, const float *__restrict__ z1,
-                                 const float *__restrict__ x2, const float *__restrict__ y2,
-                                 const float *__restrict__ z2, int n_tri, int n_padded,
-                                 float size_eps, float4 *__restrict__ packed) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_padded) return;
-    // never-hit record: det == 0 and t' = -1  =>  t = -inf (sign bit set)
-    float n[3] = {0.f, 0.f, 0.f}, d = -1.f, a[3] = {0.f, 0.f, 0.f}, ad = 0.f, b[3] = {0.f, 0.f, 0.f},
-          bd = 0.f;
+// One CTA per tile of TFRT_TILE_TRIS triangles, one thread per (padded) triangle: computes the
+// projected 12-float record described in common.cuh and writes it at its position in the tile's
+// stable partition by dominant axis (k = 0 first, then 1, then 2; index order inside a group).
+// Record 0 of the tile carries the group sizes.
+__global__ void __launch_bounds__(TFRT_TILE_TRIS)
+k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
+                 const float *__restrict__ zp, const float *__restrict__ x1,
+                 const float *__restrict__ y1, const float *__restrict__ z1,
+                 const float *__restrict__ x2, const float *__restrict__ y2,
+                 const float *__restrict__ z2, int n_tri, float size_eps,
+                 float4 *__restrict__ packed) {
+    __shared__ int s_cnt[3][TFRT_TILE_TRIS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * TFRT_TILE_TRIS + threadIdx.x;
+    // never-hit record (padding, degenerate triangles): u = -1 => sign bit set => never valid
+    int k = 0;
+    float n1 = 0.f, n2 = 0.f, dd = 0.f, nk = 0.f;
+    float au1 = 0.f, au2 = 0.f, au0 = -1.f, bv1 = 0.f, bv2 = 0.f, bv0 = -1.f;
     if (i < n_tri) {
         const double A[3] = {xp[i], yp[i], zp[i]};
         const double e1[3] = {x1[i] - A[0], y1[i] - A[1], z1[i] - A[2]};
@@ -32,20 +38,48 @@ __global__ void k_pack_triangles(const float *__restrict__ xp, const float *__re
             const double bv[3] = {(N[1] * e1[2] - N[2] * e1[1]) * inv,
                                   (N[2] * e1[0] - N[0] * e1[2]) * inv,
                                   (N[0] * e1[1] - N[1] * e1[0]) * inv};
-            for (int k = 0; k < 3; ++k) {
-                n[k] = (float)N[k];
-                a[k] = (float)av[k];
-                b[k] = (float)bv[k];
-            }
-            d = (float)(N[0] * A[0] + N[1] * A[1] + N[2] * A[2]);
-            ad = (float)(-(av[0] * A[0] + av[1] * A[1] + av[2] * A[2]) + (double)size_eps);
-            bd = (float)(-(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + (double)size_eps);
+            const double ad = -(av[0] * A[0] + av[1] * A[1] + av[2] * A[2]) + (double)size_eps;
+            const double bd = -(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + (double)size_eps;
+            // dominant axis of the normal; plane scaled so that its k-coefficient is 1:
+            //   P[k] = dd - m1 P[k1] - m2 P[k2]  for every P on the plane
+            k = fabs(N[1]) > fabs(N[0]) ? 1 : 0;
+            if (fabs(N[2]) > fabs(N[k])) k = 2;
+            const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+            const double m1 = N[k1] / N[k], m2 = N[k2] / N[k];
+            const double dk = A[k] + m1 * A[k1] + m2 * A[k2];
+            n1 = (float)m1; n2 = (float)m2; dd = (float)dk; nk = (float)N[k];
+            // u = a.P + ad with P[k] eliminated (exact on the plane)
+            au1 = (float)(av[k1] - av[k] * m1); au2 = (float)(av[k2] - av[k] * m2);
+            au0 = (float)(ad + av[k] * dk);
+            bv1 = (float)(bv[k1] - bv[k] * m1); bv2 = (float)(bv[k2] - bv[k] * m2);
+            bv0 = (float)(bd + bv[k] * dk);
         }
     }
-    float4 *o = packed + (size_t)i * 3;
-    o[0] = make_float4(n[0], n[1], n[2], d);
-    o[1] = make_float4(a[0], a[1], a[2], ad);
-    o[2] = make_float4(b[0], b[1], b[2], bd);
+    // stable partition by k inside the tile
+    int rank_in_warp = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const unsigned m = __ballot_sync(0xffffffffu, k == g);
+        if (lane == 0) s_cnt[g][wid] = __popc(m);
+        if (k == g) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    int total[3] = {0, 0, 0}, before = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int w = 0; w < TFRT_TILE_TRIS / 32; ++w) {
+            const int c = s_cnt[g][w];
+            if (g == k && w < wid) before += c;
+            total[g] += c;
+        }
+    }
+    const int pos = (k == 0 ? 0 : (k == 1 ? total[0] : total[0] + total[1])) + before + rank_in_warp;
+    float4 *o = packed + ((size_t)blockIdx.x * TFRT_TILE_TRIS + pos) * 3;
+    o[0] = make_float4(n1, n2, dd, __int_as_float(i));
+    o[1] = make_float4(au1, au2, au0, nk);
+    // group sizes of the tile ride in record 0 (k = 0 group size | k = 1 group size << 16)
+    o[2] = make_float4(bv1, bv2, bv0, __int_as_float(pos == 0 ? (total[0] | (total[1] << 16)) : 0));
 }
 
 // K3 forward: gather face corners, unit normal normalize((p2-p1) x (p3-p2))
@@ -136,10 +170,9 @@ extern "C" int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, flo
                                    float *packed, void *stream) {
     TFRT_REQUIRE(n_tri >= 0 && packed, "tfrt_pack_triangles: bad arguments");
     if (n_tri == 0) return 0;
-    const int n_padded = tfrt_div_up(n_tri, TFRT_TILE_TRIS) * TFRT_TILE_TRIS;
-    k_pack_triangles<<<tfrt_div_up(n_padded, 128), 128, 0, (cudaStream_t)stream>>>(
-        tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], n_tri, n_padded,
-        size_eps, reinterpret_cast<float4 *>(packed));
+    k_pack_triangles<<<tfrt_div_up(n_tri, TFRT_TILE_TRIS), TFRT_TILE_TRIS, 0, (cudaStream_t)stream>>>(
+        tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], n_tri, size_eps,
+        reinterpret_cast<float4 *>(packed));
     tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;

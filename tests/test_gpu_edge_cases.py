@@ -133,3 +133,49 @@ def test_largest_mesh_with_a_ray_subsample():
         ograds = torch.autograd.grad(oerr.sum(), oparams)
         for g, og in zip(grads, ograds):
             assert helpers.rel_err(g.cpu().numpy(), og.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("step_count", [13, 91])
+def test_search_is_watertight_at_edges_and_vertices(step_count):
+    """Rays aimed exactly at interior vertices and edge midpoints of the lens' first surface (the
+    worst case for the fp32 search: every such ray lies in the inflation band of 2-6 triangles) must
+    all hit it -- no ray may slip between two triangles -- and the hit triangle must be one of the
+    triangles adjacent to the aimed feature.  Covers all three axis groups of the projected layout:
+    the same mesh is also tested rotated so that its normals are mostly along y and along z."""
+    from tensorflowraytrace_b200 import engine as eng
+    rng = np.random.default_rng(step_count)
+    surf = scenes.lens_surfaces(step_count)[0]
+    verts = scenes.surface_vertices(surf)
+    faces = surf["faces"]
+    r = np.hypot(verts[:, 1], verts[:, 2])
+    inner = np.nonzero(r < 0.9)[0]
+    pick = rng.choice(inner, size=min(3000, inner.size), replace=False)
+    targets = [verts[pick]]
+    f = faces[rng.choice(faces.shape[0], size=min(3000, faces.shape[0]), replace=False)]
+    f = f[(r[f] < 0.9).all(axis=1)]
+    for a, b in ((0, 1), (1, 2), (2, 0)):
+        lam = rng.uniform(0.05, 0.95, size=(f.shape[0], 1))
+        targets.append(lam * verts[f[:, a]] + (1 - lam) * verts[f[:, b]])
+    aim = np.concatenate(targets)
+    start = aim + np.stack([np.full(aim.shape[0], -3.0), rng.uniform(-0.3, 0.3, aim.shape[0]),
+                            rng.uniform(-0.3, 0.3, aim.shape[0])], axis=1)
+    dev = torch.device("cuda:0")
+    for perm in ((0, 1, 2), (1, 2, 0), (2, 0, 1)):       # normals mostly along x, then y, then z
+        V = verts[:, perm].astype(np.float32)
+        S, A = start[:, perm].astype(np.float32), aim[:, perm].astype(np.float32)
+        E = (S + (A - S) * np.float32(0.25)).astype(np.float32)
+        tri = [torch.tensor(np.ascontiguousarray(V[faces[:, c], k]), device=dev)
+               for c in range(3) for k in range(3)]
+        rays = [torch.tensor(np.ascontiguousarray(S[:, k]), device=dev) for k in range(3)] + \
+               [torch.tensor(np.ascontiguousarray(E[:, k]), device=dev) for k in range(3)]
+        out = eng.OpticalSystem3D._intersection(*rays, *tri, 1e-10, 1e-5, 1e-4)
+        valid, gather_trig = out[3].cpu().numpy(), out[8].cpu().numpy()
+        assert valid.all(), (perm, int((~valid).sum()))
+        # the hit triangle touches the aimed point: distance from the aim to the triangle's plane
+        # patch is ~0 (fp32), checked through the hit point itself
+        hit = np.stack([out[0].detach().cpu().numpy(), out[1].detach().cpu().numpy(),
+                        out[2].detach().cpu().numpy()], axis=1)
+        assert np.abs(hit - A).max() < 2e-5, (perm, float(np.abs(hit - A).max()))
+        corners = V[faces[gather_trig]]                                   # (n, 3, 3)
+        lo, hi = corners.min(axis=1) - 2e-5, corners.max(axis=1) + 2e-5
+        assert ((A >= lo) & (A <= hi)).all(), perm
