@@ -453,6 +453,12 @@ def run_ours(args):
             "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
             "share_of_step": k_ms * 1e-3 / seconds,
             "flop_per_test": FLOP_PER_TEST,
+            # `achieved` / `frac` use the ALGORITHMIC count (45 FLOP per Moller-Trumbore test,
+            # SURVEY.md 8(d)); the kernel's projected plane form executes 25 FLOP per test
+            # (10 FFMA + 1 FMUL + 3 FADD + 1 reciprocal), so `frac` can exceed 1 while the FMA
+            # pipe itself is ~70 % busy: both views are given
+            "executed_flop_per_test": 25.0,
+            "frac_executed": 25.0 * tests_per_launch / (k_ms / k_n * 1e-3) / fp32_peak,
             # the kernel's projected plane form issues 10 FFMA + 1 FMUL + 3 FADD (as 14 packed
             # f32x2 instructions per ray pair) + 1 MUFU.RCP per test: 14 FMA-pipe lane-slots, i.e.
             # fewer than the algorithmic 45-FLOP Moller-Trumbore count the roofline is quoted on

@@ -47,11 +47,13 @@ static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 
 // Wald's ray-triangle test: k = dominant axis of the normal n = e1 x e2, (k1, k2) = (k+1, k+2) mod 3,
 // the plane scaled so that its k-coefficient is 1:
 //   q0 = (m1, m2, dd, index)    det = D[k] + m1 D[k1] + m2 D[k2],  t' = dd - O[k] - m1 O[k1] - m2 O[k2]
-//   q1 = (a1, a2, a0, n[k])     u = a1 P[k1] + a2 P[k2] + a0     (+size_eps folded into a0)
-//   q2 = (b1, b2, b0, header)   v = b1 P[k1] + b2 P[k2] + b0     (+size_eps folded into b0)
-// with m = n/n[k], dd = m.A, and (a, a0), (b, b0) the barycentric planes u = a3.P + ad,
-// a3 = (e2 x n)/|n|^2, v = b3.P + bd, b3 = (n x e1)/|n|^2, with P[k] eliminated through the plane
-// equation (exact for points on the plane): 14 FMA-pipe lane-ops per test instead of 18.
+//   q1 = (s1, s2, s0, n[k])     S = s1 P[k1] + s2 P[k2] + s0  =  2 (u + v) - C
+//   q2 = (e1, e2, e0, header)   E = e1 P[k1] + e2 P[k2] + e0  =  u - v
+// with m = n/n[k], dd = m.A, u = a3.P + ad and v = b3.P + bd the barycentric planes
+// (a3 = (e2 x n)/|n|^2, b3 = (n x e1)/|n|^2, size_eps folded into ad, bd), P[k] eliminated through
+// the plane equation (exact for points on the plane), C = 1 + 3 size_eps.  The kernel accepts a hit
+// iff |E| + |S - |E|| <= C, which is u >= 0, v >= 0, u + v <= C: 14 FMA-pipe lane-ops and two
+// integer compares per test.
 // det * n[k] is the reference's denominator (tfrt/geometry.py:300) up to sign.
 // Inside a tile the records are grouped by k (stable: index order inside a group) so that the
 // kernel runs three specialised loops without a per-triangle branch; `index` is the triangle's

@@ -11,16 +11,20 @@
 //  * per (ray, triangle) the projected precomputed-plane test (Wald's projection onto the
 //    dominant axis k of the normal, plane scaled to a unit k-coefficient; record layout in
 //    common.cuh) costs 14 fp32 ops issued as 7 FFMA2/FADD2/FMUL2 per ray (two rays per
-//    instruction) + 1 MUFU.RCP + 3 integer ops:
+//    instruction) + 1 MUFU.RCP + 2 integer compares:
 //        det = D[k] + m1 D[k1] + m2 D[k2]      t' = dd - O[k] - m1 O[k1] - m2 O[k2]
 //        t   = t'/det     (origin pre-shifted by ray_start_eps so t >= 0 <=> valid)
 //        P1  = O[k1] + t D[k1]                 P2 = O[k2] + t D[k2]
-//        u   = a1 P1 + a2 P2 + a0              v  = b1 P1 + b2 P2 + b0
-//        w   = (1+3 eps) - u - v
-//    valid & nearer  <=>  (bits(t) | signbit(u|v|w))  <  best   as unsigned integers;
+//        S   = s1 P1 + s2 P2 + s0  (= 2(u+v) - C)      E = e1 P1 + e2 P2 + e0  (= u - v)
+//        x   = |E| + |S - |E||     (absolute values are free operand modifiers of FADD2)
+//    with u, v the barycentrics inflated by size_eps and C = 1 + 3 size_eps:
+//        inside  <=>  u >= 0, v >= 0, u + v <= C  <=>  x <= C
+//    (min(u,v) = (u+v-|u-v|)/2 and min(p,q) >= 0 <=> p+q >= |p-q|, applied twice), so
+//    valid & nearer  <=>  bits(x) <= bits(C)  and  bits(t) < best   as unsigned integers
+//    (negative t, NaN and +inf all compare high);
 //    the triangles of a tile are grouped by k, so three specialised loops run back to back
 //    with the roles of the ray components fixed at compile time;
-//  * the running best is (key, triangle index); the scan is in index order inside an axis
+//  * the running best is (bits(t), triangle index); the scan is in index order inside an axis
 //    group and strict '<' keeps the first, so exact ties between triangles of one group (e.g.
 //    the coplanar halves of a flat target) go to the lowest index, the behaviour of argmin in
 //    the reference's CPU kernels; an exact tie between triangles of different dominant axes of
@@ -96,6 +100,7 @@ __device__ __forceinline__ float2 k_mul2(float2 a, float2 b) { return __fmul2_rn
 __device__ __forceinline__ float2 k_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 #endif
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
 
 template <int R2, bool kQueue>
 __global__ void __launch_bounds__(kThreads, (R2 >= 4 ? TFRT_K1_MINBLOCKS : 1))
@@ -181,7 +186,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             for (int i = 0; i < kStages; ++i) produce_one();   // fill the ring
     }
 
-    const float2 one2 = f2(w_one, w_one);   // 1 + 3*size_eps (eps is folded into ad, bd)
+    const uint32_t c_bits = __float_as_uint(w_one);   // C = 1 + 3*size_eps (eps is folded into the planes)
     uint32_t seq = 0;                       // tiles this warp (CTA) has consumed so far
     for (int item_seq = 0;; ++item_seq) {
         int item;
@@ -260,10 +265,9 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                     const float4 q2 = tile[j * 3 + 2];
                     // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
                     const float2 m1 = f2(q0.x, q0.x), m2 = f2(q0.y, q0.y), dd = f2(q0.z, q0.z);
-                    const float2 a1 = f2(q1.x, q1.x), a2 = f2(q1.y, q1.y), a0 = f2(q1.z, q1.z);
-                    const float2 b1 = f2(q2.x, q2.x), b2 = f2(q2.y, q2.y), b0 = f2(q2.z, q2.z);
-                    uint32_t key[2 * R2];
-                    float2 dets[R2];
+                    const float2 s1 = f2(q1.x, q1.x), s2 = f2(q1.y, q1.y), s0 = f2(q1.z, q1.z);
+                    const float2 e1 = f2(q2.x, q2.x), e2 = f2(q2.y, q2.y), e0 = f2(q2.z, q2.z);
+                    float2 tt[R2], xx[R2], dets[R2];
                     bool cand = false;
 #pragma unroll
                     for (int r = 0; r < R2; ++r) {
@@ -278,20 +282,23 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                         const float2 t = k_mul2(tq, inv);
                         const float2 p1 = k_fma2(t, D[K1][r], O[K1][r]);
                         const float2 p2 = k_fma2(t, D[K2][r], O[K2][r]);
-                        float2 u = k_fma2(a1, p1, a0);
-                        u = k_fma2(a2, p2, u);
-                        float2 v = k_fma2(b1, p1, b0);
-                        v = k_fma2(b2, p2, v);
-                        float2 w = k_add2(one2, neg2(u));
-                        w = k_add2(w, neg2(v));
-                        // sign bit of (u|v|w) set <=> outside the (inflated) triangle: fold into key
-                        key[2 * r] = __float_as_uint(t.x) |
-                                     ((__float_as_uint(u.x) | __float_as_uint(v.x) |
-                                       __float_as_uint(w.x)) & 0x80000000u);
-                        key[2 * r + 1] = __float_as_uint(t.y) |
-                                         ((__float_as_uint(u.y) | __float_as_uint(v.y) |
-                                           __float_as_uint(w.y)) & 0x80000000u);
-                        cand |= (key[2 * r] < best[2 * r]) | (key[2 * r + 1] < best[2 * r + 1]);
+                        // S = 2(u+v) - C and E = u - v straight from their own planes; then
+                        //   x = |E| + |S - |E||  <=  C   <=>   u >= 0, v >= 0, u + v <= C
+                        // (min(u,v) = (u+v-|u-v|)/2 and min(p,q) >= 0 <=> p+q >= |p-q|, twice);
+                        // the absolute values are free operand modifiers of FADD2.
+                        float2 sv = k_fma2(s1, p1, s0);
+                        sv = k_fma2(s2, p2, sv);
+                        float2 ev = k_fma2(e1, p1, e0);
+                        ev = k_fma2(e2, p2, ev);
+                        const float2 ea = abs2(ev);
+                        const float2 kk = k_add2(sv, neg2(ea));
+                        const float2 x = k_add2(ea, abs2(kk));
+                        // valid & nearer <=> bits(x) <= bits(C) and bits(t) < best as unsigned
+                        // integers (negative t, NaN and +inf all compare high)
+                        cand |= (__float_as_uint(x.x) <= c_bits && __float_as_uint(t.x) < best[2 * r]) |
+                                (__float_as_uint(x.y) <= c_bits && __float_as_uint(t.y) < best[2 * r + 1]);
+                        tt[r] = t;
+                        xx[r] = x;
                         dets[r] = det;
                     }
                     // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so
@@ -301,16 +308,22 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                         // |det * n[k]| >= intersect_eps is the reference's safe-denominator
                         // validity (tfrt/geometry.py:306)
                         const float nk = q1.w;
+                        // the conditions are re-evaluated from an opaque copy of C, so that the
+                        // common path does not have to keep eight per-ray predicates alive
+                        uint32_t c_rare = c_bits;
+                        asm volatile("" : "+r"(c_rare));
 #pragma unroll
                         for (int r = 0; r < R2; ++r) {
-                            if (key[2 * r] < best[2 * r] &&
+                            if (__float_as_uint(xx[r].x) <= c_rare &&
+                                __float_as_uint(tt[r].x) < best[2 * r] &&
                                 fabsf(dets[r].x * nk) >= intersect_eps) {
-                                best[2 * r] = key[2 * r];
+                                best[2 * r] = __float_as_uint(tt[r].x);
                                 bidx[2 * r] = tri;
                             }
-                            if (key[2 * r + 1] < best[2 * r + 1] &&
+                            if (__float_as_uint(xx[r].y) <= c_rare &&
+                                __float_as_uint(tt[r].y) < best[2 * r + 1] &&
                                 fabsf(dets[r].y * nk) >= intersect_eps) {
-                                best[2 * r + 1] = key[2 * r + 1];
+                                best[2 * r + 1] = __float_as_uint(tt[r].y);
                                 bidx[2 * r + 1] = tri;
                             }
                         }

@@ -18,10 +18,10 @@ k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
     __shared__ int s_cnt[3][TFRT_TILE_TRIS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i = blockIdx.x * TFRT_TILE_TRIS + threadIdx.x;
-    // never-hit record (padding, degenerate triangles): u = -1 => sign bit set => never valid
+    // never-hit record (padding, degenerate triangles): S = 4, E = 0 => x = 4 > C => never valid
     int k = 0;
     float n1 = 0.f, n2 = 0.f, dd = 0.f, nk = 0.f;
-    float au1 = 0.f, au2 = 0.f, au0 = -1.f, bv1 = 0.f, bv2 = 0.f, bv0 = -1.f;
+    float au1 = 0.f, au2 = 0.f, au0 = 4.f, bv1 = 0.f, bv2 = 0.f, bv0 = 0.f;
     if (i < n_tri) {
         const double A[3] = {xp[i], yp[i], zp[i]};
         const double e1[3] = {x1[i] - A[0], y1[i] - A[1], z1[i] - A[2]};
@@ -49,10 +49,13 @@ k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
             const double dk = A[k] + m1 * A[k1] + m2 * A[k2];
             n1 = (float)m1; n2 = (float)m2; dd = (float)dk; nk = (float)N[k];
             // u = a.P + ad with P[k] eliminated (exact on the plane)
-            au1 = (float)(av[k1] - av[k] * m1); au2 = (float)(av[k2] - av[k] * m2);
-            au0 = (float)(ad + av[k] * dk);
-            bv1 = (float)(bv[k1] - bv[k] * m1); bv2 = (float)(bv[k2] - bv[k] * m2);
-            bv0 = (float)(bd + bv[k] * dk);
+            const double u1 = av[k1] - av[k] * m1, u2 = av[k2] - av[k] * m2, u0 = ad + av[k] * dk;
+            const double v1 = bv[k1] - bv[k] * m1, v2 = bv[k2] - bv[k] * m2, v0 = bd + bv[k] * dk;
+            // the kernel tests the planes S = 2(u+v) - C and E = u - v (see intersect3d.cu)
+            const double C = 1.0 + 3.0 * (double)size_eps;
+            au1 = (float)(2.0 * (u1 + v1)); au2 = (float)(2.0 * (u2 + v2));
+            au0 = (float)(2.0 * (u0 + v0) - C);
+            bv1 = (float)(u1 - v1); bv2 = (float)(u2 - v2); bv0 = (float)(u0 - v0);
         }
     }
     // stable partition by k inside the tile
