@@ -18,7 +18,9 @@ out = ["# Round 1 — bench.py lines (B200, `gpurun`)\n",
        "Raw JSON printed by `python bench.py --config <cfg>` (default steps 3, warm-up 3; cfg5 is the "
        "default config). `value` = ray×boundary tests/s of the step with rays resident in HBM; `e2e` = the "
        "same step from pinned host rays with gradients/loss copied back; `roofline.frac` = 45 FLOP × tests "
-       "÷ kernel time ÷ the FP32 FMA peak measured in the same run.\n",
+       "÷ kernel time ÷ the FP32 FMA peak measured in the same run — the ALGORITHMIC Möller–Trumbore count; the "
+       "kernel's projected plane form executes 25 FLOP per test, so the fraction exceeds 1 while the FMA pipe "
+       "(14 lane-slots per test, next column) is about 70 % busy.\n",
        "| config | workload | ms/step | tests/s | rays/s | fwd-only tests/s | roofline.frac | FMA-pipe "
        "slots busy | e2e tests/s | CPU baseline tests/s (cores) |",
        "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
