@@ -307,6 +307,32 @@ def mixed_2d(ray_count=2000, seed=7):
     return scene
 
 
+def segments_2d(ray_count=240, seed=11):
+    """Segments only (the reference pairs rays and boundaries wrongly when segments and arcs are
+    mixed), every category and reaction branch of the 2D path: a tilted acrylic
+    slab (refraction in and out, six wavelengths), a mirror segment hit from both sides (the 2D
+    zero-index rule is one-sided, tfrt/geometry.py:618-646), a right-angle prism with total internal
+    reflection on its hypotenuse (dev/light_guide.py:31-37 style), a stop and a target segment."""
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-0.5, 0.5, ray_count)
+    starts = np.stack([np.full(ray_count, -3.0), rng.uniform(-0.4, 0.4, ray_count)], 1)
+    wl = np.asarray(RAINBOW_6)[np.arange(ray_count) % 6]
+    src = rays_2d(starts, ang, wl)
+    slab = {"segments": np.array([[0.0, 1.0, 0.1, -1.0], [0.5, -1.0, 0.4, 1.0]]),
+            "mat_in": 1, "mat_out": 0}
+    mirror = {"segments": np.array([[-1.0, 1.5, 3.0, 1.8], [3.0, -1.9, -1.0, -1.6]]),
+              "mat_in": 2, "mat_out": 0}
+    prism = {"segments": np.array([[2.0, -0.6, 2.0, 0.6], [2.0, 0.6, 3.2, -0.6], [3.2, -0.6, 2.0, -0.6]]),
+             "mat_in": 1, "mat_out": 0}
+    stop = {"segments": np.array([[4.5, 0.9, 4.5, 3.0]])}
+    target = {"segments": np.array([[6.0, -6.0, 6.0, 6.0]])}
+    scene = _scene2d(f"segments_2d_{ray_count}rays", src, 7,
+                     optical_segments=[slab, mirror, prism], stop_segments=[stop],
+                     target_segments=[target])
+    scene["materials"] = ["vacuum", "acrylic", "reflective"]
+    return scene
+
+
 def build_engine_2d(scene, eps=None, parametric=False, **engine_kwargs):
     """Instantiate a 2D scene through the public API (ManualSegmentBoundary / ManualArcBoundary
     / OpticalSystem2D / OpticalEngine + StandardReaction), as dev/single_pass.py:34-72 does.

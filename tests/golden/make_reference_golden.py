@@ -36,8 +36,8 @@ import torch  # noqa: E402
 
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-from oracle.reference_runner import (EPS, RAYS2, RAYS3, f32_round, import_reference,  # noqa: E402
-                                     reference_engine_2d, reference_engine_3d)
+from oracle.reference_runner import (EPS, RAYS2, RAYS3, _polydata, f32_round,  # noqa: E402
+                                     import_reference, reference_engine_2d, reference_engine_3d)
 
 
 def golden_scenes():
@@ -51,6 +51,7 @@ def golden_scenes():
         "ref_mirror_stop3d": scenes.mirror_stop_3d(),
         "ref_wedge2d": scenes.config1(ray_count=64),
         "ref_arclens2d": scenes.arc_lens_2d(ray_count=90),
+        "ref_segments2d": scenes.segments_2d(),
     }
 
 
@@ -308,6 +309,135 @@ def optimizer_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- multi-surface flow
+
+MULTI_STEPS = ((1.0, 0.0), (1.0, 0.7), (0.5, 0.7))       # (lr_scale, momentum) per step
+MULTI_KW = dict(learning_rate=0.002)
+MULTI_RINGS, MULTI_SIDE = 4, 8
+
+
+def multisurface_inputs():
+    """Plain-data description shared by the generator (reference classes) and the GPU test (ours):
+    hexagonal zero-point disk in the y-z plane, initial parameters of the two surfaces."""
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import mesh_tools
+    pts, faces = mesh_tools.hexagonal_mesh(1.0, MULTI_RINGS)
+    verts = np.stack([np.zeros(len(pts)), pts[:, 0], pts[:, 1]], axis=1)
+    r2 = pts[:, 0] ** 2 + pts[:, 1] ** 2
+    return verts, faces, [-0.1 * (1.0 - r2), 0.25 + 0.1 * (1.0 - r2)]
+
+
+def multisurface_vectors(ref):
+    """The optimisation flow of dev/simple_3d_optimize.py:22-140 on the reference's own classes:
+    `mesh_tools.get_closest_point / mesh_parametrization_tools / mesh_smoothing_tool`,
+    `ParametricMultiTriangleBoundary` + `ThicknessConstraint`s + `vertex_update_map`, an undense
+    `AngularSource` with a rank field, `SGD_Optimizer.single_step` with accumulators, `smooth`."""
+    import tfrt.distributions as rd
+    import tfrt.mesh_tools as rmt
+    import tfrt.optimizer as ropt
+    tf = ref.tf
+    verts, faces, init = multisurface_inputs()
+    zero = _polydata(ref, verts, faces)
+    top = rmt.get_closest_point(zero, (0, 0, 0))
+    vum, acc = rmt.mesh_parametrization_tools(zero, top)
+    smo = rmt.mesh_smoothing_tool(zero, [1.0, 0.02])
+    out = {"top_parent": np.array(top), "vertex_update_map": np.asarray(vum).astype(np.bool_),
+           "accumulator": np.asarray(acc, dtype=np.float64), "smoother": np.asarray(smo, dtype=np.float64)}
+    base_points = rd.StaticUniformSquare(0.2, MULTI_SIDE)
+    angles = rd.StaticUniformSphere(math.pi / 16.0, MULTI_SIDE * MULTI_SIDE)
+    source = ref.sources.AngularSource(
+        3, (-4.0, 0.0, 0.0), (1.0, 0.0, 0.0), angles, base_points, [575.0] * (MULTI_SIDE * MULTI_SIDE),
+        dense=False, extra_fields={"rank": ("base_point", base_points, "ranks")})
+    mat = {"mat_in": tf.constant(1, dtype=tf.int64), "mat_out": tf.constant(0, dtype=tf.int64)}
+    lens = ref.boundaries.ParametricMultiTriangleBoundary(
+        zero, ref.boundaries.FromVectorVG((1, 0, 0)),
+        [ref.boundaries.ThicknessConstraint(0.0, "min"), ref.boundaries.ThicknessConstraint(0.2, "min")],
+        [True, False], initial_parameters=[torch.from_numpy(f32_round(p)) for p in init],
+        material_list=[mat, mat], vertex_update_map=vum)
+    tv = np.array([[8.0, -50.0, -50.0], [8.0, 50.0, -50.0], [8.0, 50.0, 50.0], [8.0, -50.0, 50.0]])
+    target = ref.boundaries.ManualTriangleBoundary(mesh=_polydata(ref, tv, np.array([[0, 1, 2], [0, 2, 3]])))
+    system = ref.engine.OpticalSystem3D(**EPS)
+    system.optical = lens.surfaces
+    system.targets = [target]
+    system.sources = [source]
+    system.materials = [{"n": ref.materials.vacuum}, {"n": ref.materials.acrylic}]
+    system.update()
+    eng = ref.engine.OpticalEngine(3, [ref.operation.StandardReaction()],
+                                   simple_ray_inheritance={"wavelength", "rank"})
+    eng.optical_system = system
+    eng.validate_system()
+    for i, p in enumerate(lens.parameters):                     # constraints applied by update()
+        out[f"constrained_{i}"] = p.numpy().copy()
+    for f in ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2", "norm"):
+        out[f"merged_{f}"] = system._merged[f].numpy().astype(np.float64)
+
+    def error_function(engine):
+        output = tf.stack([engine.finished_rays["y_end"], engine.finished_rays["z_end"]], axis=1)
+        return tf.math.squared_difference(output, engine.finished_rays["rank"] * (-0.4))
+
+    opt = ropt.SGD_Optimizer(eng, lens.parameters, error_function, 3, **MULTI_KW)
+    accs = [torch.from_numpy(out["accumulator"])] * 2
+    smoother = torch.from_numpy(out["smoother"])
+    errors = []
+    for k, (lr_scale, momentum) in enumerate(MULTI_STEPS):
+        errors.append(float(opt.single_step(accs, lr_scale=lr_scale, momentum=momentum)))
+        for p in lens.parameters:
+            opt.smooth(p, smoother)
+        for i, p in enumerate(lens.parameters):
+            out[f"step{k}_{i}"] = p.numpy().copy()
+    system.update()                                             # re-applies the constraints
+    for i, p in enumerate(lens.parameters):
+        out[f"final_{i}"] = p.numpy().copy()
+    out["errors"] = np.array(errors)
+    return out
+
+
+# ------------------------------------------------------------------------------- two sources + OldestAncestor
+
+TWO_SPLIT = 70
+
+
+def two_source_scene():
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import scenes
+    return scenes.lens_optimize_config(ray_count=180, step_count=3, seed=5, name="golden_two")
+
+
+def two_source_vectors(ref):
+    """Two `ManualSource`s in one system (amalgamation order, tfrt/engine.py:203-216) traced with
+    `[StandardReaction(), OldestAncestor()]` (tfrt/operation.py:166-196): every history set carries
+    the running source index of the ray it descends from."""
+    scene = two_source_scene()
+    eng, system, params = reference_engine_3d(ref, scene)           # boundaries, materials
+    srcs = []
+    for sl in (slice(0, TWO_SPLIT), slice(TWO_SPLIT, None)):
+        src = ref.sources.ManualSource(3)
+        for k, v in scene["sources"].items():
+            src[k] = torch.from_numpy(np.ascontiguousarray(f32_round(v[sl])))
+        srcs.append(src)
+    system.sources = srcs
+    eng2 = ref.engine.OpticalEngine(3, [ref.operation.StandardReaction(), ref.operation.OldestAncestor()],
+                                    compile_dead_rays=True, simple_ray_inheritance={"wavelength", "rank"})
+    eng2.optical_system = system
+    eng2.annotate()
+    system.update()
+    eng2.validate_system()
+    eng2.ray_trace(scene["max_iterations"])
+    out = {}
+    for set_name in ("active", "finished", "dead"):
+        s = getattr(eng2, set_name + "_rays")
+        try:
+            anc = s["oldest_ancestor"]
+        except KeyError:
+            continue
+        if anc.shape[0] == 0:
+            continue
+        out[f"{set_name}_oldest_ancestor"] = anc.numpy().astype(np.int64)
+        for f in RAYS3:
+            out[f"{set_name}_{f}"] = s[f].numpy().astype(np.float64)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -318,6 +448,14 @@ def main():
     path = os.path.join(HERE, "ref_sources.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = two_source_vectors(ref)
+    path = os.path.join(HERE, "ref_two_sources.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, sets { {k: v.shape for k, v in data.items() if k.endswith('ancestor')} }")
+    data = multisurface_vectors(ref)
+    path = os.path.join(HERE, "ref_multisurface.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, errors {data['errors']}")
     data = optimizer_vectors(ref)
     path = os.path.join(HERE, "ref_optimizer.npz")
     np.savez_compressed(path, **data)

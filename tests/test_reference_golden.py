@@ -268,3 +268,136 @@ def test_optimizer_trajectory_matches_reference():
             moved = np.abs(want[f"step{k}_{i}"] - want[f"initial_{i}"]).max()
             diff = np.abs(params[i].detach().cpu().numpy() - want[f"step{k}_{i}"]).max()
             assert diff < 2e-4 * moved + 1e-7, (k, i, diff, moved)
+
+
+# ------------------------------------------------------------------------------------ multi-surface flow
+
+def _multisurface_ours(device):
+    """The fixture's scene on this package's classes (same constructor calls as the reference)."""
+    import math
+    from tensorflowraytrace_b200 import boundaries, distributions, engine, materials, mesh_tools, \
+        operation, sources
+    verts, faces, init = mrg.multisurface_inputs()
+    zero = boundaries.TriangleMesh(verts, faces)
+    top = mesh_tools.get_closest_point(zero, (0, 0, 0))
+    vum, acc = mesh_tools.mesh_parametrization_tools(zero, top)
+    smo = mesh_tools.mesh_smoothing_tool(zero, [1.0, 0.02])
+    if device is None:
+        return zero, top, vum, acc, smo
+    side = mrg.MULTI_SIDE
+    base_points = distributions.StaticUniformSquare(0.2, side)
+    angles = distributions.StaticUniformSphere(math.pi / 16.0, side * side)
+    source = sources.AngularSource(
+        3, (-4.0, 0.0, 0.0), (1.0, 0.0, 0.0), angles, base_points, [575.0] * (side * side),
+        dense=False, extra_fields={"rank": ("base_point", base_points, "ranks")})
+    mat = {"mat_in": np.int64(1), "mat_out": np.int64(0)}
+    lens = boundaries.ParametricMultiTriangleBoundary(
+        zero, boundaries.FromVectorVG((1, 0, 0)),
+        [boundaries.ThicknessConstraint(0.0, "min"), boundaries.ThicknessConstraint(0.2, "min")],
+        [True, False], initial_parameters=init, material_list=[mat, mat], vertex_update_map=vum)
+    tv = np.array([[8.0, -50.0, -50.0], [8.0, 50.0, -50.0], [8.0, 50.0, 50.0], [8.0, -50.0, 50.0]])
+    target = boundaries.ManualTriangleBoundary(
+        mesh=boundaries.TriangleMesh(tv, np.array([[0, 1, 2], [0, 2, 3]])))
+    system = engine.OpticalSystem3D(**helpers.EPS)
+    system.optical = lens.surfaces
+    system.targets = [target]
+    system.sources = [source]
+    system.materials = [{"n": materials.vacuum}, {"n": materials.acrylic}]
+    system.update()
+    eng = engine.OpticalEngine(3, [operation.StandardReaction()],
+                               simple_ray_inheritance={"wavelength", "rank"})
+    eng.optical_system = system
+    eng.validate_system()
+    return eng, system, lens, acc, smo
+
+
+def test_mesh_tools_match_reference_functions():
+    """`get_closest_point`, `mesh_parametrization_tools`, `mesh_smoothing_tool` (sparse here) against
+    the dense arrays the reference's own tfrt/mesh_tools.py:221-421 produced for the same mesh."""
+    want = load("ref_multisurface")
+    zero, top, vum, acc, smo = _multisurface_ours(None)
+    assert int(top) == int(want["top_parent"])
+    assert np.array_equal(np.asarray(vum).astype(bool), want["vertex_update_map"])
+    assert np.abs(acc.toarray() - want["accumulator"]).max() == 0.0
+    assert np.abs(smo.toarray() - want["smoother"]).max() < 1e-15
+
+
+@pytest.mark.gpu
+def test_multisurface_optimisation_flow_matches_reference():
+    """dev/simple_3d_optimize.py's flow end to end on the CUDA path against the reference's own classes:
+    constraints applied by update(), merged fields with vertex_update_map, three
+    `single_step(accumulators)` + `smooth` rounds, constraints re-applied."""
+    from tensorflowraytrace_b200 import mesh_tools, optimizer
+    want = load("ref_multisurface")
+    eng, system, lens, acc, smo = _multisurface_ours("cuda")
+    for i, p in enumerate(lens.parameters):
+        assert np.abs(p.detach().cpu().numpy() - want[f"constrained_{i}"]).max() < 1e-6, i
+    tri, norm, _, _ = system.merged_device_arrays()
+    for c, f in enumerate(("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")):
+        assert np.abs(tri[c].cpu().numpy() - want[f"merged_{f}"]).max() < 1e-6, f
+    assert np.abs(norm.cpu().numpy() - want["merged_norm"]).max() < 1e-5
+
+    def error_function(engine):
+        fin = engine.finished_rays
+        output = torch.stack([fin["y_end"], fin["z_end"]], dim=1)
+        return (output - fin["rank"] * (-0.4)) ** 2
+
+    opt = optimizer.SGD_Optimizer(eng, lens.parameters, error_function, 3, **mrg.MULTI_KW)
+    accs = [mesh_tools.to_torch_sparse(acc, "cuda")] * 2
+    smoother = mesh_tools.to_torch_sparse(smo, "cuda")
+    for k, (lr_scale, momentum) in enumerate(mrg.MULTI_STEPS):
+        e = opt.single_step(accs, lr_scale=lr_scale, momentum=momentum)
+        assert abs(float(e) - float(want["errors"][k])) < 2e-4 * float(want["errors"][k]), k
+        for p in lens.parameters:
+            opt.smooth(p, smoother)
+        for i, p in enumerate(lens.parameters):
+            moved = np.abs(want[f"step{k}_{i}"] - want[f"constrained_{i}"]).max()
+            diff = np.abs(p.detach().cpu().numpy() - want[f"step{k}_{i}"]).max()
+            assert diff < 5e-4 * moved + 2e-7, (k, i, diff, moved)
+    system.update()
+    for i, p in enumerate(lens.parameters):
+        assert np.abs(p.detach().cpu().numpy() - want[f"final_{i}"]).max() < 2e-6, i
+
+
+# ------------------------------------------------------------------------------------ two sources, OldestAncestor
+
+def test_oracle_matches_reference_two_sources():
+    """Amalgamation order of two sources: the reference's `oldest_ancestor` (running index over the
+    sources, tfrt/operation.py:186-193) equals the oracle's slot of the concatenated rays."""
+    want = load("ref_two_sources")
+    scene = mrg.two_source_scene()
+    eng, _ = helpers.oracle_from_scene(scene, fp32_vertices=False, compile_dead_rays=True)
+    eng.ray_trace(scene["max_iterations"])
+    for set_name in ("active", "finished"):
+        s = getattr(eng, set_name + "_rays")
+        assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_oldest_ancestor"])
+        for f in helpers.RAY_FIELDS:
+            assert close(s[f].detach().numpy(), want[f"{set_name}_{f}"], 1e-10), (set_name, f)
+
+
+@pytest.mark.gpu
+def test_cuda_two_sources_and_oldest_ancestor_match_reference():
+    from tensorflowraytrace_b200 import engine as eng_mod, operation, scenes, sources
+    want = load("ref_two_sources")
+    scene = mrg.two_source_scene()
+    base, _, _ = scenes.build_engine(scene, eps=helpers.EPS)
+    system = base.optical_system
+    srcs = []
+    for sl in (slice(0, mrg.TWO_SPLIT), slice(mrg.TWO_SPLIT, None)):
+        src = sources.ManualSource(3)
+        src.feed({k: v[sl] for k, v in scene["sources"].items()})
+        srcs.append(src)
+    system.sources = srcs
+    e = eng_mod.OpticalEngine(3, [operation.StandardReaction(), operation.OldestAncestor()],
+                              compile_dead_rays=True, simple_ray_inheritance={"wavelength", "rank"})
+    e.optical_system = system
+    e.annotate()
+    system.update()
+    e.validate_system()
+    e.ray_trace(scene["max_iterations"])
+    for set_name in ("active", "finished"):
+        s = getattr(e, set_name + "_rays")
+        assert np.array_equal(s["oldest_ancestor"].cpu().numpy().astype(np.int64),
+                              want[f"{set_name}_oldest_ancestor"]), set_name
+        for f in helpers.RAY_FIELDS:
+            assert helpers.rel_err(s[f].detach().cpu().numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
