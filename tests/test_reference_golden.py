@@ -334,8 +334,8 @@ def test_multisurface_optimisation_flow_matches_reference():
         assert np.abs(p.detach().cpu().numpy() - want[f"constrained_{i}"]).max() < 1e-6, i
     tri, norm, _, _ = system.merged_device_arrays()
     for c, f in enumerate(("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")):
-        assert np.abs(tri[c].cpu().numpy() - want[f"merged_{f}"]).max() < 1e-6, f
-    assert np.abs(norm.cpu().numpy() - want["merged_norm"]).max() < 1e-5
+        assert np.abs(tri[c].detach().cpu().numpy() - want[f"merged_{f}"]).max() < 1e-6, f
+    assert np.abs(norm.detach().cpu().numpy() - want["merged_norm"]).max() < 1e-5
 
     def error_function(engine):
         fin = engine.finished_rays
