@@ -474,6 +474,22 @@ def _numpy(self, *a, **k):
 _torch.Tensor.numpy = _numpy
 
 
+def _reflected(name):
+    """TF converts python sequences on the left of a tensor operator (`(0, 0, 4) - tensor`); torch's
+    reflected operators return NotImplemented for them."""
+    orig = getattr(_torch.Tensor, name)
+
+    def op(self, other):
+        if isinstance(other, (list, tuple)):
+            other = _torch.as_tensor(other, dtype=self.dtype)
+        return orig(self, other)
+    return op
+
+
+for _name in ("__rsub__", "__radd__", "__rmul__", "__rtruediv__"):
+    setattr(_torch.Tensor, _name, _reflected(_name))
+
+
 class GradientTape:
     def __init__(self, persistent=False, watch_accessed_variables=True):
         self.persistent = persistent

@@ -438,6 +438,79 @@ def two_source_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- a12 variants
+
+def boundary_inputs():
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import mesh_tools
+    pts, faces = mesh_tools.hexagonal_mesh(1.0, 3)
+    verts = np.stack([np.zeros(len(pts)), pts[:, 0], pts[:, 1]], axis=1)
+    masters = [i for i in range(len(verts)) if verts[i, 2] >= -1e-9]      # mirror symmetry in z
+    init = 0.1 * (1.0 - pts[:, 0] ** 2 - pts[:, 1] ** 2)
+    return verts, faces, masters, init
+
+
+def attach_mirror_slaves(v, m, free):
+    v = np.asarray(v.detach().cpu() if hasattr(v, "detach") else v)
+    return {s for s in free if abs(v[s, 1] - v[m, 1]) < 1e-6 and abs(v[s, 2] + v[m, 2]) < 1e-6}
+
+
+GUIDE_ARGS = ((0.0, 0.0, 0.0), (4.0, 0.0, 0.0), 0.5)
+# caps off: with caps the reference prunes the cap vertices out of `_vertices` but keeps the faces
+# that index them (tfrt/boundaries.py:1608, :1703-1717), so its own gather goes out of range
+GUIDE_KW = dict(theta_res=10, z_res=7, initial_taper=(0.05, 0.2), start_cap=False, end_cap=False)
+
+
+def boundary_weights(n_faces, seed):
+    rng = np.random.default_rng(seed)
+    return rng.normal(size=(n_faces, 12))
+
+
+def _boundary_record(ref, out, name, b):
+    """Fields of a reference boundary + tape gradient of a fixed random functional of them."""
+    tf = ref.tf
+    n = int(b["xp"].shape[0])
+    w = torch.from_numpy(boundary_weights(n, n))
+    with tf.GradientTape() as tape:
+        b.update()
+        cols = [b[k] for k in ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")]
+        loss = sum((c * w[:, i]).sum() for i, c in enumerate(cols)) + (b["norm"] * w[:, 9:12]).sum()
+        grad = tape.gradient(loss, b.parameters)
+    out[f"{name}_parameters"] = b.parameters.numpy().copy()
+    out[f"{name}_vertices"] = b._vertices.numpy().copy()
+    for i, k in enumerate(("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")):
+        out[f"{name}_{k}"] = cols[i].numpy().copy()
+    out[f"{name}_norm"] = b["norm"].numpy().copy()
+    out[f"{name}_faces"] = np.asarray(b._faces)[:, 1:4].astype(np.int64)
+    out[f"{name}_grad"] = grad.numpy().copy()
+    out[f"{name}_loss"] = np.array(float(loss.detach()))
+
+
+def boundary_vectors(ref):
+    """`MasterSlaveParametricTriangleBoundary` (gather, tfrt/boundaries.py:1116-1224) and
+    `ParametricCylindricalGuide` (min-pinning constraint, repeat / pad, :1416-1611), full and
+    rotationally symmetric: parameters -> vertices -> fields -> norm, and the tape gradient."""
+    B = ref.boundaries
+    out = {}
+    verts, faces, masters, init = boundary_inputs()
+    ms = B.MasterSlaveParametricTriangleBoundary(
+        masters, attach_mirror_slaves, _polydata(ref, verts, faces), B.FromVectorVG((1, 0, 0)),
+        initial_parameters=torch.from_numpy(f32_round(init)), material_dict={})
+    out["ms_gather"] = np.asarray(ms._gather).astype(np.int64)
+    _boundary_record(ref, out, "ms", ms)
+    # (material_dict cannot be passed to the guide: the reference forwards **kwargs to
+    # mesh_tools.cylindrical_mesh, tfrt/boundaries.py:1525-1534)
+    for name, sym in (("guide", False), ("guide_sym", True)):
+        g = B.ParametricCylindricalGuide(*GUIDE_ARGS, rotationally_symmetric=sym, **GUIDE_KW)
+        with torch.no_grad():                       # a non-trivial shape: bump the parameters
+            bump = 0.03 * torch.sin(torch.arange(g.parameters.shape[0], dtype=torch.float64) * 0.7)
+            g.parameters.add_(torch.from_numpy(f32_round(bump.numpy())))
+        _boundary_record(ref, out, name, g)
+        out[f"{name}_accumulator"] = np.asarray(g._accumulator, dtype=np.float64)
+        out[f"{name}_vertex_update_map"] = np.asarray(g._vertex_update_map).astype(np.bool_)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -446,6 +519,10 @@ def main():
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
     data = source_vectors(ref)
     path = os.path.join(HERE, "ref_sources.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = boundary_vectors(ref)
+    path = os.path.join(HERE, "ref_boundaries.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
     data = two_source_vectors(ref)

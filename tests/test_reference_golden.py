@@ -401,3 +401,50 @@ def test_cuda_two_sources_and_oldest_ancestor_match_reference():
                               want[f"{set_name}_oldest_ancestor"]), set_name
         for f in helpers.RAY_FIELDS:
             assert helpers.rel_err(s[f].detach().cpu().numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+
+
+# ------------------------------------------------------------------------------------ a12 variants
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ms", "guide", "guide_sym"])
+def test_parametric_boundary_variants_match_reference(name):
+    """parameters -> vertices -> fields -> unit normal and the gradient back to the
+    parameters for `MasterSlaveParametricTriangleBoundary` (gather) and `ParametricCylindricalGuide`
+    (min-pinning constraint, repeat for rotational symmetry), against the arrays and the
+    GradientTape gradient of the reference's own classes (tfrt/boundaries.py:890-923, 1116-1224,
+    1416-1611)."""
+    from tensorflowraytrace_b200 import boundaries as B
+    want = load("ref_boundaries")
+    mat = {"mat_in": np.int64(1), "mat_out": np.int64(0)}
+    if name == "ms":
+        verts, faces, masters, init = mrg.boundary_inputs()
+        b = B.MasterSlaveParametricTriangleBoundary(
+            masters, mrg.attach_mirror_slaves, B.TriangleMesh(verts, faces), B.FromVectorVG((1, 0, 0)),
+            initial_parameters=init, material_dict=mat)
+        assert np.array_equal(b._gather.cpu().numpy().astype(np.int64), want["ms_gather"])
+    else:
+        b = B.ParametricCylindricalGuide(*mrg.GUIDE_ARGS, rotationally_symmetric=(name == "guide_sym"),
+                                         material_dict=mat, **mrg.GUIDE_KW)
+        n = b.parameters.shape[0]
+        bump = 0.03 * torch.sin(torch.arange(n, dtype=torch.float64) * 0.7)
+        with torch.no_grad():
+            b.parameters.add_(torch.tensor(helpers.f32_round(bump.numpy()), dtype=b.parameters.dtype,
+                                           device=b.parameters.device))
+        assert np.array_equal(np.asarray(b.vertex_update_map).astype(bool), want[f"{name}_vertex_update_map"])
+        acc = b.accumulator
+        acc = acc.toarray() if hasattr(acc, "toarray") else np.asarray(acc.to_dense().cpu() if hasattr(acc, "to_dense") else acc)
+        assert np.abs(acc - want[f"{name}_accumulator"]).max() == 0.0
+    b.update()
+    assert np.abs(b.parameters.detach().cpu().numpy() - want[f"{name}_parameters"]).max() < 1e-6
+    assert np.array_equal(b.faces.cpu().numpy().astype(np.int64), want[f"{name}_faces"])
+    assert np.abs(b.vertices.detach().cpu().numpy() - want[f"{name}_vertices"]).max() < 1e-6
+    fields = ("xp", "yp", "zp", "x1", "y1", "z1", "x2", "y2", "z2")
+    for k in fields:
+        assert np.abs(b[k].detach().cpu().numpy() - want[f"{name}_{k}"]).max() < 1e-6, k
+    assert np.abs(b["norm"].detach().cpu().numpy() - want[f"{name}_norm"]).max() < 1e-5
+    n_faces = b["xp"].shape[0]
+    w = torch.tensor(mrg.boundary_weights(n_faces, n_faces), dtype=torch.float32, device=b["xp"].device)
+    loss = sum((b[k] * w[:, i]).sum() for i, k in enumerate(fields)) + (b["norm"] * w[:, 9:12]).sum()
+    (g,) = torch.autograd.grad(loss, [b.parameters])
+    assert abs(float(loss) - float(want[f"{name}_loss"])) < 1e-4 * max(abs(float(want[f"{name}_loss"])), 1.0)
+    assert helpers.rel_err(g.cpu().numpy(), want[f"{name}_grad"]) < 1e-4
