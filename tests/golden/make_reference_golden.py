@@ -511,6 +511,78 @@ def boundary_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- 2D parametric lens
+
+PARAM2D_POINTS, PARAM2D_RAYS = 9, 120
+
+
+def param2d_inputs():
+    """Plain data of the 2D optimisation scene: a parametric front face (points sliding from x = 0
+    towards x = -0.3), a flat back face, rays from x = -3, per-ray goal -0.4 * start height."""
+    y = np.linspace(-1.0, 1.0, PARAM2D_POINTS)
+    rng = np.random.default_rng(21)
+    y0 = rng.uniform(-0.5, 0.5, PARAM2D_RAYS)
+    ang = rng.uniform(-0.12, 0.12, PARAM2D_RAYS)
+    rays = {"x_start": np.full(PARAM2D_RAYS, -3.0), "y_start": y0,
+            "x_end": -3.0 + np.cos(ang), "y_end": y0 + np.sin(ang),
+            "wavelength": np.asarray([680.0, 575.0, 450.0])[np.arange(PARAM2D_RAYS) % 3], "rank": y0}
+    return {"zero": ((0.0, -1.0), (0.0, 1.0)), "one": ((-0.3, -1.0), (-0.3, 1.0)),
+            "init": 0.8 * (1.0 - y ** 2), "back": np.array([[0.4, 1.0, 0.4, -1.0]]),
+            "target": np.array([[6.0, -6.0, 6.0, 6.0]]), "rays": rays, "goal_scale": -0.4}
+
+
+def param2d_vectors(ref):
+    """`ParametricSegmentBoundary` (tfrt/boundaries.py:528-627) in a 2D system, traced by the
+    reference engine, with the GradientTape gradient of an imaging loss to its parameters: pins the
+    2D backward path (segment geometry, angle-form Snell) end to end."""
+    import tfrt.distributions as rd
+    tf = ref.tf
+    d = param2d_inputs()
+    zero = rd.StaticUniformAperaturePoints(*d["zero"], PARAM2D_POINTS)
+    one = rd.StaticUniformAperaturePoints(*d["one"], PARAM2D_POINTS)
+    # One repair, stated: SegmentBoundaryBase.update_materials passes `self` twice
+    # (tfrt/boundaries.py:485-489) and raises TypeError as soon as the fields exist, i.e. in every
+    # ParametricSegmentBoundary constructor.  It is replaced by a no-op for this fixture; the
+    # materials are set with annotation_helper, as the reference's scripts do.
+    ref.boundaries.SegmentBoundaryBase.update_materials = lambda self: None
+    front = ref.boundaries.ParametricSegmentBoundary(
+        zero, one, initial_parameters=torch.from_numpy(f32_round(d["init"])))
+    back = ref.boundaries.ManualSegmentBoundary()
+    back.feed_segments(f32_round(d["back"]))
+    for b in (front, back):
+        ref.engine.annotation_helper(b, "mat_in", 1, "x_start", dtype=tf.int64)
+        ref.engine.annotation_helper(b, "mat_out", 0, "x_start", dtype=tf.int64)
+    target = ref.boundaries.ManualSegmentBoundary()
+    target.feed_segments(f32_round(d["target"]))
+    src = ref.sources.ManualSource(2)
+    for k, v in d["rays"].items():
+        src[k] = torch.from_numpy(np.ascontiguousarray(f32_round(v)))
+    src["slot"] = torch.arange(PARAM2D_RAYS, dtype=torch.float64)
+    system = ref.engine.OpticalSystem2D(**EPS)
+    system.optical_segments = [front, back]
+    system.target_segments = [target]
+    system.sources = [src]
+    system.materials = [{"n": ref.materials.vacuum}, {"n": ref.materials.acrylic}]
+    system.update()
+    eng = ref.engine.OpticalEngine(2, [ref.operation.StandardReaction()], compile_dead_rays=True,
+                                   simple_ray_inheritance={"wavelength", "slot", "rank"})
+    eng.optical_system = system
+    eng.validate_system()
+    with tf.GradientTape() as tape:
+        system.update()
+        eng.clear_ray_history()
+        eng.ray_trace(3)
+        fin = eng.finished_rays
+        error = tf.math.squared_difference(fin["y_end"], fin["rank"] * d["goal_scale"])
+        grad = tape.gradient(error, front.parameters)
+    out = {"grad": grad.numpy().copy(), "loss": np.array(float(error.sum().detach())),
+           "parameters": front.parameters.numpy().copy()}
+    for k in ("x_start", "y_start", "x_end", "y_end"):
+        out[f"front_{k}"] = front[k].numpy().copy()
+    _record_sets(out, eng, RAYS2)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -521,6 +593,10 @@ def main():
     path = os.path.join(HERE, "ref_sources.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = param2d_vectors(ref)
+    path = os.path.join(HERE, "ref_param2d.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, loss {data['loss']}, |grad| max {np.abs(data['grad']).max()}, finished {data['finished_slot'].shape}")
     data = boundary_vectors(ref)
     path = os.path.join(HERE, "ref_boundaries.npz")
     np.savez_compressed(path, **data)

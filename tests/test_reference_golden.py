@@ -448,3 +448,49 @@ def test_parametric_boundary_variants_match_reference(name):
     (g,) = torch.autograd.grad(loss, [b.parameters])
     assert abs(float(loss) - float(want[f"{name}_loss"])) < 1e-4 * max(abs(float(want[f"{name}_loss"])), 1.0)
     assert helpers.rel_err(g.cpu().numpy(), want[f"{name}_grad"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------ 2D parametric lens
+
+@pytest.mark.gpu
+def test_2d_parametric_lens_gradient_matches_reference():
+    """`ParametricSegmentBoundary` in a 2D system: trace + imaging loss + gradient to the boundary
+    parameters through the fused 2D kernels, against the reference engine's GradientTape."""
+    from tensorflowraytrace_b200 import boundaries as B, distributions as D, engine as eng_mod, \
+        materials, operation, sources
+    want = load("ref_param2d")
+    d = mrg.param2d_inputs()
+    zero = D.StaticUniformAperaturePoints(*d["zero"], mrg.PARAM2D_POINTS)
+    one = D.StaticUniformAperaturePoints(*d["one"], mrg.PARAM2D_POINTS)
+    front = B.ParametricSegmentBoundary(zero, one, initial_parameters=d["init"])
+    back = B.ManualSegmentBoundary()
+    back.feed_segments(d["back"])
+    for b in (front, back):
+        eng_mod.annotation_helper(b, "mat_in", 1, "x_start", dtype=torch.int64)
+        eng_mod.annotation_helper(b, "mat_out", 0, "x_start", dtype=torch.int64)
+    target = B.ManualSegmentBoundary()
+    target.feed_segments(d["target"])
+    src = sources.ManualSource(2)
+    src.feed(d["rays"])
+    system = eng_mod.OpticalSystem2D(**helpers.EPS)
+    system.optical_segments = [front, back]
+    system.target_segments = [target]
+    system.sources = [src]
+    system.materials = [{"n": materials.vacuum}, {"n": materials.acrylic}]
+    system.update()
+    e = eng_mod.OpticalEngine(2, [operation.StandardReaction()], compile_dead_rays=True,
+                              simple_ray_inheritance={"wavelength", "rank"})
+    e.optical_system = system
+    e.validate_system()
+    for k in ("x_start", "y_start", "x_end", "y_end"):
+        assert np.abs(front[k].detach().cpu().numpy() - want[f"front_{k}"]).max() < 1e-6, k
+    e.ray_trace(3)
+    fin = e.finished_rays
+    slot = e.last_history_slots["finished"].cpu().numpy().astype(np.int64)
+    assert np.array_equal(slot, want["finished_slot"])
+    for f in helpers.RAY_FIELDS_2D:
+        assert helpers.rel_err(fin[f].detach().cpu().numpy(), want[f"finished_{f}"]) < 1e-5, f
+    err = (fin["y_end"] - fin["rank"] * d["goal_scale"]) ** 2
+    assert abs(float(err.sum()) - float(want["loss"])) < 1e-4 * float(want["loss"])
+    (g,) = torch.autograd.grad(err.sum(), [front.parameters])
+    assert helpers.rel_err(g.cpu().numpy(), want["grad"]) < 1e-4
