@@ -797,11 +797,12 @@ class ParametricCylindricalGuide(TriangleBoundaryBase):
         self._vertices = self._zero_points
         self._faces = torch.from_numpy(faces).to(dtype=torch.int32, device=self._zero_points.device)
         self._n_side = theta_res * z_res
-        self._n_caps = int(bool(start_cap)) + int(bool(end_cap))
+        # cap vertices first / last, as in the reference's mesh (tfrt/mesh_tools.py:905-945)
+        self._cap_pad = (int(bool(start_cap)), int(bool(end_cap)))
         self._theta_res, self._z_res = theta_res, z_res
         self._guide_map, self._accumulator = mt.mesh_parametrization_tools(
             self._mesh, mt.get_closest_point(self._mesh, start),
-            active_vertices=range(self._n_side))
+            active_vertices=range(self._cap_pad[0], self._cap_pad[0] + self._n_side))
         self._vertex_update_map = None
         self._update_map_dev = None
         self.use_vertex_update_map = use_vertex_update_map
@@ -840,7 +841,7 @@ class ParametricCylindricalGuide(TriangleBoundaryBase):
         p = self.parameters
         if self._rotationally_symmetric:
             p = p.repeat_interleave(self._theta_res)
-        p = torch.nn.functional.pad(p, (0, self._n_caps))       # cap vertices stay on the axis
+        p = torch.nn.functional.pad(p, self._cap_pad)            # cap vertices stay on the axis
         self._vertices = self._zero_points + p.reshape(-1, 1) * self._vectors
         if self.auto_update_mesh:
             self.update_mesh_from_vertices()

@@ -14,33 +14,45 @@ import numpy as np
 
 
 def hexagonal_mesh(radius=1.0, step_count=10):
-    """Regular hexagon of equilateral triangles in the z=0 plane, normals +z.
-
-    Lattice points p = i*a1 + j*a2 (axial coordinates, |i|,|j|,|i+j| <= S); every unit lattice
-    cell contributes an "up" and a "down" triangle when all corners lie in the hexagon.
-    """
+    """Regular hexagon of equilateral triangles in the z = 0 plane (corner distance `radius`,
+    `step_count` rings: 1 + 3 S (S + 1) vertices, 6 S^2 faces), with the reference's exact vertex and
+    face order (tfrt/mesh_tools.py:713-795): vertex 0 is the centre, ring r holds 6 r vertices
+    starting at the corner on +x and running counter-clockwise; the faces of a ring are woven
+    edge by edge, alternating between a triangle with two outer vertices and one with two inner
+    ones.  Returns (points (V, 3), faces (F, 3) int64)."""
     S = int(step_count)
-    h = radius / S
-    ii, jj = np.meshgrid(np.arange(-S, S + 1), np.arange(-S, S + 1), indexing="ij")
-    inside = (np.abs(ii) <= S) & (np.abs(jj) <= S) & (np.abs(ii + jj) <= S)
-    index = -np.ones(inside.shape, dtype=np.int64)
-    index[inside] = np.arange(inside.sum())
-    pi_, pj_ = ii[inside].astype(np.float64), jj[inside].astype(np.float64)
-    points = np.stack([h * (pi_ + 0.5 * pj_), h * (np.sqrt(3.0) / 2.0) * pj_,
-                       np.zeros_like(pi_)], axis=1)
-
-    def idx(di, dj):
-        out = -np.ones(inside.shape, dtype=np.int64)
-        src = index[max(di, 0):index.shape[0] + min(di, 0), max(dj, 0):index.shape[1] + min(dj, 0)]
-        out[max(-di, 0):index.shape[0] + min(-di, 0), max(-dj, 0):index.shape[1] + min(-dj, 0)] = src
-        return out
-
-    a, b, c, d = index, idx(1, 0), idx(0, 1), idx(1, 1)
-    up = np.stack([a, b, c], axis=-1).reshape(-1, 3)       # (i,j) (i+1,j) (i,j+1): CCW
-    down = np.stack([b, d, c], axis=-1).reshape(-1, 3)     # (i+1,j) (i+1,j+1) (i,j+1): CCW
-    faces = np.concatenate([up, down], axis=0)
-    faces = faces[(faces >= 0).all(axis=1)]
-    return points, faces.astype(np.int64)
+    radii = np.linspace(0.0, radius, S + 1)
+    corner = np.stack([np.cos(np.pi / 3.0 * np.arange(7)), np.sin(np.pi / 3.0 * np.arange(7)),
+                       np.zeros(7)], axis=1)
+    points = [np.zeros((1, 3))]
+    faces = []
+    inner_base, inner_count = 0, 1          # the previous ring (the centre counts as a ring of one)
+    outer_base = 1
+    for r in range(1, S + 1):
+        # ring vertices: r per hexagon edge, the edge's end corner belongs to the next edge
+        edges = [np.linspace(radii[r] * corner[e], radii[r] * corner[e + 1], r + 1)[:-1]
+                 for e in range(6)]
+        points.append(np.concatenate(edges, axis=0))
+        outer_count = 6 * r
+        po = pi = 0                         # positions on the outer / inner ring (cyclic)
+        first = outer_base + po; po += 1
+        second = inner_base + pi % inner_count; pi += 1
+        kept = second
+        for _ in range(6):
+            take_outer = True
+            for _ in range(2 * r - 1):
+                if take_outer:
+                    third = outer_base + po % outer_count; po += 1
+                    faces.append((third, second, first))
+                else:
+                    third = inner_base + pi % inner_count; pi += 1
+                    faces.append((first, second, third))
+                first, kept, second = second, second, third
+                take_outer = not take_outer
+            first, second = third, kept
+        inner_base, inner_count = outer_base, outer_count
+        outer_base += outer_count
+    return np.concatenate(points, axis=0), np.array(faces, dtype=np.int64).reshape(-1, 3)
 
 
 def circular_cap_sag(points, curvature_radius):
@@ -49,55 +61,53 @@ def circular_cap_sag(points, curvature_radius):
     return curvature_radius - np.sqrt(np.maximum(curvature_radius ** 2 - r2, 0.0))
 
 
-def cylindrical_mesh(start, end, radius=1.0, theta_res=6, z_res=8, start_cap=True, end_cap=True):
-    """Closed (optionally capped) cylinder between two axis points, normals pointing outward."""
+def cylindrical_mesh(start, end, radius=1.0, theta_res=6, z_res=8, start_cap=True, end_cap=True,
+                     use_twist=False, epsilion=1e-6):
+    """Cylinder between two axis points with optional caps, with the reference's exact vertex and
+    face order (tfrt/mesh_tools.py:800-952): vertices = [start point if start_cap] + ring 0 ..
+    ring z_res-1 + [end point if end_cap]; faces = start-cap fan, then per ring and per theta the
+    two triangles of the quad, then the end-cap fan; windings as the reference writes them (the
+    normals (p2-p1) x (p3-p2) point outward)."""
     start = np.asarray(start, dtype=np.float64).reshape(3)
     end = np.asarray(end, dtype=np.float64).reshape(3)
     axis = end - start
     u = np.cross(axis, (1.0, 0.0, 0.0))
-    if np.linalg.norm(u) < 1e-6:
+    if np.linalg.norm(u) < epsilion:
         u = np.cross(axis, (0.0, 1.0, 0.0))
-    if np.linalg.norm(u) < 1e-6:
-        raise ValueError("cylindrical_mesh: could not find vectors perpendicular to axis.")
+    if np.linalg.norm(u) < epsilion:
+        raise ValueError("cylindrical_mesh: could not find vectors perpendicular to axis.  Try "
+                         "decreasing epsilion?")
     u = u * radius / np.linalg.norm(u)
     v = np.cross(axis, u)
     v = v * radius / np.linalg.norm(v)
 
-    theta = np.linspace(0.0, 2.0 * np.pi, theta_res + 1)[:-1]
-    z = np.linspace(0.0, 1.0, z_res)
-    ring = (np.cos(theta)[:, None] * u[None, :] + np.sin(theta)[:, None] * v[None, :])
-    side = start[None, None, :] + z[:, None, None] * axis[None, None, :] + ring[None, :, :]
-    points = [side.reshape(-1, 3)]
-    n_side = z_res * theta_res
+    theta, z = np.meshgrid(np.linspace(0.0, 2.0 * np.pi, theta_res + 1)[:-1],
+                           np.linspace(0.0, 1.0, z_res))
+    if use_twist:                       # half a triangle of twist per layer
+        theta = theta + (np.pi / theta_res * np.arange(z_res)).reshape(-1, 1)
+    side = (start + z[..., None] * axis + np.cos(theta)[..., None] * u
+            + np.sin(theta)[..., None] * v)                                  # (z_res, theta_res, 3)
+
+    off = 1 if start_cap else 0
+    points = ([start[None, :]] if start_cap else []) + [side.reshape(-1, 3)] + \
+             ([end[None, :]] if end_cap else [])
+    points = np.concatenate(points, axis=0)
 
     t = np.arange(theta_res)
     tn = (t + 1) % theta_res
     faces = []
-    for k in range(1, z_res):
-        lo, hi = (k - 1) * theta_res, k * theta_res
-        faces.append(np.stack([lo + tn, hi + t, lo + t], axis=1))
-        faces.append(np.stack([hi + t, lo + tn, hi + tn], axis=1))
-    next_vertex = n_side
     if start_cap:
-        points.append(start[None, :])
-        faces.append(np.stack([t, np.full_like(t, next_vertex), tn], axis=1))
-        next_vertex += 1
+        faces.append(np.stack([t + 1, np.zeros_like(t), tn + 1], axis=1))
+    for k in range(1, z_res):
+        lo, hi = (k - 1) * theta_res + off, k * theta_res + off
+        quad = np.stack([np.stack([lo + tn, hi + t, lo + t], axis=1),
+                         np.stack([hi + t, lo + tn, hi + tn], axis=1)], axis=1)   # (theta, 2, 3)
+        faces.append(quad.reshape(-1, 3))
     if end_cap:
-        points.append(end[None, :])
-        top = (z_res - 1) * theta_res
-        faces.append(np.stack([top + tn, np.full_like(t, next_vertex), top + t], axis=1))
-        next_vertex += 1
-    points = np.concatenate(points, axis=0)
+        last = points.shape[0] - 1
+        top = (z_res - 1) * theta_res + off
+        faces.append(np.stack([tn + top, np.full_like(t, last), t + top], axis=1))
     faces = np.concatenate(faces, axis=0).astype(np.int64)
-
-    # orient every face outward (away from the axis mid-point) so "outside" is unambiguous
-    p0, p1, p2 = points[faces[:, 0]], points[faces[:, 1]], points[faces[:, 2]]
-    nrm = np.cross(p1 - p0, p2 - p1)
-    centroid = (p0 + p1 + p2) / 3.0
-    rel = centroid - (start + 0.5 * axis)[None, :]
-    # remove the axial component for side faces so the test is radial there
-    flip = np.einsum("ij,ij->i", nrm, rel) < 0
-    faces[flip] = faces[flip][:, ::-1]
     return points, faces
 
 

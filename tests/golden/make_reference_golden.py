@@ -583,6 +583,32 @@ def param2d_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- mesh generators
+
+def mesh_cases():
+    return {
+        "hex_1": ("hexagonal_mesh", dict(radius=1.0, step_count=1)),
+        "hex_2": ("hexagonal_mesh", dict(radius=0.37, step_count=2)),
+        "hex_7": ("hexagonal_mesh", dict(radius=1.0, step_count=7)),
+        "cyl_capped": ("cylindrical_mesh", dict(start=(0, 0, 0), end=(4, 0, 0), radius=0.5, theta_res=8, z_res=5)),
+        "cyl_open": ("cylindrical_mesh", dict(start=(1, 2, 3), end=(1.5, -2, 4), radius=0.3, theta_res=10,
+                                              z_res=7, start_cap=False, end_cap=False)),
+        "cyl_one_cap_twist": ("cylindrical_mesh", dict(start=(0, 0, 0), end=(0, 0, 2), radius=1.0, theta_res=6,
+                                                       z_res=4, start_cap=True, end_cap=False, use_twist=True)),
+    }
+
+
+def mesh_vectors(ref):
+    """Vertex and face arrays of the reference's own mesh generators (tfrt/mesh_tools.py:713-952)."""
+    import tfrt.mesh_tools as rmt
+    out = {}
+    for name, (fn, kw) in mesh_cases().items():
+        pd = getattr(rmt, fn)(**kw)
+        out[f"{name}_points"] = np.asarray(pd.points, dtype=np.float64)
+        out[f"{name}_faces"] = np.asarray(pd.faces).reshape(-1, 4)[:, 1:].astype(np.int64)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -591,6 +617,10 @@ def main():
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
     data = source_vectors(ref)
     path = os.path.join(HERE, "ref_sources.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    data = mesh_vectors(ref)
+    path = os.path.join(HERE, "ref_meshes.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
     data = param2d_vectors(ref)

@@ -494,3 +494,18 @@ def test_2d_parametric_lens_gradient_matches_reference():
     assert abs(float(err.sum()) - float(want["loss"])) < 1e-4 * float(want["loss"])
     (g,) = torch.autograd.grad(err.sum(), [front.parameters])
     assert helpers.rel_err(g.cpu().numpy(), want["grad"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------ mesh generators
+
+@pytest.mark.parametrize("name", sorted(mrg.mesh_cases()))
+def test_mesh_generators_match_reference_functions(name):
+    """`mesh_tools.hexagonal_mesh` / `cylindrical_mesh`: same vertices (bit-exact) in the same order
+    and the same faces in the same order and winding as the reference's generators, so vertex
+    indices (parameters, accumulators, constraints) and triangle indices mean the same thing."""
+    from tensorflowraytrace_b200 import mesh_tools
+    want = load("ref_meshes")
+    fn, kw = mrg.mesh_cases()[name]
+    pts, faces = getattr(mesh_tools, fn)(**kw)
+    assert np.array_equal(faces, want[f"{name}_faces"])
+    assert np.abs(pts - want[f"{name}_points"]).max() < 1e-15
