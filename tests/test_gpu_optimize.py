@@ -87,7 +87,7 @@ def test_cylindrical_guide_parameters_and_symmetry():
                                                 rotationally_symmetric=True, **kw)
     assert full.parameters.shape == (108,) and sym.parameters.shape == (9,)
     assert float(full.parameters.min()) == 0.0
-    assert torch.equal(full.vertices[-2:], full._zero_points[-2:])       # caps on the axis
+    assert torch.equal(full.vertices[[0, -1]], full._zero_points[[0, -1]])   # caps (first, last vertex) stay on the axis
     assert torch.allclose(full.vertices, sym.vertices)
     grads = []
     for guide in (full, sym):
