@@ -18,11 +18,12 @@ Dense sources take the cross product of their domains in the reference's order: 
 index arrays are `tf.meshgrid(*ranges)` (default 'xy' indexing) flattened row-major
 (tfrt/sources.py:283-292), i.e. for domains (d0, d1, d2, ...) the flattened order has d1
 slowest, then d0, then d2 ... fastest.  Undense sources pair their variables element-wise.
-`PrecompiledSource` (pickled ray sets, :1099-1358) is out of scope.
+  PrecompiledSource  ray sets stored in / loaded from the reference's pickle format   :1099-1358
 """
 
 import itertools
 import math
+import pickle
 
 import numpy as np
 import torch
@@ -450,3 +451,156 @@ class AperatureSource(SourceBase):
     @property
     def end_point_distribution(self):
         return self._end_point_distribution
+
+
+# =============================================================================================
+
+class PrecompiledSource(RecursivelyUpdatable):
+    """A ray set that was generated once (a random source behind a static optic, a costly extra
+    field, the output of a previous trace) and is re-used, optionally drawing a random subset and
+    jittering the end points at every update (tfrt/sources.py:1099-1358).
+
+    arg : str  -> file written by `save` here or by the reference's `PrecompiledSource.save`
+                  (pickle of {"dimension", "standard_domains", "fields": {name: ndarray}});
+          int  -> dimension of a new, empty source (fill it with `from_samples`);
+          else -> an updated source object whose fields are copied.
+    The stored rays live on the field device; `update()` samples `sample_count` of them with
+    replacement (`do_downsample`) and adds N(0, sigma) jitter per coordinate when
+    `start_perturbation` / `end_perturbation` are given, all on the device."""
+
+    def __init__(self, arg, sample_count=100, do_downsample=True, start_perturbation=None,
+                 end_perturbation=None, **kwargs):
+        if isinstance(arg, str):
+            with open(arg, "rb") as f:
+                data = pickle.load(f)
+            self._dimension = int(data["dimension"])
+            self._standard_domains = set(data["standard_domains"])
+            full = data["fields"]
+        elif isinstance(arg, (int, np.integer)):
+            self._dimension, self._standard_domains, full = int(arg), set(), {}
+        else:
+            self._dimension = int(arg.dimension)
+            self._standard_domains = set(getattr(arg, "_standard_domains", ()))
+            full = dict(arg.items())
+        if self._dimension not in (2, 3):
+            raise ValueError("PrecompiledSource: dimension must be 2 or 3")
+        self._full_fields = {k: as_field(v) for k, v in full.items()}
+        self._fields = {}
+        self.start_perturbation = start_perturbation
+        self.end_perturbation = end_perturbation
+        self.sample_count = sample_count
+        self.do_downsample = do_downsample
+        super().__init__(**kwargs)
+
+    # ---- storage
+    def save(self, filename):
+        """Write the CURRENT (possibly down-sampled) fields in the reference's pickle layout."""
+        out = {"dimension": self._dimension, "standard_domains": set(self._standard_domains),
+               "fields": {k: v.detach().cpu().numpy() for k, v in self._fields.items()}}
+        with open(filename, "wb") as f:
+            pickle.dump(out, f, pickle.HIGHEST_PROTOCOL)
+
+    def from_samples(self, samples):
+        """Fill the store by concatenating the fields of several field dicts (e.g. the
+        `finished_rays` of previous traces)."""
+        lists = {}
+        for sample in samples:
+            for field, data in sample.items():
+                lists.setdefault(field, []).append(as_field(data))
+        self._full_fields = {k: torch.cat(v, dim=0) for k, v in lists.items()}
+        self.update()
+
+    def clear(self):
+        self._full_fields = {}
+        self._fields = self._full_fields
+
+    # ---- update
+    def _generate_update_handles(self):
+        return []
+
+    def _update(self):
+        n = self.sampling_domain_size
+        if self.do_downsample and n > 0:
+            dev = self._full_fields["x_start"].device
+            idx = torch.randint(0, n, (self._sample_count,), device=dev)
+            self._fields = {k: v.index_select(0, idx) for k, v in self._full_fields.items()}
+        else:
+            self._fields = dict(self._full_fields)
+        if not self._fields:
+            return
+        dims = ("x", "y") if self._dimension == 2 else ("x", "y", "z")
+        for which, sigma in (("start", self._start_perturbation), ("end", self._end_perturbation)):
+            if sigma is None:
+                continue
+            for d, s in zip(dims, sigma.tolist()):
+                key = f"{d}_{which}"
+                self._fields[key] = self._fields[key] + float(s) * torch.randn_like(self._fields[key])
+
+    # ---- field access (the data contract of a source)
+    def __getitem__(self, key):
+        return self._fields[key]
+
+    def __setitem__(self, key, item):
+        self._fields[key] = as_field(item)
+
+    def __bool__(self):
+        return bool(self._fields)
+
+    @property
+    def keys(self):
+        return self._fields.keys
+
+    @property
+    def items(self):
+        return self._fields.items
+
+    @property
+    def dimension(self):
+        return self._dimension
+
+    @property
+    def standard_domains(self):
+        return self._standard_domains
+
+    @property
+    def sampling_domain_size(self):
+        f = self._full_fields.get("x_start")
+        return 0 if f is None else int(f.shape[0])
+
+    @property
+    def sample_count(self):
+        return self._sample_count
+
+    @sample_count.setter
+    def sample_count(self, val):
+        if int(val) != val:
+            raise TypeError("PrecompiledSource: sample_count must be of integer type.")
+        if val <= 0:
+            raise ValueError("PrecompiledSource: sample_count must be > 0.")
+        self._sample_count = int(val)
+
+    def _perturbation(self, val, which):
+        if val is None:
+            return None
+        try:
+            return torch.broadcast_to(torch.as_tensor(val, dtype=torch.float32),
+                                      (self._dimension,)).clone()
+        except RuntimeError as e:
+            raise ValueError(f"PrecompiledSource: {which}_perturbation must be None, scalar, or "
+                             "must have one entry per dimension.") from e
+
+    @property
+    def start_perturbation(self):
+        return self._start_perturbation
+
+    @start_perturbation.setter
+    def start_perturbation(self, val):
+        self._start_perturbation = self._perturbation(val, "start")
+
+    @property
+    def end_perturbation(self):
+        return self._end_perturbation
+
+    @end_perturbation.setter
+    def end_perturbation(self, val):
+        self._end_perturbation = self._perturbation(val, "end")

@@ -609,6 +609,21 @@ def mesh_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- PrecompiledSource file
+
+def precompiled_file(ref):
+    """A file written by the reference's own `PrecompiledSource.save` (tfrt/sources.py:1206-1215)
+    from a 3D `PointSource`: the data format either side of the path (pickle of dimension,
+    standard_domains, fields)."""
+    import tfrt.distributions as rd
+    src = ref.sources.PointSource(3, (-1.0, 0.0, 0.0), (1.0, 0.0, 0.0),
+                                  rd.StaticUniformSphere(math.pi / 8, 12), [575.0, 450.0])
+    pre = ref.sources.PrecompiledSource(src, do_downsample=False)
+    path = os.path.join(HERE, "ref_precompiled_source.pkl")
+    pre.save(path)
+    return path
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -619,6 +634,7 @@ def main():
     path = os.path.join(HERE, "ref_sources.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
+    print(precompiled_file(ref), os.path.getsize(os.path.join(HERE, "ref_precompiled_source.pkl")), "bytes")
     data = mesh_vectors(ref)
     path = os.path.join(HERE, "ref_meshes.npz")
     np.savez_compressed(path, **data)

@@ -179,3 +179,27 @@ def test_search_is_watertight_at_edges_and_vertices(step_count):
         corners = V[faces[gather_trig]]                                   # (n, 3, 3)
         lo, hi = corners.min(axis=1) - 2e-5, corners.max(axis=1) + 2e-5
         assert ((A >= lo) & (A <= hi)).all(), perm
+
+
+def test_precompiled_source_feeds_the_trace():
+    """A PrecompiledSource built from a trace's finished rays (`from_samples`, the reference's
+    "static optic traced once" use, tfrt/sources.py:1099-1120) drives a second system."""
+    from tensorflowraytrace_b200 import sources
+    scene = scenes.config2(ray_count=2000, step_count=4)
+    first, _, _ = scenes.build_engine(scene, eps=helpers.EPS)
+    first.ray_trace(1)                                   # stop after the first surface
+    act = first.active_rays
+    assert _count(act) > 1500
+    pre = sources.PrecompiledSource(3, do_downsample=False)
+    pre.from_samples([{k: act[k].detach() for k in act.keys()}])
+    second, _, _ = scenes.build_engine(scene, eps=helpers.EPS)
+    second.optical_system.sources = [pre]
+    second.optical_system.update()
+    second.ray_trace(3)
+    # the rays continue from where the first trace left them: same finished set as a full trace
+    full, _, _ = scenes.build_engine(scene, eps=helpers.EPS)
+    full.ray_trace(3)
+    a, b = second.finished_rays, full.finished_rays
+    assert _count(a) == _count(b) > 1500
+    for f in RAYS:
+        assert helpers.rel_err(a[f].detach().cpu().numpy(), b[f].detach().cpu().numpy()) < 1e-5, f

@@ -176,3 +176,67 @@ def test_parametric_segment_boundaries_and_constraints():
     assert abs(float((p0 - p1).max().detach()) + 0.3) < 1e-6
     with pytest.raises(ValueError):
         B.ParametricMultiSegmentBoundary(zero, one, [B.NoConstraint()], [True, False])
+
+
+# ------------------------------------------------------------------------------------------------
+# PrecompiledSource (tfrt/sources.py:1099-1358)
+
+def test_precompiled_source_reads_the_reference_pickle_format(tmp_path):
+    """tests/golden/ref_precompiled_source.pkl was written by the reference's own
+    PrecompiledSource.save (make_reference_golden.precompiled_file) from a 3D PointSource."""
+    import os
+    import pickle
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "golden", "ref_precompiled_source.pkl")
+    raw = pickle.load(open(path, "rb"))
+    pre = sources.PrecompiledSource(path, do_downsample=False)
+    assert pre.dimension == 3 and pre.standard_domains == raw["standard_domains"]
+    assert pre.sampling_domain_size == 24 and set(pre.keys()) == set(raw["fields"])
+    for k, v in raw["fields"].items():
+        assert np.allclose(npy(pre[k]), v, atol=1e-6), k
+    # the same rays as this package's PointSource with the same arguments
+    src = sources.PointSource(3, (-1.0, 0.0, 0.0), (1.0, 0.0, 0.0), D.StaticUniformSphere(PI / 8, 12),
+                              [575.0, 450.0])
+    for k in raw["fields"]:
+        assert np.allclose(npy(src[k]), raw["fields"][k], atol=2e-6), k
+    # round trip through our save(), in the reference's layout
+    out = str(tmp_path / "again.pkl")
+    pre.save(out)
+    again = pickle.load(open(out, "rb"))
+    assert set(again) == {"dimension", "standard_domains", "fields"} and again["dimension"] == 3
+    assert all(isinstance(v, np.ndarray) for v in again["fields"].values())
+    assert np.allclose(again["fields"]["y_end"], raw["fields"]["y_end"], atol=1e-6)
+
+
+def test_precompiled_source_sampling_perturbation_and_samples():
+    src = sources.PointSource(3, (0.0, 0.0, 0.0), (1.0, 0.0, 0.0), D.StaticUniformSphere(PI / 6, 50),
+                              [500.0])
+    pre = sources.PrecompiledSource(src, sample_count=400)
+    assert pre["x_start"].shape[0] == 400 and pre.sampling_domain_size == 50
+    full = np.stack([npy(src[k]) for k in ("x_end", "y_end", "z_end")], 1)
+    got = np.stack([npy(pre[k]) for k in ("x_end", "y_end", "z_end")], 1)
+    # every drawn ray is one of the stored rays (sampling with replacement keeps rows together)
+    d = np.abs(got[:, None, :] - full[None, :, :]).max(axis=2).min(axis=1)
+    assert d.max() < 1e-6
+    before = got.copy()
+    pre.update()
+    assert not np.array_equal(before, np.stack([npy(pre[k]) for k in ("x_end", "y_end", "z_end")], 1))
+    pre.do_downsample = False
+    pre.end_perturbation = (0.0, 0.1, 0.0)
+    pre.update()
+    assert pre["x_end"].shape[0] == 50
+    assert np.allclose(npy(pre["x_end"]), full[:, 0], atol=1e-6) and np.allclose(npy(pre["z_end"]), full[:, 2], atol=1e-6)
+    dy = npy(pre["y_end"]) - full[:, 1]
+    assert 0.03 < dy.std() < 0.25
+    with pytest.raises(ValueError):
+        pre.start_perturbation = (1.0, 2.0)
+    with pytest.raises(ValueError):
+        pre.sample_count = 0
+    empty = sources.PrecompiledSource(2, do_downsample=False)
+    assert not bool(empty) and empty.sampling_domain_size == 0
+    a = {"x_start": np.zeros(3), "y_start": np.zeros(3), "x_end": np.ones(3), "y_end": np.arange(3.0)}
+    b = {"x_start": np.zeros(2), "y_start": np.ones(2), "x_end": np.ones(2), "y_end": np.arange(2.0)}
+    empty.from_samples([a, b])
+    assert empty["y_end"].shape[0] == 5 and np.allclose(npy(empty["y_start"]), [0, 0, 0, 1, 1])
+    empty.clear()
+    assert empty.sampling_domain_size == 0
