@@ -19,6 +19,7 @@ every process of a multi-GPU job its own stream so that ray shards are independe
 import itertools
 import math
 
+import numpy as np
 import torch
 
 from .boundaries import as_float_field, default_device
@@ -153,9 +154,30 @@ class RandomLambertianAngularDistribution(AngularDistributionBase):
 # 2D base points
 
 class BasePointDistributionBase(_Sampler):
+    """Points, ranks and the post-update hook list of the reference's base point distributions
+    (tfrt/distributions.py:559-626; RecursivelyUpdatable.post_update_handles, tfrt/update.py:52-61):
+    every subclass' update() is followed by the functions in `post_update_handles`."""
+
     points = property(lambda self: self._points)
     ranks = property(lambda self: self._ranks)
     name = property(lambda self: self._name)
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        inner = cls.__dict__.get("update")
+        if inner is not None:
+            def update(self, _inner=inner):
+                _inner(self)
+                for handle in list(self.post_update_handles):
+                    handle()
+            update.__doc__ = inner.__doc__
+            cls.update = update
+
+    @property
+    def post_update_handles(self):
+        if "_post_update_handles" not in self.__dict__:
+            self._post_update_handles = []
+        return self._post_update_handles
 
 
 class ManualBasePointDistribution(BasePointDistributionBase):
@@ -411,3 +433,70 @@ class RandomLambertianSphere(SphereBase):
     def update(self):
         c2 = self._uniform(self.sample_count, math.cos(self.angular_size) ** 2, 1.0)
         self._finish(torch.sqrt(c2), GOLDEN_ANGLE_FACTOR * self._uniform(self.sample_count))
+
+
+# =============================================================================================
+
+class BasePointTransformation:
+    """Scale, then rotate, then translate the points of a base point distribution after each of
+    its updates (tfrt/distributions.py:2014-2120): lets relative base points serve as absolute
+    positions, e.g. for an AperatureSource.  2D points are first lifted into the y-z plane
+    (x = 0).  rotation: a unit quaternion (w, x, y, z); translation / scale: broadcastable to
+    (n, 3).  The transformation is a post-update hook of `base`: it takes effect at the base's
+    next update() and stops when this object is deleted."""
+
+    def __init__(self, base, rotation=None, translation=None, scale=None):
+        self._base = base
+        self.rotation = rotation
+        self.translation = translation
+        self.scale = scale
+        self._base.post_update_handles.append(self._apply_transformation)
+
+    def __del__(self):
+        try:
+            self._base.post_update_handles.remove(self._apply_transformation)
+        except (ValueError, AttributeError):
+            pass
+
+    def _apply_transformation(self):
+        from .sources import rotate_by_quaternion
+        pts = self._base._points
+        if pts.shape[1] == 2:
+            pts = torch.nn.functional.pad(pts, (1, 0))
+        if self._scale is not None:
+            pts = pts * self._scale.to(pts.device)
+        if self._rotation is not None:
+            pts = rotate_by_quaternion(self._rotation.cpu().numpy(), pts)
+        if self._translation is not None:
+            pts = pts + self._translation.to(pts.device)
+        self._base._points = pts
+
+    @property
+    def rotation(self):
+        return self._rotation
+
+    @rotation.setter
+    def rotation(self, val):
+        if val is not None:
+            val = torch.as_tensor(np.asarray(val, dtype=np.float64), dtype=torch.float32)
+            if tuple(val.shape) != (4,):
+                raise ValueError("BasePointTransformation: rotation must be a quaternion.")
+        self._rotation = val
+
+    @property
+    def translation(self):
+        return self._translation
+
+    @translation.setter
+    def translation(self, val):
+        self._translation = None if val is None else torch.as_tensor(
+            np.asarray(val, dtype=np.float64), dtype=torch.float32)
+
+    @property
+    def scale(self):
+        return self._scale
+
+    @scale.setter
+    def scale(self, val):
+        self._scale = None if val is None else torch.as_tensor(
+            np.asarray(val, dtype=np.float64), dtype=torch.float32)

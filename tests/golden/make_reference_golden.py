@@ -246,9 +246,22 @@ def build_case(dist_mod, src_mod, spec):
     return cls(*[arg(a) for a in args], **kwargs)
 
 
+def transformation_case(dist_mod):
+    """A StaticUniformSquare scaled, rotated by 90 degrees about z and translated (reference:
+    BasePointTransformation, tfrt/distributions.py:2014-2120); returns the distribution."""
+    base = dist_mod.StaticUniformSquare(0.5, 3, 0.25, 2)
+    q = (math.cos(math.pi / 4), 0.0, 0.0, math.sin(math.pi / 4))
+    keep = dist_mod.BasePointTransformation(base, rotation=q, translation=(1.0, 2.0, 3.0),
+                                            scale=(1.0, 2.0, 0.5))
+    base.update()
+    base._keep_transformation_alive = keep
+    return base
+
+
 def source_vectors(ref):
     import tfrt.distributions as rd
     out = {}
+    out["transformed_square__points"] = np.asarray(transformation_case(rd).points, dtype=np.float64)
     for name, spec in source_cases().items():
         obj = build_case(rd, ref.sources, spec)
         if name.startswith("dist_"):

@@ -509,3 +509,11 @@ def test_mesh_generators_match_reference_functions(name):
     pts, faces = getattr(mesh_tools, fn)(**kw)
     assert np.array_equal(faces, want[f"{name}_faces"])
     assert np.abs(pts - want[f"{name}_points"]).max() < 1e-15
+
+
+def test_base_point_transformation_matches_reference():
+    from tensorflowraytrace_b200 import distributions as D
+    want = load("ref_sources")["transformed_square__points"]
+    got = mrg.transformation_case(D).points.detach().cpu().numpy().astype(np.float64)
+    assert got.shape == want.shape == (6, 3)
+    assert np.allclose(got, want, atol=2e-6)
