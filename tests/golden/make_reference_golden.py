@@ -637,6 +637,51 @@ def precompiled_file(ref):
     return path
 
 
+# ------------------------------------------------------------------------------- projection result
+
+def projection_scene():
+    """Rays that reach every category in ONE pass: the mirror / stop scene's rays moved behind the
+    lens (x = 1) so that they meet the stop, the mirror, nothing, or -- aimed sideways -- the target."""
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import scenes
+    scene = scenes.mirror_stop_3d(ray_count=240, seed=3)
+    src = scene["sources"]
+    n = src["x_start"].shape[0]
+    shift = 5.0
+    for k in ("x_start", "x_end"):
+        src[k] = src[k] + shift
+    down = np.arange(n) % 4 == 0                       # a quarter of the rays go straight to the target
+    src["x_end"] = np.where(down, src["x_start"], src["x_end"])
+    src["y_end"] = np.where(down, src["y_start"] - 1.0, src["y_end"])
+    src["z_end"] = np.where(down, src["z_start"], src["z_end"])
+    up = np.arange(n) % 5 == 1                         # and a fifth leave upwards: they hit nothing
+    src["x_end"] = np.where(up, src["x_start"], src["x_end"])
+    src["y_end"] = np.where(up, src["y_start"] + 0.5, src["y_end"])
+    return scene
+
+
+def _flatten(prefix, d, out):
+    for k, v in d.items():
+        if isinstance(v, dict):
+            _flatten(f"{prefix}{k}.", v, out)
+        else:
+            out[f"{prefix}{k}"] = np.asarray(v.numpy() if hasattr(v, "numpy") else v)
+
+
+def projection_vectors(ref):
+    """`OpticalEngine.process_projection_3D` (tfrt/engine.py:1988-2191) with
+    compile_technical_intersections, all four compile flags and dead_ray_length: the full nested
+    result dict of one pass (rays by category + gathered optical / stop / target boundary fields)."""
+    scene = projection_scene()
+    eng, system, _ = reference_engine_3d(ref, scene, compile_technical_intersections=True,
+                                         dead_ray_length=5.0)
+    rays = {k: v for k, v in system._amalgamated_sources.items()}
+    result = eng.process_projection(dict(rays))
+    out = {}
+    _flatten("", result, out)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -648,6 +693,10 @@ def main():
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays, {os.path.getsize(path)} bytes")
     print(precompiled_file(ref), os.path.getsize(os.path.join(HERE, "ref_precompiled_source.pkl")), "bytes")
+    data = projection_vectors(ref)
+    path = os.path.join(HERE, "ref_projection.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays:", {k: v.shape for k, v in data.items() if k.endswith("x_start")})
     data = mesh_vectors(ref)
     path = os.path.join(HERE, "ref_meshes.npz")
     np.savez_compressed(path, **data)

@@ -517,3 +517,54 @@ def test_base_point_transformation_matches_reference():
     got = mrg.transformation_case(D).points.detach().cpu().numpy().astype(np.float64)
     assert got.shape == want.shape == (6, 3)
     assert np.allclose(got, want, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------ projection result
+
+def _check_projection(result, want, tol):
+    flat = {}
+
+    def walk(prefix, d):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                walk(f"{prefix}{k}.", v)
+            else:
+                flat[f"{prefix}{k}"] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    walk("", result)
+    missing = set(want) - set(flat)
+    assert not missing, sorted(missing)
+    counts = {c: want[f"rays.{c}.x_start"].shape[0] for c in ("active", "finished", "stopped", "dead")}
+    assert min(counts.values()) > 10, counts                      # every category is populated
+    for key, w in want.items():
+        g = flat[key]
+        assert g.shape == w.shape, (key, g.shape, w.shape)
+        if w.dtype.kind in "iub":
+            assert np.array_equal(g.astype(np.int64), w.astype(np.int64)), key
+        else:
+            assert helpers.rel_err(g, w) < tol, (key, helpers.rel_err(g, w))
+
+
+def test_oracle_projection_result_matches_reference():
+    """One `process_projection_3D` pass with technical intersections, every compile flag and
+    dead-ray lengthening: the whole nested result (tfrt/engine.py:1988-2191) against the reference."""
+    want = load("ref_projection")
+    scene = mrg.projection_scene()
+    eng, _ = helpers.oracle_from_scene(scene, fp32_vertices=False, compile_dead_rays=True,
+                                       compile_stopped_rays=True, compile_technical_intersections=True,
+                                       dead_ray_length=5.0)
+    rays = dict(eng.optical_system._amalgamated_sources)
+    _check_projection(eng.process_projection_3D(rays), want, 1e-10)
+
+
+@pytest.mark.gpu
+def test_cuda_projection_result_matches_reference():
+    from tensorflowraytrace_b200 import scenes
+    want = load("ref_projection")
+    scene = mrg.projection_scene()
+    engine, _, src = scenes.build_engine(scene, eps=helpers.EPS, compile_dead_rays=True,
+                                         compile_stopped_rays=True,
+                                         compile_technical_intersections=True, dead_ray_length=5.0)
+    src["slot"] = torch.arange(scene["sources"]["x_start"].shape[0], dtype=torch.float32)
+    engine.optical_system.update()
+    rays = dict(engine.optical_system._amalgamated_sources)
+    _check_projection(engine.process_projection_3D(rays), want, 1e-5)
