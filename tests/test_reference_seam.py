@@ -91,3 +91,70 @@ def test_reference_engine_with_the_cuda_seam_reproduces_the_reference(name):
         assert abs(float(error.sum().detach()) - float(want["loss"])) < 1e-5 * float(want["loss"])
         for i, g in enumerate(grads):
             assert helpers.rel_err(g.numpy(), want[f"grad_{i}"]) < 1e-4, i
+
+
+def _cuda_intersect_2d():
+    """Replacement of the reference's `OpticalSystem2D.intersect(self, rays)` (seam b2,
+    tfrt/engine.py:523-616): the merged segment / arc fields of the REFERENCE system go to the GPU,
+    this package's 2D seam finds and evaluates the hits, the result dicts come back as float64."""
+    from types import SimpleNamespace
+    from tensorflowraytrace_b200 import engine as ours, kernels
+    dev = torch.device("cuda:0")
+    calls = {"n": 0}
+
+    def to_dev(d):
+        return {k: (v.to(device=dev, dtype=torch.float32) if v.is_floating_point() else v.to(dev))
+                for k, v in d.items()} if bool(d) else {}
+
+    def back(d):
+        out = {}
+        for k, v in d.items():
+            v = v.cpu()
+            out[k] = v.to(torch.float64) if v.is_floating_point() else \
+                (v.bool() if k == "valid" else v.long())
+        return out
+
+    def intersect(self, rays):
+        calls["n"] += 1
+        seg, arc = to_dev(self._merged_segments), to_dev(self._merged_arcs)
+
+        def merged_device_arrays():
+            s = torch.stack([seg[k] for k in kernels.SEG_FIELDS]).contiguous() if seg else None
+            a = torch.stack([arc[k] for k in kernels.ARC_FIELDS]).contiguous() if arc else None
+            return s, a
+
+        adapter = SimpleNamespace(
+            _merged_segments=seg, _merged_arcs=arc, merged_device_arrays=merged_device_arrays,
+            intersect_epsilion=float(self.intersect_epsilion), size_epsilion=float(self.size_epsilion),
+            ray_start_epsilion=float(self.ray_start_epsilion))
+        drays = {k: rays[k].to(device=dev, dtype=torch.float32) for k in kernels.RAY_FIELDS_2D}
+        s_res, a_res = ours.OpticalSystem2D.intersect(adapter, drays)
+        return back(s_res), back(a_res)
+
+    return intersect, calls
+
+
+@pytest.mark.parametrize("name", ["ref_wedge2d", "ref_arclens2d", "ref_segments2d"])
+def test_reference_2d_engine_with_the_cuda_seam_reproduces_the_reference(name):
+    rr, ref = _reference()
+    want = dict(np.load(os.path.join(HERE, "golden", f"{name}.npz")))
+    scene = mrg.golden_scenes()[name]
+    seam, calls = _cuda_intersect_2d()
+    original = ref.engine.OpticalSystem2D.intersect
+    ref.engine.OpticalSystem2D.intersect = seam
+    try:
+        eng, system = rr.reference_engine_2d(ref, scene)
+        eng.ray_trace(scene["max_iterations"])
+    finally:
+        ref.engine.OpticalSystem2D.intersect = original
+    assert calls["n"] >= 2
+    checked = 0
+    for set_name in ("active", "finished", "stopped", "dead"):
+        if f"{set_name}_slot" not in want:
+            continue
+        s = getattr(eng, set_name + "_rays")
+        assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
+        for f in helpers.RAY_FIELDS_2D:
+            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+        checked += 1
+    assert checked >= 2
