@@ -682,6 +682,37 @@ def projection_vectors(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- 2D projection result
+
+def projection_scene_2d():
+    """Rays placed behind the prism of `segments_2d` so that ONE pass meets every category: the
+    target, the stop, optical faces (prism, mirror) and nothing."""
+    sys.path.insert(0, ROOT)
+    from tensorflowraytrace_b200 import scenes
+    scene = scenes.segments_2d()
+    n = 200
+    rng = np.random.default_rng(8)
+    y0 = rng.uniform(-0.5, 2.5, n)
+    ang = rng.uniform(-0.6, 0.9, n)
+    ang = np.where(np.arange(n) % 4 == 1, math.pi + rng.uniform(-0.5, 0.5, n), ang)   # backwards: prism
+    ang = np.where(np.arange(n) % 5 == 2, math.pi / 2 + rng.uniform(-0.1, 0.1, n), ang)  # upwards: nothing
+    wl = np.asarray(scenes.RAINBOW_6)[np.arange(n) % 6]
+    scene["sources"] = scenes.rays_2d(np.stack([np.full(n, 3.6), y0], 1), ang, wl)
+    return scene
+
+
+def projection_vectors_2d(ref):
+    """`OpticalEngine.process_projection_2D` (tfrt/engine.py:1544-1986), segments only, with
+    compile_technical_intersections, all compile flags and dead_ray_length."""
+    scene = projection_scene_2d()
+    eng, system = reference_engine_2d(ref, scene, compile_technical_intersections=True,
+                                      dead_ray_length=3.0)
+    result = eng.process_projection(dict(system._amalgamated_sources))
+    out = {}
+    _flatten("", result, out)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -695,6 +726,10 @@ def main():
     print(precompiled_file(ref), os.path.getsize(os.path.join(HERE, "ref_precompiled_source.pkl")), "bytes")
     data = projection_vectors(ref)
     path = os.path.join(HERE, "ref_projection.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays:", {k: v.shape for k, v in data.items() if k.endswith("x_start")})
+    data = projection_vectors_2d(ref)
+    path = os.path.join(HERE, "ref_projection2d.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays:", {k: v.shape for k, v in data.items() if k.endswith("x_start")})
     data = mesh_vectors(ref)

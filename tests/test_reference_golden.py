@@ -568,3 +568,19 @@ def test_cuda_projection_result_matches_reference():
     engine.optical_system.update()
     rays = dict(engine.optical_system._amalgamated_sources)
     _check_projection(engine.process_projection_3D(rays), want, 1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_projection_result_2d_matches_reference():
+    """One `process_projection_2D` pass (segments only) with technical intersections, every compile
+    flag and dead-ray lengthening against the reference's result dict (tfrt/engine.py:1544-1986)."""
+    from tensorflowraytrace_b200 import scenes
+    want = load("ref_projection2d")
+    scene = mrg.projection_scene_2d()
+    engine, _, src = scenes.build_engine_2d(scene, eps=helpers.EPS, compile_dead_rays=True,
+                                            compile_stopped_rays=True,
+                                            compile_technical_intersections=True, dead_ray_length=3.0)
+    src["slot"] = torch.arange(scene["sources"]["x_start"].shape[0], dtype=torch.float32)
+    engine.optical_system.update()
+    rays = dict(engine.optical_system._amalgamated_sources)
+    _check_projection(engine.process_projection_2D(rays), want, 1e-5)
