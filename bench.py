@@ -405,8 +405,11 @@ def run_ours(args):
     tests_total = parallel.sum_over_ranks(tests_local)
     rays_total = parallel.sum_over_ranks(n_local)
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    # clocks / throttle reasons are sampled on rank 0's GPU only: one nvidia-smi poller per rank
+    # (NVML takes driver locks) can cost another rank a timed step on an 8-GPU box
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     kernels.profile_enable(True)
     kernels.profile_read()
     kernels.launch_count(reset=True)
@@ -414,7 +417,7 @@ def run_ours(args):
     launches = kernels.launch_count(reset=True)
     k_ms, k_n = kernels.profile_read()
     kernels.profile_enable(False)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else {}
 
     # forward-only (update + trace), same inputs
     def step_forward():
