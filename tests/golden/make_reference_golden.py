@@ -713,6 +713,26 @@ def projection_vectors_2d(ref):
     return out
 
 
+# ------------------------------------------------------------------------------- GhostThrough (hook path)
+
+def ghost_vectors(ref):
+    """The operation-hook path (tfrt/engine.py:2193-2302 `single_pass`, tfrt/operation.py:311-333):
+    the segments-only 2D scene traced with `[GhostThrough()]` instead of StandardReaction -- rays
+    pass straight through every optical segment.  (2D only: the reference's 3D branch copies
+    `z_start` instead of `z_end`, operation.py:330.)"""
+    scene = golden_scenes()["ref_segments2d"]
+    eng, system = reference_engine_2d(ref, scene)
+    ghost = ref.engine.OpticalEngine(2, [ref.operation.GhostThrough()], compile_dead_rays=True,
+                                     compile_stopped_rays=True,
+                                     simple_ray_inheritance={"wavelength", "slot"})
+    ghost.optical_system = system
+    ghost.validate_system()
+    ghost.ray_trace(5)
+    out = {}
+    _record_sets(out, ghost, RAYS2)
+    return out
+
+
 def main():
     ref = import_reference()
     data = function_vectors(ref)
@@ -728,6 +748,10 @@ def main():
     path = os.path.join(HERE, "ref_projection.npz")
     np.savez_compressed(path, **data)
     print(f"{path}: {len(data)} arrays:", {k: v.shape for k, v in data.items() if k.endswith("x_start")})
+    data = ghost_vectors(ref)
+    path = os.path.join(HERE, "ref_ghost2d.npz")
+    np.savez_compressed(path, **data)
+    print(f"{path}: {len(data)} arrays:", {k: v.shape for k, v in data.items() if k.endswith("slot")})
     data = projection_vectors_2d(ref)
     path = os.path.join(HERE, "ref_projection2d.npz")
     np.savez_compressed(path, **data)

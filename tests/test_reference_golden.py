@@ -584,3 +584,31 @@ def test_cuda_projection_result_2d_matches_reference():
     engine.optical_system.update()
     rays = dict(engine.optical_system._amalgamated_sources)
     _check_projection(engine.process_projection_2D(rays), want, 1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_ghost_through_hook_path_matches_reference():
+    """The operation-hook path (`single_pass` with a non-StandardReaction operation): the
+    segments-only 2D scene traced with `[GhostThrough()]` against the reference engine's own run --
+    same membership and order of every history set, same rays."""
+    from tensorflowraytrace_b200 import engine as eng_mod, operation, scenes
+    want = load("ref_ghost2d")
+    scene = SCENES["ref_segments2d"]
+    base, _, src = scenes.build_engine_2d(scene, eps=helpers.EPS)
+    src["slot"] = torch.arange(scene["sources"]["x_start"].shape[0], dtype=torch.float32)
+    system = base.optical_system
+    system.update()
+    ghost = eng_mod.OpticalEngine(2, [operation.GhostThrough()], compile_dead_rays=True,
+                                  compile_stopped_rays=True,
+                                  simple_ray_inheritance={"wavelength", "slot"})
+    ghost.optical_system = system
+    ghost.validate_system()
+    ghost.ray_trace(5)
+    for set_name in ("active", "finished", "stopped"):
+        s = getattr(ghost, set_name + "_rays")
+        assert np.array_equal(s["slot"].cpu().numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
+        for f in helpers.RAY_FIELDS_2D:
+            assert helpers.rel_err(s[f].detach().cpu().numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+    assert "dead_slot" not in want
+    dead = ghost.dead_rays
+    assert not bool(dead) or dead["x_start"].shape[0] == 0
