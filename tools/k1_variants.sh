@@ -1,6 +1,7 @@
 #!/bin/bash
 # Build tuning variants of the search kernel into build/k1/ (run here, on the CPU box), then
-# `gpurun -- tools/k1_variants.sh run` times them on the B200.
+# `gpurun -- tools/k1_variants.sh run` times them on the B200.  Run-time switches of every binary:
+# TFRT_K1_QUEUE=0|1|2 (item queue never / auto / always), TFRT_K1_ITEMS_PER_CTA=n.
 set -e
 cd "$(dirname "$0")/.."
 SRC="tools/k1_bench.cu tensorflowraytrace_b200/csrc/abi.cu tensorflowraytrace_b200/csrc/pack.cu tensorflowraytrace_b200/csrc/intersect3d.cu"
@@ -14,6 +15,10 @@ V[r3]="-DTFRT_K1_FORCE_R2=3"
 V[r6]="-DTFRT_K1_FORCE_R2=6 -DTFRT_K1_MINBLOCKS=2"
 V[t256]="-DTFRT_K1_THREADS=256 -DTFRT_K1_MINBLOCKS=2"
 V[s2]="-DTFRT_K1_STAGES=2"
+V[s4]="-DTFRT_K1_STAGES=4"
+V[mb3]="-DTFRT_K1_MINBLOCKS=3"
+V[mb5]="-DTFRT_K1_MINBLOCKS=5"
+V[scalar]="-DTFRT_K1_SCALAR=1"
 if [ "$1" = "run" ]; then
   for v in "${!V[@]}"; do printf "%-12s " $v; ./build/k1/$v ${2:-4194304} ${3:-100}; done | sort
   exit 0
