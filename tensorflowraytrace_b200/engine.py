@@ -482,6 +482,63 @@ class OpticalSystem2D(OpticalSystemBase):
         return raw_seg, raw_arc
 
 
+    # ---- the reference's per-geometry seams (tfrt/engine.py:626-866), same names and signatures
+    @staticmethod
+    def _seg_or_arc(seg_u, arc_u, seg_valid, arc_valid):
+        """Where a ray hits both a segment and an arc keep the nearer (tfrt/engine.py:626-657)."""
+        has_both = seg_valid & arc_valid
+        seg_less = seg_u < arc_u
+        return (torch.where(has_both, seg_less, seg_valid),
+                torch.where(has_both, ~seg_less, arc_valid))
+
+    @staticmethod
+    def _get_arc_norm(radius, arc_u, gather_ray):
+        """Arc normal angle: the hit's polar angle, turned by pi for negative radii, wrapped to
+        (-pi, pi] (tfrt/engine.py:666-670; `gather_ray` indexes the arcs, as in the reference)."""
+        radius = radius[gather_ray]
+        arc_norm = torch.where(radius < 0, arc_u + geometry.PI, arc_u)
+        return torch.remainder(arc_norm + geometry.PI, 2 * geometry.PI) - geometry.PI
+
+    @staticmethod
+    def _one_geometry(rays4, seg=None, arc=None, eps=(1e-10, 1e-5, 1e-4)):
+        from types import SimpleNamespace
+        names = kernels.SEG_FIELDS if seg is not None else kernels.ARC_FIELDS
+        merged = dict(zip(names, seg if seg is not None else arc))
+        stacked = torch.stack(list(seg if seg is not None else arc)).to(torch.float32).contiguous()
+        adapter = SimpleNamespace(
+            _merged_segments=merged if seg is not None else {},
+            _merged_arcs=merged if arc is not None else {},
+            merged_device_arrays=lambda: (stacked, None) if seg is not None else (None, stacked),
+            intersect_epsilion=float(eps[0]), size_epsilion=float(eps[1]),
+            ray_start_epsilion=float(eps[2]))
+        rays = dict(zip(kernels.RAY_FIELDS_2D, rays4))
+        seg_res, arc_res = OpticalSystem2D.intersect(adapter, rays)
+        return seg_res if seg is not None else arc_res
+
+    @staticmethod
+    def _segment_intersection(rx1, ry1, rx2, ry2, sx1, sy1, sx2, sy2, intersect_epsilion,
+                              size_epsilion, ray_start_epsilion):
+        """N rays x M segments -> per-ray nearest valid hit (tfrt/engine.py:672-749): x, y, valid,
+        ray_u, seg_u, gather_ray, gather_segment; values of rays without a valid hit are
+        unspecified, as in the reference."""
+        r = OpticalSystem2D._one_geometry(
+            (rx1, ry1, rx2, ry2), seg=(sx1, sy1, sx2, sy2),
+            eps=(intersect_epsilion, size_epsilion, ray_start_epsilion))
+        return (r["x"], r["y"], r["valid"], r["ray_u"], r["segment_u"], r["gather_ray"],
+                r["gather_segment"])
+
+    @staticmethod
+    def _arc_intersection(rx1, ry1, rx2, ry2, xc, yc, a1, a2, r, intersect_epsilion,
+                          size_epsilion, ray_start_epsilion):
+        """N rays x M arcs -> per-ray nearest valid hit (tfrt/engine.py:751-866): x, y, valid,
+        ray_u, arc_u (the hit's polar angle), gather_ray, gather_arc."""
+        res = OpticalSystem2D._one_geometry(
+            (rx1, ry1, rx2, ry2), arc=(xc, yc, a1, a2, r),
+            eps=(intersect_epsilion, size_epsilion, ray_start_epsilion))
+        return (res["x"], res["y"], res["valid"], res["ray_u"], res["arc_u"], res["gather_ray"],
+                res["gather_arc"])
+
+
 # =========================================================================================
 
 class OpticalEngine:

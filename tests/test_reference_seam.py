@@ -158,3 +158,45 @@ def test_reference_2d_engine_with_the_cuda_seam_reproduces_the_reference(name):
             assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
         checked += 1
     assert checked >= 2
+
+
+@pytest.mark.parametrize("name", ["ref_wedge2d", "ref_arclens2d", "ref_segments2d"])
+def test_reference_2d_engine_with_per_geometry_cuda_seams(name):
+    """Seam b1 in 2D: the reference's `_segment_intersection` / `_arc_intersection` staticmethods
+    (tfrt/engine.py:672-866) replaced by this package's methods of the same names; the reference's
+    own `intersect` (norms, `_seg_or_arc`), projection and reaction code runs around them."""
+    from tensorflowraytrace_b200 import engine as ours
+    rr, ref = _reference()
+    want = dict(np.load(os.path.join(HERE, "golden", f"{name}.npz")))
+    scene = mrg.golden_scenes()[name]
+    dev = torch.device("cuda:0")
+    calls = {"n": 0}
+
+    def wrap(fn):
+        def seam(*args):
+            calls["n"] += 1
+            tensors = [a.to(device=dev, dtype=torch.float32) for a in args[:-3]]
+            out = fn(*tensors, *[float(a) for a in args[-3:]])
+            x, y, valid, ray_u, geo_u, gather_ray, gather_geo = out
+            f64 = lambda t: t.to(device="cpu", dtype=torch.float64)      # noqa: E731
+            return (f64(x), f64(y), valid.cpu().bool(), f64(ray_u), f64(geo_u),
+                    gather_ray.cpu().long(), gather_geo.cpu().long())
+        return staticmethod(seam)
+
+    cls = ref.engine.OpticalSystem2D
+    saved = (cls.__dict__["_segment_intersection"], cls.__dict__["_arc_intersection"])
+    cls._segment_intersection = wrap(ours.OpticalSystem2D._segment_intersection)
+    cls._arc_intersection = wrap(ours.OpticalSystem2D._arc_intersection)
+    try:
+        eng, system = rr.reference_engine_2d(ref, scene)
+        eng.ray_trace(scene["max_iterations"])
+    finally:
+        cls._segment_intersection, cls._arc_intersection = saved
+    assert calls["n"] >= 2
+    for set_name in ("active", "finished", "stopped", "dead"):
+        if f"{set_name}_slot" not in want:
+            continue
+        s = getattr(eng, set_name + "_rays")
+        assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
+        for f in helpers.RAY_FIELDS_2D:
+            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
