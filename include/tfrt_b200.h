@@ -10,9 +10,10 @@
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in `_host`.
  *   - All work is enqueued on the given stream (a cudaStream_t passed as void*); no hidden
- *     synchronisation; the caller owns every buffer, including workspaces.  The only memory
- *     the library allocates itself is a 256-byte per-device array of work counters for the
- *     persistent search kernel (first call) and the 4-byte sink of tfrt_fp32_peak.
+ *     synchronisation; the caller owns every buffer, including workspaces and the work counters
+ *     of the persistent search kernel, so any number of calls may be in flight on any number of
+ *     streams and host threads.  The library keeps no per-call state; the only memory it
+ *     allocates itself is the 4-byte sink of the tfrt_fp32_peak measurement helper.
  *   - Return value 0 = success; nonzero = error, message in tfrt_last_error() (thread local).
  *   - Rays are structure-of-arrays fp32, "slot" indexed: slot i is source ray i for the whole
  *     trace (rays never split: StandardReaction emits exactly one child per active ray,
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFRT_B200_ABI_VERSION 3
+#define TFRT_B200_ABI_VERSION 4
 
 /* ray status after one projection (tfrt/engine.py:2063-2111) */
 #define TFRT_STATUS_ACTIVE 0   /* hit an OPTICAL boundary: reacts and continues */
@@ -57,6 +58,9 @@ typedef struct {
 
 const char *tfrt_last_error(void);
 int tfrt_abi_version(void);
+/* hash of the sources the library was built from (set by the build; "unknown" otherwise): lets a
+ * binding detect a stale library after a kernel edit that did not bump the ABI version */
+const char *tfrt_source_hash(void);
 /* sizeof() of the ABI structs as compiled into the library, so a binding can verify its mirror:
  * which = 0 TfrtMaterial, 1 TfrtTrace3DArgs, 2 TfrtTrace3DBwdArgs, 3 TfrtTrace2DArgs;
  * 0 for an unknown code. */
@@ -84,10 +88,18 @@ int tfrt_faces_backward(const float *vertices, const int32_t *faces, const uint8
  * re-derives edge vectors for all M x N pairs, tfrt/geometry.py:286-298).
  * tfrt_packed_floats(T) floats of workspace; size_eps is OpticalSystemBase.size_epsilion
  * (tfrt/engine.py:177-179), folded into the packed plane offsets.
+ *
+ * margin_ulps: the fp32 search accepts a hit when the barycentrics are inside the triangle
+ * inflated by size_eps PLUS a per-triangle margin of `margin_ulps` units in the last place of the
+ * triangle's largest coordinate (converted to barycentric units by the smallest altitude); the
+ * winner is then re-evaluated in fp64 and must pass the reference's exact rule
+ * (tfrt/engine.py:1138-1141), otherwise that ray is searched again exactly.  The margin scales
+ * with the scene (millimetre units, a lens far from the origin).  0 = the fp32 band is exactly
+ * size_eps (rays within fp32 rounding of an outer mesh edge may then be missed).
  */
 size_t tfrt_packed_floats(int32_t n_tri);
-int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps, float *packed,
-                        void *stream);
+int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps,
+                        float margin_ulps, float *packed, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * b1  intersection seam.
@@ -96,13 +108,21 @@ int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps
  * hit (argmin over triangles, lowest index on ties) + gather.
  * ray[6] = x_start,y_start,z_start,x_end,y_end,z_end (N each).  Outputs (N each): x,y,z, valid,
  * ray_u, trig_u, trig_v, gather_trig (gather_ray is arange(N) in the reference and is omitted).
- * `hit_ws` is N uint64 of workspace.
+ * `hit_ws` is N + 1 uint64 of workspace (the last word is the search kernel's work counter).
+ * margin_ulps must equal the value given to tfrt_pack_triangles.
+ * `diag` (4 int32, may be NULL) receives the re-validation counters:
+ *   diag[0] = winners of the fp32 search that failed the reference's rule in fp64 and were
+ *             searched again exactly (expected: a few per 100 000 rays, the rays within rounding
+ *             of a triangle edge);
+ *   diag[1] = of those, failures far beyond fp32 rounding -- a defect of the search, never
+ *             expected (tests assert 0);
+ *   diag[2] = exact re-searches that found a valid hit;  diag[3] reserved.
  */
 int tfrt_intersect3d(const float *const ray[6], int32_t n_rays, const float *const tri[9],
                      const float *packed, int32_t n_tri, float intersect_eps, float size_eps,
-                     float ray_start_eps, uint64_t *hit_ws, float *x, float *y, float *z,
-                     uint8_t *valid, float *ray_u, float *trig_u, float *trig_v,
-                     int32_t *gather_trig, void *stream);
+                     float ray_start_eps, float margin_ulps, uint64_t *hit_ws, float *x, float *y,
+                     float *z, uint8_t *valid, float *ray_u, float *trig_u, float *trig_v,
+                     int32_t *gather_trig, int32_t *diag, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * b4  whole-loop seam: OpticalEngine.ray_trace (tfrt/engine.py:2311-2330) with
@@ -118,9 +138,11 @@ typedef struct {
     float size_eps;         /* .size_epsilion (must equal the value used for `packed`) */
     float ray_start_eps;    /* .ray_start_epsilion */
     float new_ray_length;   /* OpticalEngine.new_ray_length  tfrt/engine.py:1228 */
+    float margin_ulps;      /* the value given to tfrt_pack_triangles */
     int32_t index_mode;     /* 1: StandardReaction("index") mat_in/mat_out + materials table;
                                0: ("value") per-triangle n_in / n_out */
     int32_t n_materials;
+    int32_t n_lambda;       /* columns of n_table */
 
     const float *src[7];    /* x_start,y_start,z_start,x_end,y_end,z_end,wavelength; N each */
     const float *tri[9];    /* xp,yp,zp,x1,y1,z1,x2,y2,z2; T each */
@@ -134,6 +156,11 @@ typedef struct {
     const float *n_in;      /* n_optical (value mode) */
     const float *n_out;
     const TfrtMaterial *materials; /* n_materials, device */
+    const double *n_table;  /* optional (n_materials, n_lambda): refractive indices of ARBITRARY
+                               material callables (tfrt/operation.py:265-267 evaluates any
+                               mat["n"](wavelength)), tabulated by the caller over the distinct
+                               wavelengths of the source set; takes precedence over `materials` */
+    const int32_t *lambda_index; /* N: column of n_table for every source ray */
     const float *packed;    /* tfrt_pack_triangles output */
 
     /* workspace + history ("tape"), all caller-allocated */
@@ -150,11 +177,19 @@ typedef struct {
     int32_t *tape_outpos;   /* K*N : position of the slot in its category list at that iteration */
     int32_t *live;          /* (K+1)*N : live[k] = slots entering iteration k, ascending */
     int32_t *cat_ids[3];    /* N each: slots that STOPPED / FINISHED / DIED, iteration-major */
-    int32_t *block_counts;  /* 8*ceil(N/256) */
+    void *sync_ws;          /* tfrt_trace3d_sync_bytes(N, K) bytes, 16-byte aligned: per-iteration
+                               work counters of the search kernel, CTA tickets and look-back
+                               words of the single-pass compaction (zeroed by the call) */
     int32_t *counters;      /* (K+1)*4: [k][0]=live entering k, [k][1..3]=cumulative
                                stopped/finished/dead before k */
+    int32_t *diag;          /* 4: re-validation counters, summed over iterations (meaning as in
+                               tfrt_intersect3d) */
 } TfrtTrace3DArgs;
 
+size_t tfrt_trace3d_sync_bytes(int32_t n_rays, int32_t max_iterations);
+
+/* Enqueues 1 + 2 K kernels (set-up, then search + reaction per iteration); no memsets, no host
+ * round trip: the live counts stay on the device. */
 int tfrt_trace3d_forward(const TfrtTrace3DArgs *args, void *stream);
 
 /* Materialise one history set in the reference's order (concat over iterations of the

@@ -6,10 +6,12 @@ pybind, so one nvcc invocation builds it in seconds and the resulting .so travel
 source tree.  `python -m tensorflowraytrace_b200._build` or `__graft_entry__.build()`.
 """
 
+import hashlib
 import os
 import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -35,23 +37,52 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
-        return True
-    lib_m = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"),
+def can_build():
+    """nvcc and the CUDA sources are both present."""
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return os.path.exists(exe) and len(sources()) == len(SOURCES)
+
+
+def _deps():
+    return sources() + [os.path.join(CSRC, "common.cuh"),
                         os.path.join(HERE, "..", "include", "tfrt_b200.h")]
-    return any(os.path.getmtime(d) > lib_m for d in deps if os.path.exists(d))
+
+
+def source_hash():
+    """Hash of every file the library is built from; compiled into the library
+    (tfrt_source_hash) so that a stale .so is detected whatever the file times say."""
+    h = hashlib.sha256()
+    for path in _deps():
+        if os.path.exists(path):
+            h.update(os.path.basename(path).encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def needs_build():
+    """True when the library is missing (file-time checks are not used: a copied tree has
+    arbitrary times; `_lib.load` compares the embedded source hash instead)."""
+    return not os.path.exists(LIB_PATH)
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into libtfrt_b200.so (sm_100a).  Returns the library path."""
+    """Compile every CUDA source into libtfrt_b200.so (sm_100a).  Returns the library path.
+    The library is written under a temporary name and renamed, so concurrent processes (one per
+    GPU under torchrun) never load a half-written file."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    fd, tmp = tempfile.mkstemp(prefix=".libtfrt_b200.", suffix=".so", dir=HERE)
+    os.close(fd)
+    cmd = ([_nvcc()] + NVCC_FLAGS + [f'-DTFRT_SOURCE_HASH="{source_hash()}"']
+           + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources())
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.chmod(tmp, 0o755)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(proc.stderr)
     return LIB_PATH

@@ -29,8 +29,10 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("size_eps", ctypes.c_float),
         ("ray_start_eps", ctypes.c_float),
         ("new_ray_length", ctypes.c_float),
+        ("margin_ulps", ctypes.c_float),
         ("index_mode", ctypes.c_int32),
         ("n_materials", ctypes.c_int32),
+        ("n_lambda", ctypes.c_int32),
         ("src", c_void_p * 7),
         ("tri", c_void_p * 9),
         ("norm", c_void_p),
@@ -40,6 +42,8 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("n_in", c_void_p),
         ("n_out", c_void_p),
         ("materials", c_void_p),
+        ("n_table", c_void_p),
+        ("lambda_index", c_void_p),
         ("packed", c_void_p),
         ("cur", c_void_p * 6),
         ("cur_d", c_void_p),
@@ -50,8 +54,9 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("tape_outpos", c_void_p),
         ("live", c_void_p),
         ("cat_ids", c_void_p * 3),
-        ("block_counts", c_void_p),
+        ("sync_ws", c_void_p),
         ("counters", c_void_p),
+        ("diag", c_void_p),
     ]
 
 
@@ -106,17 +111,17 @@ class TfrtTrace2DArgs(ctypes.Structure):
 
 # every symbol include/tfrt_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "tfrt_last_error", "tfrt_abi_version", "tfrt_struct_size",
+    "tfrt_last_error", "tfrt_abi_version", "tfrt_source_hash", "tfrt_struct_size",
     "tfrt_faces_forward", "tfrt_faces_backward",
     "tfrt_packed_floats", "tfrt_pack_triangles",
     "tfrt_intersect3d",
-    "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
+    "tfrt_trace3d_sync_bytes", "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
     "tfrt_trace3d_backward",
     "tfrt_intersect2d", "tfrt_trace2d_forward", "tfrt_trace2d_backward",
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STRUCT_MIRRORS = (TfrtMaterial, TfrtTrace3DArgs, TfrtTrace3DBwdArgs, TfrtTrace2DArgs)
 
 _lib = None
@@ -126,6 +131,16 @@ def lib_path():
     return _build.LIB_PATH
 
 
+def _stale(path):
+    """The library's embedded source hash differs from the hash of the sources on disk."""
+    try:
+        probe = ctypes.CDLL(path)
+        probe.tfrt_source_hash.restype = ctypes.c_char_p
+        return probe.tfrt_source_hash().decode() != _build.source_hash()
+    except (OSError, AttributeError):
+        return True
+
+
 def load():
     """Load (building first if needed) libtfrt_b200.so; raises RuntimeError on failure."""
     global _lib
@@ -133,16 +148,23 @@ def load():
         return _lib
     if not os.path.exists(_build.LIB_PATH):
         _build.build()
+    elif _build.can_build() and _stale(_build.LIB_PATH):
+        # the sources changed since the library was built (a kernel edit without an ABI bump):
+        # never measure or test old code silently
+        _build.build(force=True)
     try:
         lib = ctypes.CDLL(_build.LIB_PATH)
     except OSError as e:  # pragma: no cover
         raise RuntimeError(f"tensorflowraytrace_b200: cannot load {_build.LIB_PATH}: {e}") from e
     lib.tfrt_last_error.restype = ctypes.c_char_p
     lib.tfrt_abi_version.restype = ctypes.c_int
+    lib.tfrt_source_hash.restype = ctypes.c_char_p
     lib.tfrt_struct_size.restype = ctypes.c_size_t
     lib.tfrt_struct_size.argtypes = [ctypes.c_int]
     lib.tfrt_packed_floats.restype = ctypes.c_size_t
     lib.tfrt_packed_floats.argtypes = [ctypes.c_int32]
+    lib.tfrt_trace3d_sync_bytes.restype = ctypes.c_size_t
+    lib.tfrt_trace3d_sync_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.tfrt_launch_count.restype = ctypes.c_longlong
     lib.tfrt_launch_count.argtypes = [ctypes.c_int]
     if lib.tfrt_abi_version() != ABI_VERSION:

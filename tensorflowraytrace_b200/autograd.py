@@ -37,25 +37,36 @@ class FacesFunction(torch.autograd.Function):
         return g_vertices, None, None
 
 
+def run_trace(tri, norm, src, plan, workspace=None):
+    """Enqueue the whole-loop trace described by `plan` (asynchronous) and leave the
+    kernels.Trace3D object (tape, counters) in plan.trace.  No autograd here: the graph node is
+    created by TraceFunction when the histories are materialised."""
+    tr = kernels.Trace3D(
+        src.detach(), tri.detach(), None if norm is None else norm.detach(), plan.category,
+        plan.n_optical, plan.max_iterations,
+        packed=plan.packed, mat_in=plan.mat_in, mat_out=plan.mat_out, n_in=plan.n_in,
+        n_out=plan.n_out, materials=plan.materials, n_materials=plan.n_materials,
+        n_table=plan.n_table, lambda_index=plan.lambda_index,
+        intersect_eps=plan.intersect_eps, size_eps=plan.size_eps,
+        ray_start_eps=plan.ray_start_eps, new_ray_length=plan.new_ray_length,
+        margin_ulps=plan.margin_ulps, workspace=workspace)
+    tr.forward()
+    plan.trace = tr
+    return tr
+
+
 class TraceFunction(torch.autograd.Function):
-    """Whole-loop trace.  Inputs: tri (9,T), norm (T,3) or None (geometric normals evaluated in
-    the kernel from the corners, their gradient then arrives through `tri`), src (7,N)
-    [x_start..z_end, wavelength],
-    and a `plan` (TracePlan) carrying the non-tensor configuration.  Outputs: the four history
-    ray sets (6,n_which) in the reference's order -- active, stopped, finished, dead -- with
-    (6,0) for sets the engine does not compile.  The kernels.Trace3D object (tape) is left in
-    plan.trace for the caller (slots / iterations of the history entries, live counts)."""
+    """Autograd node of a whole-loop trace.  Inputs: tri (9,T), norm (T,3) or None (geometric
+    normals evaluated in the kernel from the corners, their gradient then arrives through
+    `tri`), src (7,N) [x_start..z_end, wavelength], and a `plan` (TracePlan) carrying the
+    non-tensor configuration.  If plan.trace is unset the trace runs here; otherwise (the
+    engine enqueued it earlier with run_trace) only the histories are materialised.  Outputs:
+    the four history ray sets (6,n_which) in the reference's order -- active, stopped, finished,
+    dead -- with (6,0) for sets the engine does not compile."""
 
     @staticmethod
     def forward(ctx, tri, norm, src, plan):
-        tr = kernels.Trace3D(
-            src, tri, norm, plan.category, plan.n_optical, plan.max_iterations,
-            packed=plan.packed, mat_in=plan.mat_in, mat_out=plan.mat_out, n_in=plan.n_in, n_out=plan.n_out,
-            materials=plan.materials, n_materials=plan.n_materials,
-            intersect_eps=plan.intersect_eps, size_eps=plan.size_eps,
-            ray_start_eps=plan.ray_start_eps, new_ray_length=plan.new_ray_length)
-        tr.forward()
-        plan.trace = tr
+        tr = plan.trace if plan.trace is not None else run_trace(tri, norm, src, plan)
         outs, plan.slots, plan.iters = [], {}, {}
         for name in ("active", "stopped", "finished", "dead"):
             if name in plan.compile:
@@ -68,12 +79,17 @@ class TraceFunction(torch.autograd.Function):
             plan.slots[name], plan.iters[name] = slot, it
         ctx.plan = plan
         ctx.trace = tr
+        ctx.lease = plan.lease      # keeps the workspace from being reused while this graph lives
         ctx.src_shape = src.shape
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, g_active, g_stopped, g_finished, g_dead):
         plan, tr = ctx.plan, ctx.trace
+        if tr.ws.generation != tr.ws_generation:
+            raise RuntimeError(
+                "tensorflowraytrace_b200: the tape of this trace was overwritten by a later trace "
+                "that reused its workspace")
         g_hist = {}
         for name, g in (("active", g_active), ("stopped", g_stopped), ("finished", g_finished),
                         ("dead", g_dead)):
@@ -92,6 +108,18 @@ class TraceFunction(torch.autograd.Function):
                 g_src_full, None)
 
 
+class WorkspaceLease:
+    """Marks a trace workspace as in use: held (strongly) by the plan of the engine's pending
+    trace and by the autograd node of its histories, and weakly by the engine.  The engine
+    reuses the workspace for its next trace only when the lease has died, i.e. when no autograd
+    graph can still read the tape."""
+
+    __slots__ = ("workspace", "__weakref__")
+
+    def __init__(self, workspace):
+        self.workspace = workspace
+
+
 class TracePlan:
     """Non-tensor configuration of one fused trace (filled by OpticalEngine.ray_trace)."""
 
@@ -102,6 +130,9 @@ class TracePlan:
         self.mat_in, self.mat_out = kw.get("mat_in"), kw.get("mat_out")
         self.n_in, self.n_out = kw.get("n_in"), kw.get("n_out")
         self.materials, self.n_materials = kw.get("materials"), kw.get("n_materials", 0)
+        self.n_table, self.lambda_index = kw.get("n_table"), kw.get("lambda_index")
+        self.margin_ulps = kw.get("margin_ulps", kernels.DEFAULT_MARGIN_ULPS)
+        self.lease = None
         self.intersect_eps = kw["intersect_eps"]
         self.size_eps = kw["size_eps"]
         self.ray_start_eps = kw["ray_start_eps"]

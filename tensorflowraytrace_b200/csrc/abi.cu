@@ -14,6 +14,10 @@ void tfrt_set_error(const char *fmt, ...) {
 
 extern "C" const char *tfrt_last_error(void) { return g_err; }
 extern "C" int tfrt_abi_version(void) { return TFRT_B200_ABI_VERSION; }
+#ifndef TFRT_SOURCE_HASH
+#define TFRT_SOURCE_HASH "unknown"
+#endif
+extern "C" const char *tfrt_source_hash(void) { return TFRT_SOURCE_HASH; }
 extern "C" size_t tfrt_struct_size(int which) {
     switch (which) {
     case 0: return sizeof(TfrtMaterial);

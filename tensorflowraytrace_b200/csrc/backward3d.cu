@@ -43,6 +43,9 @@ struct BwdParams {
     const int32_t *mat_in, *mat_out;
     const float *n_in, *n_out;
     const TfrtMaterial *materials;
+    const double *n_table;      // optional tabulated indices (see TfrtTrace3DArgs)
+    const int32_t *lambda_index;
+    int n_lambda;
     float *g_ray[6];            // running cotangent of the ray entering iteration k+1 / k
     double *g_acc;              // T*12
     float *g_src[6];            // written at k == 0 when non-null
@@ -152,7 +155,11 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                 const double nh[3] = {nr[0] * ninv, nr[1] * ninv, nr[2] * ninv};
                 const double nu = nh[0] * uh[0] + nh[1] * uh[1] + nh[2] * uh[2];
                 double n_in, n_out;
-                if (P.index_mode) {
+                if (P.n_table) {
+                    const int li = P.lambda_index[slot];
+                    n_in = P.n_table[(size_t)P.mat_in[tri] * P.n_lambda + li];
+                    n_out = P.n_table[(size_t)P.mat_out[tri] * P.n_lambda + li];
+                } else if (P.index_mode) {
                     const double wl = P.src_wavelength[slot];
                     n_in = tfrt_material_n(P.materials[P.mat_in[tri]], wl);
                     n_out = tfrt_material_n(P.materials[P.mat_out[tri]], wl);
@@ -322,6 +329,7 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         P.norm = a->norm; P.src_wavelength = a->src[6];
         P.mat_in = a->mat_in; P.mat_out = a->mat_out; P.n_in = a->n_in; P.n_out = a->n_out;
         P.materials = a->materials;
+        P.n_table = a->n_table; P.lambda_index = a->lambda_index; P.n_lambda = a->n_lambda;
         for (int c = 0; c < 6; ++c) {
             P.g_ray[c] = b->g_ray_ws + (size_t)c * N;
             P.g_src[c] = b->g_src[c];

@@ -43,28 +43,64 @@ static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 
 // ---------------------------------------------------------------------------------------------
 // packed triangle layout
 //
-// One triangle = 12 floats = three float4 (one broadcast LDS.128 each), in the projected form of
-// Wald's ray-triangle test: k = dominant axis of the normal n = e1 x e2, (k1, k2) = (k+1, k+2) mod 3,
-// the plane scaled so that its k-coefficient is 1:
-//   q0 = (m1, m2, dd, index)    det = D[k] + m1 D[k1] + m2 D[k2],  t' = dd - O[k] - m1 O[k1] - m2 O[k2]
-//   q1 = (s1, s2, s0, n[k])     S = s1 P[k1] + s2 P[k2] + s0  =  2 (u + v) - C
-//   q2 = (e1, e2, e0, header)   E = e1 P[k1] + e2 P[k2] + e0  =  u - v
+// Per triangle, 9 coefficients of the projected form of Wald's ray-triangle test: k = dominant
+// axis of the normal n = e1 x e2, (k1, k2) = (k+1, k+2) mod 3, the plane scaled so that its
+// k-coefficient is 1:
+//   m1, m2, dd      det = D[k] + m1 D[k1] + m2 D[k2],  t' = dd - O[k] - m1 O[k1] - m2 O[k2]
+//   s1, s2, s0      S = s1 P[k1] + s2 P[k2] + s0  =  2 (u + v) - C
+//   e1, e2, e0      E = e1 P[k1] + e2 P[k2] + e0  =  u - v
 // with m = n/n[k], dd = m.A, u = a3.P + ad and v = b3.P + bd the barycentric planes
-// (a3 = (e2 x n)/|n|^2, b3 = (n x e1)/|n|^2, size_eps folded into ad, bd), P[k] eliminated through
-// the plane equation (exact for points on the plane), C = 1 + 3 size_eps.  The kernel accepts a hit
-// iff |E| + |S - |E|| <= C, which is u >= 0, v >= 0, u + v <= C: 14 FMA-pipe lane-ops and two
-// integer compares per test.
-// det * n[k] is the reference's denominator (tfrt/geometry.py:300) up to sign.
-// Inside a tile the records are grouped by k (stable: index order inside a group) so that the
-// kernel runs three specialised loops without a per-triangle branch; `index` is the triangle's
-// position in the merged set, `header` of record 0 = (size of group 0) | (size of group 1) << 16.
-// FFMA2 takes a 32-bit register broadcast to both halves (SASS operand `R.F32`), so a
-// coefficient multiplies the two rays of a pair without being stored twice.
+// (a3 = (e2 x n)/|n|^2, b3 = (n x e1)/|n|^2, the inflation folded into ad, bd), P[k] eliminated
+// through the plane equation (exact for points on the plane), C = 1 + 3 size_eps.  The kernel
+// accepts a hit iff |E| + |S - |E|| <= C, which is u >= 0, v >= 0, u + v <= C: 14 FMA-pipe
+// lane-ops per test.  det * n[k] is the reference's denominator (tfrt/geometry.py:300) up to
+// sign.
+//
+// Storage: triangles travel in PAIRS (A, B) of one dominant axis, one pair record = 24 floats =
+// six float4, every coefficient as the adjacent pair (A's, B's) that a packed f32x2 instruction
+// takes as its 64-bit operand:
+//   f4[0] = (m1A, m1B, m2A, m2B)    f4[1] = (ddA, ddB, s1A, s1B)    f4[2] = (s2A, s2B, s0A, s0B)
+//   f4[3] = (e1A, e1B, e2A, e2B)    f4[4] = (e0A, e0B, indexA, indexB)
+//   f4[5] = (n[k]A, n[k]B, header, 0)           (read only on the rare hit path; the last word
+//           of the mesh's very first record holds the scene scale = largest |coordinate|)
+// `index` is the triangle's position in the merged set.  A tile holds TFRT_TILE_TRIS consecutive
+// triangles of the merged set, grouped by k (stable: index order inside a group) so that the
+// kernel runs three specialised loops without a per-triangle branch; a group of odd size is
+// completed with a never-hit half (S = 4 > C), hence TFRT_TILE_PAIRS = TRIS/2 + 2 pair slots;
+// `header` of the tile's record 0 = pairs in group 0 | pairs in group 1 << 8 | group 2 << 16.
 #define TFRT_TRI_FLOATS 12
 #define TFRT_TILE_TRIS 256                      // triangles per shared-memory stage
-#define TFRT_TILE_BYTES (TFRT_TILE_TRIS * TFRT_TRI_FLOATS * 4)
+#define TFRT_TILE_PAIRS (TFRT_TILE_TRIS / 2 + 2)
+#define TFRT_TILE_BYTES (TFRT_TILE_PAIRS * 2 * TFRT_TRI_FLOATS * 4)
 
 #define TFRT_NOHIT_KEY 0x7f800000u              // +inf bits: "no valid hit yet"
+
+// Search margin of one triangle, in barycentric units: the fp32 search accepts a hit when the
+// inflated barycentrics are >= -(size_eps + margin), and the fp64 evaluation of the winner then
+// decides with the reference's exact rule (tfrt/engine.py:1138-1141).  The margin is `ulps`
+// units in the last place of the largest coordinate of the triangle (the position error of an
+// fp32 hit point near it), converted to barycentric units by the steepest barycentric gradient
+// (1 / smallest altitude).  Scale-aware: a mesh in millimetres or far from the origin gets a
+// proportionally larger margin.  A, e1 = B - A, e2 = C - A in fp64.
+__host__ __device__ inline double tfrt_tri_margin(const double A[3], const double e1[3],
+                                                  const double e2[3], double ulps) {
+    double scale = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        const double a = fabs(A[c]), b = fabs(A[c] + e1[c]), d = fabs(A[c] + e2[c]);
+        scale = fmax(scale, fmax(a, fmax(b, d)));
+    }
+    const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                         e1[0] * e2[1] - e1[1] * e2[0]};
+    const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+    if (!(nn > 0.0)) return 0.0;
+    // |grad u| = |e2| / |N|, |grad v| = |e1| / |N|, |grad w| = |e2 - e1| / |N|
+    const double l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+    const double l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+    const double d0 = e2[0] - e1[0], d1 = e2[1] - e1[1], d2 = e2[2] - e1[2];
+    const double l3 = d0 * d0 + d1 * d1 + d2 * d2;
+    const double g = sqrt(fmax(l1, fmax(l2, l3)) / nn);
+    return ulps * 1.1920928955078125e-7 * scale * g;
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy (TMA 1-D) PTX wrappers

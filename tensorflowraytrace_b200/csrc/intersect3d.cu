@@ -5,13 +5,21 @@
 // (tfrt/engine.py:1138-1148).  Every live ray is tested against every triangle.
 //
 // Design
-//  * a thread owns 2*R2 rays kept in registers as R2 f32x2 pairs (origin, direction);
+//  * a thread owns NR rays in registers (origin, direction: 6 scalars each);
 //  * triangles stream through shared memory in tiles of TFRT_TILE_TRIS, copied by one elected
 //    thread with cp.async.bulk (TMA 1-D) into a 3-stage mbarrier ring;
+//  * the tile stores triangles in PAIRS: every packed f32x2 instruction tests one ray against two
+//    triangles, with the two triangles' coefficients as the 64-bit operand and the ray's scalars
+//    as 32-bit broadcast operands (SASS `R.F32`).  The register file delivers two 32-bit operands
+//    per cycle per scheduler (tools/ffma2_probe.cu), so what an instruction costs is
+//    max(2 FMA-pipe cycles, operands read / 2); consecutive instructions that share an operand in
+//    the same slot get it from the operand reuse cache for free.  Looping the NR rays over one
+//    triangle pair makes the WIDE operands (the coefficient pairs) the shared ones: ~23 operand
+//    reads per test instead of ~33 for the transposed layout (two rays x one triangle), which
+//    puts the loop back on the FMA pipe (profiles/r2_k1_tuning.md);
 //  * per (ray, triangle) the projected precomputed-plane test (Wald's projection onto the
 //    dominant axis k of the normal, plane scaled to a unit k-coefficient; record layout in
-//    common.cuh) costs 14 fp32 ops issued as 7 FFMA2/FADD2/FMUL2 per ray (two rays per
-//    instruction) + 1 MUFU.RCP + 2 integer compares:
+//    common.cuh) costs 14 fp32 ops = 7 packed instructions per test + 1 MUFU.RCP:
 //        det = D[k] + m1 D[k1] + m2 D[k2]      t' = dd - O[k] - m1 O[k1] - m2 O[k2]
 //        t   = t'/det     (origin pre-shifted by ray_start_eps so t >= 0 <=> valid)
 //        P1  = O[k1] + t D[k1]                 P2 = O[k2] + t D[k2]
@@ -19,54 +27,49 @@
 //        x   = |E| + |S - |E||     (absolute values are free operand modifiers of FADD2)
 //    with u, v the barycentrics inflated by size_eps and C = 1 + 3 size_eps:
 //        inside  <=>  u >= 0, v >= 0, u + v <= C  <=>  x <= C
-//    (min(u,v) = (u+v-|u-v|)/2 and min(p,q) >= 0 <=> p+q >= |p-q|, applied twice), so
-//    valid & nearer  <=>  bits(x) <= bits(C)  and  bits(t) < best   as unsigned integers
-//    (negative t, NaN and +inf all compare high);
-//    the triangles of a tile are grouped by k, so three specialised loops run back to back
+//    (min(u,v) = (u+v-|u-v|)/2 and min(p,q) >= 0 <=> p+q >= |p-q|, applied twice);
+//  * x >= 0 or NaN, so "some ray of this thread is inside one of the two triangles" is
+//    min over the thread's x values <= C: one FMNMX3 per ray (two x values each), one compare and
+//    one warp vote per triangle pair; everything else (is the hit nearer? |den| >= eps? which
+//    ray?) happens in the rare warp-uniform branch behind the vote;
+//  * the triangles of a tile are grouped by k, so three specialised loops run back to back
 //    with the roles of the ray components fixed at compile time;
-//  * the running best is (bits(t), triangle index); the scan is in index order inside an axis
-//    group and strict '<' keeps the first, so exact ties between triangles of one group (e.g.
-//    the coplanar halves of a flat target) go to the lowest index, the behaviour of argmin in
-//    the reference's CPU kernels; an exact tie between triangles of different dominant axes of
-//    one tile goes to the lower axis (a bit-equal t from two different planes: a near tie by
-//    the north star's rule);
-//  * optional split of the triangle range over blockIdx.y, merged with a 64-bit atomicMin on
-//    (key << 32 | index) -- same tie rule -- so small ray counts still fill 148 SMs.
-#include <atomic>
-#include <type_traits>
+//  * the running best is (bits(t), triangle index), updated to the lexicographic minimum: exact
+//    ties go to the lowest triangle index whatever the scan order, the behaviour of argmin in the
+//    reference's CPU kernels (e.g. the coplanar halves of a flat target), and the same rule the
+//    64-bit atomicMin on (key << 32 | index) applies when the triangle range is split over CTAs.
 #include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
 // Tunables.  The defaults are the measured best of the variants timed by tools/k1_variants.sh
-// (profiles/r1_k1_tuning.md); tools/k1_bench.cu compiles the others with -D.
+// (profiles/r2_k1_tuning.md); tools/k1_bench.cu compiles the others with -D.
 #ifndef TFRT_K1_THREADS
 #define TFRT_K1_THREADS 128
 #endif
 #ifndef TFRT_K1_STAGES
 #define TFRT_K1_STAGES 3
 #endif
-#ifndef TFRT_K1_UNROLL
-#define TFRT_K1_UNROLL 2
+#ifndef TFRT_K1_FORCE_NR    // 0: choose rays per thread from the ray count
+#define TFRT_K1_FORCE_NR 0
 #endif
-#ifndef TFRT_K1_FORCE_R2    // 0: choose rays per thread from the ray count
-#define TFRT_K1_FORCE_R2 0
-#endif
-#ifndef TFRT_K1_MINBLOCKS   // 4 CTAs of 128 threads per SM <=> at most 128 registers
-#define TFRT_K1_MINBLOCKS 4
+#ifndef TFRT_K1_MINBLOCKS   // 3 CTAs of 128 threads per SM <=> at most 168 registers
+#define TFRT_K1_MINBLOCKS 3
 #endif
 
 namespace {
 
 constexpr int kThreads = TFRT_K1_THREADS;
 constexpr int kStages = TFRT_K1_STAGES;
-constexpr int kUnroll = TFRT_K1_UNROLL;
 
 constexpr int kItemQueue = 8;   // published work items in flight (the producer is at most
                                 // kStages + 1 items ahead of the slowest consumer warp)
 
 struct __align__(16) IntersectSmem {
-    float4 tile[kStages][TFRT_TILE_TRIS * 3];
+    float4 tile[kStages][TFRT_TILE_PAIRS * 6];
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint64_t item_ready[kItemQueue];
@@ -79,31 +82,15 @@ struct __align__(16) IntersectSmem {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-// packed f32x2 arithmetic (SASS FFMA2 / FMUL2 / FADD2); TFRT_K1_SCALAR=1 builds the same kernel from
-// scalar FFMA / FMUL / FADD for the tuning study (profiles/r1_k1_tuning.md)
-#ifndef TFRT_K1_SCALAR
-#define TFRT_K1_SCALAR 0
-#endif
-#if TFRT_K1_SCALAR
-__device__ __forceinline__ float2 k_fma2(float2 a, float2 b, float2 c) {
-    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
-}
-__device__ __forceinline__ float2 k_mul2(float2 a, float2 b) {
-    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
-}
-__device__ __forceinline__ float2 k_add2(float2 a, float2 b) {
-    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
-}
-#else
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }   // SASS: R.F32
 __device__ __forceinline__ float2 k_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 k_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 k_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-#endif
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
 
-template <int R2, bool kQueue>
-__global__ void __launch_bounds__(kThreads, (R2 >= 4 ? TFRT_K1_MINBLOCKS : 1))
+template <int NR, bool kQueue>
+__global__ void __launch_bounds__(kThreads, (NR >= 8 ? TFRT_K1_MINBLOCKS : 1))
 k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const float *__restrict__ sz, const float *__restrict__ ex,
               const float *__restrict__ ey, const float *__restrict__ ez,
@@ -111,7 +98,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               int n_live_static, const float4 *__restrict__ packed, int n_tiles,
               int tiles_per_split, int splits, float intersect_eps, float ray_start_eps,
               float w_one, unsigned long long *__restrict__ hit, int use_atomic, int dir_mode,
-              unsigned int *__restrict__ work_counter) {
+              unsigned int *__restrict__ work_counter, float start_floor_ulps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     IntersectSmem &sm = *reinterpret_cast<IntersectSmem *>(smem_raw);
 
@@ -128,7 +115,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
     // tiles before it starts them, which unbalances launches made of few, short items.
     // !kQueue (short items): one item at a time, fetched between two __syncthreads.
     const int n_live = n_live_ptr ? *n_live_ptr : n_live_static;
-    const int rays_per_cta = kThreads * 2 * R2;
+    const int rays_per_cta = kThreads * NR;
     const int ray_blocks = (n_live + rays_per_cta - 1) / rays_per_cta;
     const int total_items = ray_blocks * splits;
     const int tid = threadIdx.x;
@@ -168,7 +155,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         const int s = g % kStages;
         if (g >= (uint32_t)kStages) mbar_wait(&sm.empty[s], ((g / kStages) - 1) & 1);
         mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
-        bulk_g2s(sm.tile[s], packed + (size_t)(sm.p_tile_begin + sm.p_tile) * TFRT_TILE_TRIS * 3,
+        bulk_g2s(sm.tile[s], packed + (size_t)(sm.p_tile_begin + sm.p_tile) * TFRT_TILE_PAIRS * 6,
                  TFRT_TILE_BYTES, &sm.full[s]);
         ++sm.p_tile;
         sm.p_g = g + 1;
@@ -178,7 +165,7 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
         const int s = g % kStages;
         if (g >= (uint32_t)kStages) mbar_wait(&sm.empty[s], ((g / kStages) - 1) & 1);
         mbar_arrive_expect_tx(&sm.full[s], TFRT_TILE_BYTES);
-        bulk_g2s(sm.tile[s], packed + (size_t)tile * TFRT_TILE_TRIS * 3, TFRT_TILE_BYTES,
+        bulk_g2s(sm.tile[s], packed + (size_t)tile * TFRT_TILE_PAIRS * 6, TFRT_TILE_BYTES,
                  &sm.full[s]);
     };
     if constexpr (kQueue) {
@@ -187,6 +174,12 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
     }
 
     const uint32_t c_bits = __float_as_uint(w_one);   // C = 1 + 3*size_eps (eps is folded into the planes)
+    // Floor of the ray-start exclusion, as a distance: a ray that starts on a surface (the
+    // previous hit, rounded to fp32) is off its plane by about an ulp of the scene's coordinates,
+    // so the search cannot tell hits nearer than a few ulps from the self-hit.  The exact
+    // exclusion (ray_start_epsilion) is applied to the winner in fp64 afterwards.
+    const float start_floor =
+        start_floor_ulps * 1.1920929e-7f * __ldg(reinterpret_cast<const float *>(packed) + 23);
     uint32_t seq = 0;                       // tiles this warp (CTA) has consumed so far
     for (int item_seq = 0;; ++item_seq) {
         int item;
@@ -211,41 +204,34 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             }
         }
 
-        // ---- load this thread's rays: pair r = positions (2r, 2r+1) * kThreads + tid
-        float2 O[3][R2], D[3][R2];
-        uint32_t best[2 * R2];
-        int32_t bidx[2 * R2];
+        // ---- load this thread's rays: ray i = live position base + i * kThreads + tid
+        float O[3][NR], D[3][NR];
+        uint32_t best[NR];
+        int32_t bidx[NR];
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-            float o[2][3], d[2][3];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int p = base + (2 * r + h) * kThreads + tid;
-                if (p < n_live) {
-                    const int slot = live ? live[p] : p;
-                    const float ax = sx[slot], ay = sy[slot], az = sz[slot];
-                    // dir_mode: the last three arrays hold the direction (end - start) itself,
-                    // the form the trace loop keeps between iterations (no cancellation error)
-                    d[h][0] = dir_mode ? ex[slot] : ex[slot] - ax;
-                    d[h][1] = dir_mode ? ey[slot] : ey[slot] - ay;
-                    d[h][2] = dir_mode ? ez[slot] : ez[slot] - az;
-                    // shift the origin by ray_start_eps along the ray:
-                    // t_shifted >= 0 <=> ray_u >= eps
-                    o[h][0] = fmaf(ray_start_eps, d[h][0], ax);
-                    o[h][1] = fmaf(ray_start_eps, d[h][1], ay);
-                    o[h][2] = fmaf(ray_start_eps, d[h][2], az);
-                } else {  // padding lane: zero direction => det == 0 => never a hit
-                    o[h][0] = o[h][1] = o[h][2] = 0.f;
-                    d[h][0] = d[h][1] = d[h][2] = 0.f;
-                }
-                best[2 * r + h] = TFRT_NOHIT_KEY;
-                bidx[2 * r + h] = 0;
+        for (int i = 0; i < NR; ++i) {
+            const int p = base + i * kThreads + tid;
+            if (p < n_live) {
+                const int slot = live ? live[p] : p;
+                const float ax = sx[slot], ay = sy[slot], az = sz[slot];
+                // dir_mode: the last three arrays hold the direction (end - start) itself,
+                // the form the trace loop keeps between iterations (no cancellation error)
+                D[0][i] = dir_mode ? ex[slot] : ex[slot] - ax;
+                D[1][i] = dir_mode ? ey[slot] : ey[slot] - ay;
+                D[2][i] = dir_mode ? ez[slot] : ez[slot] - az;
+                // shift the origin along the ray by the search's start exclusion (in units of
+                // |D|, like ray_u): t_shifted >= 0 <=> ray_u >= start
+                const float start = fmaxf(ray_start_eps, start_floor * rsqrtf(
+                    D[0][i] * D[0][i] + D[1][i] * D[1][i] + D[2][i] * D[2][i]));
+                O[0][i] = fmaf(start, D[0][i], ax);
+                O[1][i] = fmaf(start, D[1][i], ay);
+                O[2][i] = fmaf(start, D[2][i], az);
+            } else {  // padding lane: zero direction => det == 0 => never a hit
+                O[0][i] = O[1][i] = O[2][i] = 0.f;
+                D[0][i] = D[1][i] = D[2][i] = 0.f;
             }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                O[c][r] = f2(o[0][c], o[1][c]);
-                D[c][r] = f2(d[0][c], d[1][c]);
-            }
+            best[i] = TFRT_NOHIT_KEY;
+            bidx[i] = 0;
         }
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -258,30 +244,29 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
             // ray components taking the roles (k, k1, k2) are fixed at compile time.
             auto run_group = [&](auto kc, int j0, int j1) {
                 constexpr int K = decltype(kc)::value, K1 = (K + 1) % 3, K2 = (K + 2) % 3;
-#pragma unroll kUnroll
                 for (int j = j0; j < j1; ++j) {
-                    const float4 q0 = tile[j * 3 + 0];
-                    const float4 q1 = tile[j * 3 + 1];
-                    const float4 q2 = tile[j * 3 + 2];
-                    // broadcast operands (SASS: R.F32): one register feeds both rays of a pair
-                    const float2 m1 = f2(q0.x, q0.x), m2 = f2(q0.y, q0.y), dd = f2(q0.z, q0.z);
-                    const float2 s1 = f2(q1.x, q1.x), s2 = f2(q1.y, q1.y), s0 = f2(q1.z, q1.z);
-                    const float2 e1 = f2(q2.x, q2.x), e2 = f2(q2.y, q2.y), e0 = f2(q2.z, q2.z);
-                    float2 tt[R2], xx[R2], dets[R2];
-                    bool cand = false;
+                    // one pair record = six float4 (layout: common.cuh); .x / .y halves of every
+                    // float2 below belong to the pair's first / second triangle
+                    const float4 c0 = tile[j * 6 + 0], c1 = tile[j * 6 + 1], c2 = tile[j * 6 + 2];
+                    const float4 c3 = tile[j * 6 + 3], c4 = tile[j * 6 + 4];
+                    const float2 m1 = f2(c0.x, c0.y), m2 = f2(c0.z, c0.w), dd = f2(c1.x, c1.y);
+                    const float2 s1 = f2(c1.z, c1.w), s2 = f2(c2.x, c2.y), s0 = f2(c2.z, c2.w);
+                    const float2 e1 = f2(c3.x, c3.y), e2 = f2(c3.z, c3.w), e0 = f2(c4.x, c4.y);
+                    float2 tt[NR], xx[NR];
+                    float xmin = __int_as_float(0x7f800000);
 #pragma unroll
-                    for (int r = 0; r < R2; ++r) {
-                        float2 det = k_fma2(m1, D[K1][r], D[K][r]);
-                        det = k_fma2(m2, D[K2][r], det);
-                        float2 tq = k_add2(dd, neg2(O[K][r]));
-                        tq = k_fma2(neg2(m1), O[K1][r], tq);
-                        tq = k_fma2(neg2(m2), O[K2][r], tq);
+                    for (int i = 0; i < NR; ++i) {
+                        float2 det = k_fma2(m1, bc(D[K1][i]), bc(D[K][i]));
+                        det = k_fma2(m2, bc(D[K2][i]), det);
+                        float2 tq = k_add2(dd, bc(-O[K][i]));
+                        tq = k_fma2(neg2(m1), bc(O[K1][i]), tq);
+                        tq = k_fma2(neg2(m2), bc(O[K2][i]), tq);
                         float2 inv;
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(det.x));
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(det.y));
                         const float2 t = k_mul2(tq, inv);
-                        const float2 p1 = k_fma2(t, D[K1][r], O[K1][r]);
-                        const float2 p2 = k_fma2(t, D[K2][r], O[K2][r]);
+                        const float2 p1 = k_fma2(t, bc(D[K1][i]), bc(O[K1][i]));
+                        const float2 p2 = k_fma2(t, bc(D[K2][i]), bc(O[K2][i]));
                         // S = 2(u+v) - C and E = u - v straight from their own planes; then
                         //   x = |E| + |S - |E||  <=  C   <=>   u >= 0, v >= 0, u + v <= C
                         // (min(u,v) = (u+v-|u-v|)/2 and min(p,q) >= 0 <=> p+q >= |p-q|, twice);
@@ -293,48 +278,55 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                         const float2 ea = abs2(ev);
                         const float2 kk = k_add2(sv, neg2(ea));
                         const float2 x = k_add2(ea, abs2(kk));
-                        // valid & nearer <=> bits(x) <= bits(C) and bits(t) < best as unsigned
-                        // integers (negative t, NaN and +inf all compare high)
-                        cand |= (__float_as_uint(x.x) <= c_bits && __float_as_uint(t.x) < best[2 * r]) |
-                                (__float_as_uint(x.y) <= c_bits && __float_as_uint(t.y) < best[2 * r + 1]);
-                        tt[r] = t;
-                        xx[r] = x;
-                        dets[r] = det;
+                        // x >= 0 or NaN (fminf drops a NaN operand): the smallest x decides
+                        // whether any of the thread's rays is inside one of the two triangles
+                        xmin = fminf(fminf(xmin, x.x), x.y);             // one FMNMX3
+                        tt[i] = t;
+                        xx[i] = x;
                     }
-                    // Rare path (a few hits per ray over the whole mesh): warp-uniform branch so
-                    // the common case pays one vote instead of predicated selects per test.
-                    if (__any_sync(0xffffffffu, cand)) {
-                        const int tri = __float_as_int(q0.w);
-                        // |det * n[k]| >= intersect_eps is the reference's safe-denominator
-                        // validity (tfrt/geometry.py:306)
-                        const float nk = q1.w;
-                        // the conditions are re-evaluated from an opaque copy of C, so that the
-                        // common path does not have to keep eight per-ray predicates alive
+                    // Rare path (a few inside hits per ray over the whole mesh): warp-uniform
+                    // branch, so the common case pays the min chain, one compare and one vote per
+                    // (NR rays x 2 triangles).
+                    if (__any_sync(0xffffffffu, xmin <= w_one)) {
+                        const float4 c5 = tile[j * 6 + 5];
                         uint32_t c_rare = c_bits;
                         asm volatile("" : "+r"(c_rare));
 #pragma unroll
-                        for (int r = 0; r < R2; ++r) {
-                            if (__float_as_uint(xx[r].x) <= c_rare &&
-                                __float_as_uint(tt[r].x) < best[2 * r] &&
-                                fabsf(dets[r].x * nk) >= intersect_eps) {
-                                best[2 * r] = __float_as_uint(tt[r].x);
-                                bidx[2 * r] = tri;
-                            }
-                            if (__float_as_uint(xx[r].y) <= c_rare &&
-                                __float_as_uint(tt[r].y) < best[2 * r + 1] &&
-                                fabsf(dets[r].y * nk) >= intersect_eps) {
-                                best[2 * r + 1] = __float_as_uint(tt[r].y);
-                                bidx[2 * r + 1] = tri;
+                        for (int h = 0; h < 2; ++h) {
+                            const int tri = __float_as_int(h ? c4.w : c4.z);
+                            // |det * n[k]| >= intersect_eps is the reference's safe-denominator
+                            // validity (tfrt/geometry.py:306)
+                            const float nk = h ? c5.y : c5.x;
+                            const float m1h = h ? m1.y : m1.x, m2h = h ? m2.y : m2.x;
+#pragma unroll
+                            for (int i = 0; i < NR; ++i) {
+                                const float det = fmaf(m2h, D[K2][i], fmaf(m1h, D[K1][i], D[K][i]));
+                                // nearer, or equally near with a lower index: the winner is the
+                                // lexicographic minimum of (bits(t), index) whatever the scan
+                                // order (negative t, NaN and +inf compare high as unsigned)
+                                const uint32_t tb = __float_as_uint(h ? tt[i].y : tt[i].x);
+                                const uint32_t xb = __float_as_uint(h ? xx[i].y : xx[i].x);
+                                const bool ok = (xb <= c_rare) &
+                                                ((tb < best[i]) | ((tb == best[i]) & (tri < bidx[i]))) &
+                                                (tb < TFRT_NOHIT_KEY) &
+                                                (fabsf(det * nk) >= intersect_eps);
+                                best[i] = ok ? tb : best[i];
+                                bidx[i] = ok ? tri : bidx[i];
                             }
                         }
                     }
+                    // keeps the loop test below the rare-path branch (otherwise ptxas hoists it
+                    // above and parks the predicate in a general register)
+                    asm volatile("" : "+r"(j));
                 }
             };
-            const int header = __float_as_int(tile[2].w);
-            const int c0 = header & 0xffff, c1 = c0 + (header >> 16);
-            run_group(std::integral_constant<int, 0>{}, 0, c0);
-            run_group(std::integral_constant<int, 1>{}, c0, c1);
-            run_group(std::integral_constant<int, 2>{}, c1, TFRT_TILE_TRIS);
+            // pairs per axis group of this tile (record 0 carries them)
+            const int header = __float_as_int(tile[5].z);
+            const int n0 = header & 0xff, n1 = n0 + ((header >> 8) & 0xff);
+            const int n2 = n1 + ((header >> 16) & 0xff);
+            run_group(std::integral_constant<int, 0>{}, 0, n0);
+            run_group(std::integral_constant<int, 1>{}, n0, n1);
+            run_group(std::integral_constant<int, 2>{}, n1, n2);
 
             // release the stage; the producer keeps the stream kStages tiles ahead
             __syncwarp();
@@ -350,59 +342,100 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
 
         // ---- epilogue: (key, index) per live position
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int p = base + (2 * r + h) * kThreads + tid;
-                if (p < n_live) {
-                    const unsigned long long packed_hit =
-                        ((unsigned long long)best[2 * r + h] << 32) | (uint32_t)bidx[2 * r + h];
-                    if (use_atomic)
-                        atomicMin(&hit[p], packed_hit);
-                    else
-                        hit[p] = packed_hit;
-                }
+        for (int i = 0; i < NR; ++i) {
+            const int p = base + i * kThreads + tid;
+            if (p < n_live) {
+                const unsigned long long packed_hit =
+                    ((unsigned long long)best[i] << 32) | (uint32_t)bidx[i];
+                if (use_atomic)
+                    atomicMin(&hit[p], packed_hit);
+                else
+                    hit[p] = packed_hit;
             }
         }
     }
 }
 
-// Resident CTAs per SM of the three ray-count variants {R2 = 4, 2, 1}, asked from the runtime once
-// (the persistent grid is sized from it).
-const int *occupancy_table() {
-    static int occ[3] = {0, 0, 0};
-    if (!occ[0]) {
-        const int smem = (int)sizeof(IntersectSmem);
-        int v[3] = {4, 4, 6};
-        cudaFuncSetAttribute(k_intersect3d<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_intersect3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_intersect3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[0], k_intersect3d<4, false>, kThreads, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[1], k_intersect3d<2, false>, kThreads, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[2], k_intersect3d<1, false>, kThreads, smem);
-        for (int i = 0; i < 3; ++i) occ[i] = v[i] > 0 ? v[i] : 1;
-    }
-    return occ;
+// Per-device launch configuration, initialised once per device under std::call_once: SM count,
+// resident CTAs per SM of the ray-count variants {NR = 8, 4, 2} (the persistent grid is sized from
+// it) and the dynamic shared-memory opt-in of every instantiation.
+struct DeviceConfig {
+    std::once_flag once;
+    cudaError_t status = cudaSuccess;
+    int num_sms = 0;
+    int occ[3] = {1, 1, 1};
+};
+constexpr int kMaxDevices = 64;
+DeviceConfig g_devices[kMaxDevices];
+
+template <int NR, bool Q>
+cudaError_t opt_in_smem() {
+    return cudaFuncSetAttribute(k_intersect3d<NR, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(IntersectSmem));
 }
+
+void init_device(DeviceConfig &cfg, int dev) {
+    cudaError_t e = cudaDeviceGetAttribute(&cfg.num_sms, cudaDevAttrMultiProcessorCount, dev);
+#if TFRT_K1_FORCE_NR
+    if (e == cudaSuccess) e = opt_in_smem<TFRT_K1_FORCE_NR, true>();
+    if (e == cudaSuccess) e = opt_in_smem<TFRT_K1_FORCE_NR, false>();
+#endif
+    if (e == cudaSuccess) e = opt_in_smem<8, true>();
+    if (e == cudaSuccess) e = opt_in_smem<8, false>();
+    if (e == cudaSuccess) e = opt_in_smem<4, true>();
+    if (e == cudaSuccess) e = opt_in_smem<4, false>();
+    if (e == cudaSuccess) e = opt_in_smem<2, true>();
+    if (e == cudaSuccess) e = opt_in_smem<2, false>();
+    const int smem = (int)sizeof(IntersectSmem);
+    int v[3] = {3, 4, 6};
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[0], k_intersect3d<8, false>, kThreads, smem);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[1], k_intersect3d<4, false>, kThreads, smem);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v[2], k_intersect3d<2, false>, kThreads, smem);
+    for (int i = 0; i < 3; ++i) cfg.occ[i] = v[i] > 0 ? v[i] : 1;
+    cfg.status = e;
+}
+
+struct Tunables {
+    int items_lo, items_hi, queue_mode;
+    Tunables() {
+        const char *e = getenv("TFRT_K1_ITEMS_PER_CTA");
+        items_lo = e ? atoi(e) : 8;
+        if (items_lo < 1) items_lo = 1;
+        items_hi = e ? items_lo : 64;
+        const char *q = getenv("TFRT_K1_QUEUE");     // 0 = never, 1 = auto (default), 2 = always
+        queue_mode = q ? atoi(q) : 1;
+    }
+};
 
 }  // namespace
 
 // host launcher -------------------------------------------------------------------------------
 // n_upper: upper bound of the live count (grid size); the kernel reads the exact count from
-// n_live_ptr when given.
+// n_live_ptr when given.  Contract (all in stream order): *work_counter == 0 and
+// hit[0 .. n_upper) == ~0 on entry; the launcher itself enqueues nothing but the kernel and keeps
+// no state between calls (the caller owns the counter word, so any number of launches may be in
+// flight on any number of streams).
 int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
                             const int32_t *n_live_ptr, int n_upper, const float *packed,
                             int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
-                            uint64_t *hit, int dir_mode, cudaStream_t stream) {
+                            uint64_t *hit, int dir_mode, unsigned int *work_counter,
+                            float start_floor_ulps, cudaStream_t stream) {
     if (n_upper <= 0 || n_tri <= 0) return 0;
+    TFRT_REQUIRE(work_counter && hit, "tfrt_launch_intersect3d: null workspace");
     const int n_tiles = tfrt_div_up(n_tri, TFRT_TILE_TRIS);
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        TFRT_CHECK_CUDA(cudaGetDevice(&dev));
-        TFRT_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    // Work decomposition.  Items = ray blocks (kThreads * 2*R2 rays) x triangle splits, handed
+    int cur_dev = 0;
+    TFRT_CHECK_CUDA(cudaGetDevice(&cur_dev));
+    TFRT_REQUIRE(cur_dev >= 0 && cur_dev < kMaxDevices, "tfrt_launch_intersect3d: device index %d",
+                 cur_dev);
+    DeviceConfig &cfg = g_devices[cur_dev];
+    std::call_once(cfg.once, init_device, std::ref(cfg), cur_dev);
+    TFRT_CHECK_CUDA(cfg.status);
+    static const Tunables tun;                       // thread-safe (C++11 magic static), read-only
+    const int num_sms = cfg.num_sms;
+    // Work decomposition.  Items = ray blocks (kThreads * NR rays) x triangle splits, handed
     // out dynamically to persistent CTAs, so the idle tail of a launch is about half an item per
     // CTA.  Long items are cheap to cut (an item's fixed cost -- ray gather, ring prologue,
     // 64-bit atomicMin merge -- is a few microseconds): aim for up to 64 items per resident CTA
@@ -410,98 +443,64 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
     // (measured flat between 4 and 16 items per CTA at 5-tile items, profiles/r1_k1_tuning.md).
     // Prefer 8 rays per thread (one LDS.128 feeds 8 rays); fall back to 4 / 2 rays per thread
     // and finer splits only when the ray count cannot fill the machine otherwise.
-    int r2 = 1, splits = 1;
+    int nr = 2, splits = 1;
     {
-        const int cand_r2[3] = {4, 2, 1};
-        const int *occ = occupancy_table();           // resident CTAs per SM (registers / smem)
-        static int items_lo = 0, items_hi = 0;
-        if (!items_lo) {
-            const char *e = getenv("TFRT_K1_ITEMS_PER_CTA");
-            items_lo = e ? atoi(e) : 8;
-            if (items_lo < 1) items_lo = 1;
-            items_hi = e ? items_lo : 64;
-        }
+        const int cand_nr[3] = {8, 4, 2};
         bool done = false;
         for (int min_tps = 4; min_tps >= 1 && !done; min_tps >>= 1) {   // small meshes: finer splits
             for (int c = 0; c < 3 && !done; ++c) {
-                const long long rb = tfrt_div_up(n_upper, kThreads * 2 * cand_r2[c]);
-                const long long resident = (long long)num_sms * occ[c];
+                const long long rb = tfrt_div_up(n_upper, kThreads * cand_nr[c]);
+                const long long resident = (long long)num_sms * cfg.occ[c];
                 const long long cap_lo = n_tiles / min_tps > 0 ? n_tiles / min_tps : 1;
                 const long long cap_hi = n_tiles / (4 * min_tps) > 0 ? n_tiles / (4 * min_tps) : 1;
-                long long sp_hi = (items_hi * resident + rb - 1) / rb;
-                long long sp_lo = (items_lo * resident + rb - 1) / rb;
+                long long sp_hi = (tun.items_hi * resident + rb - 1) / rb;
+                long long sp_lo = (tun.items_lo * resident + rb - 1) / rb;
                 if (sp_hi > cap_hi) sp_hi = cap_hi;
                 if (sp_lo > cap_lo) sp_lo = cap_lo;
                 long long sp = sp_hi > sp_lo ? sp_hi : sp_lo;
                 if (sp < 1) sp = 1;
-                r2 = cand_r2[c];
+                nr = cand_nr[c];
                 splits = (int)sp;
                 done = rb * sp >= 2 * resident;       // enough items to fill and balance
             }
         }
     }
-#if TFRT_K1_FORCE_R2
-    r2 = TFRT_K1_FORCE_R2;
+#if TFRT_K1_FORCE_NR
+    nr = TFRT_K1_FORCE_NR;
 #endif
-    const int ray_blocks = tfrt_div_up(n_upper, kThreads * 2 * r2);
+    const int ray_blocks = tfrt_div_up(n_upper, kThreads * nr);
     const int tiles_per_split = tfrt_div_up(n_tiles, splits);
     splits = tfrt_div_up(n_tiles, tiles_per_split);
     const int use_atomic = splits > 1;
-    if (use_atomic)
-        TFRT_CHECK_CUDA(cudaMemsetAsync(hit, 0xff, (size_t)n_upper * sizeof(uint64_t), stream));
-
-    // work counter of this launch: a rotating slot of a small device array, zeroed in stream
-    // order (launches of one stream never overlap; 64 slots cover concurrent streams)
-    static unsigned int *counters_of_device[64] = {nullptr};
-    static std::atomic<unsigned int> launch_seq{0};
-    int cur_dev = 0;
-    TFRT_CHECK_CUDA(cudaGetDevice(&cur_dev));
-    TFRT_REQUIRE(cur_dev >= 0 && cur_dev < 64, "tfrt_launch_intersect3d: device index %d", cur_dev);
-    if (!counters_of_device[cur_dev])
-        TFRT_CHECK_CUDA(cudaMalloc(&counters_of_device[cur_dev], 64 * sizeof(unsigned int)));
-    unsigned int *counter = counters_of_device[cur_dev] + (launch_seq.fetch_add(1) % 64u);
-    TFRT_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
 
     const size_t smem = sizeof(IntersectSmem);
-    const int occ_r2 = occupancy_table()[r2 >= 4 ? 0 : (r2 == 2 ? 1 : 2)];
+    const int occ_nr = cfg.occ[nr >= 8 ? 0 : (nr == 4 ? 1 : 2)];
     const long long total_upper = (long long)ray_blocks * splits;
-    const long long resident = (long long)num_sms * occ_r2;
+    const long long resident = (long long)num_sms * occ_nr;
     dim3 grid((unsigned)(total_upper < resident ? total_upper : resident)), block(kThreads);
     // Barrier-free item crossing pays for itself on long, heavy items (8 rays per thread, >= 4
     // tiles: +1 % at 16 M rays x 99 k triangles, +4 % at 1 M x 20 k, +8 % at 1 M x 2 k); launches
     // made of short items keep the one-item-at-a-time loop (profiles/r1_k1_tuning.md section 5).
-    static int queue_mode = -1;
-    if (queue_mode < 0) {
-        const char *e = getenv("TFRT_K1_QUEUE");     // 0 = never, 1 = auto (default), 2 = always
-        queue_mode = e ? atoi(e) : 1;
-    }
-    const bool use_queue = queue_mode == 2 || (queue_mode == 1 && r2 == 4 && tiles_per_split >= 4);
-#define TFRT_LAUNCH(R2, Q)                                                                      \
-    do {                                                                                        \
-        static bool attr_set = false;                                                           \
-        if (!attr_set) {                                                                        \
-            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_intersect3d<R2, Q>,                          \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                                 (int)smem));                                   \
-            attr_set = true;                                                                    \
-        }                                                                                       \
-        k_intersect3d<R2, Q><<<grid, block, smem, stream>>>(                                    \
-            ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,          \
-            reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, splits,         \
-            intersect_eps, ray_start_eps, 1.0f + 3.0f * size_eps,                               \
-            reinterpret_cast<unsigned long long *>(hit), use_atomic, dir_mode, counter);        \
-    } while (0)
+    const bool use_queue =
+        tun.queue_mode == 2 || (tun.queue_mode == 1 && nr == 8 && tiles_per_split >= 4);
+#define TFRT_LAUNCH(NR, Q)                                                                      \
+    k_intersect3d<NR, Q><<<grid, block, smem, stream>>>(                                        \
+        ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], live, n_live_ptr, n_upper,              \
+        reinterpret_cast<const float4 *>(packed), n_tiles, tiles_per_split, splits,             \
+        intersect_eps, ray_start_eps, 1.0f + 3.0f * size_eps,                                   \
+        reinterpret_cast<unsigned long long *>(hit), use_atomic, dir_mode, work_counter,        \
+        start_floor_ulps)
     const bool timed = tfrt_profile_begin(stream);
-#if TFRT_K1_FORCE_R2
-    if (use_queue) TFRT_LAUNCH(TFRT_K1_FORCE_R2, true);
-    else TFRT_LAUNCH(TFRT_K1_FORCE_R2, false);
+#if TFRT_K1_FORCE_NR
+    if (use_queue) TFRT_LAUNCH(TFRT_K1_FORCE_NR, true);
+    else TFRT_LAUNCH(TFRT_K1_FORCE_NR, false);
 #else
-    if (r2 == 4 && use_queue) TFRT_LAUNCH(4, true);
-    else if (r2 == 4) TFRT_LAUNCH(4, false);
-    else if (r2 == 2 && use_queue) TFRT_LAUNCH(2, true);
-    else if (r2 == 2) TFRT_LAUNCH(2, false);
-    else if (use_queue) TFRT_LAUNCH(1, true);
-    else TFRT_LAUNCH(1, false);
+    if (nr == 8 && use_queue) TFRT_LAUNCH(8, true);
+    else if (nr == 8) TFRT_LAUNCH(8, false);
+    else if (nr == 4 && use_queue) TFRT_LAUNCH(4, true);
+    else if (nr == 4) TFRT_LAUNCH(4, false);
+    else if (use_queue) TFRT_LAUNCH(2, true);
+    else TFRT_LAUNCH(2, false);
 #endif
 #undef TFRT_LAUNCH
     if (timed) tfrt_profile_end(stream);

@@ -4,31 +4,38 @@
 
 namespace {
 
-// One CTA per tile of TFRT_TILE_TRIS triangles, one thread per (padded) triangle: computes the
-// projected 12-float record described in common.cuh and writes it at its position in the tile's
-// stable partition by dominant axis (k = 0 first, then 1, then 2; index order inside a group).
-// Record 0 of the tile carries the group sizes.
+// One CTA per tile of TFRT_TILE_TRIS triangles, one thread per triangle: computes the projected
+// coefficients described in common.cuh and writes them into the tile's pair records, at the
+// triangle's position in the tile's stable partition by dominant axis (k = 0 first, then 1, then
+// 2; index order inside a group).  Odd groups are completed with a never-hit half, unused pair
+// slots are filled with never-hit pairs; record 0 of the tile carries the pairs per group.
 __global__ void __launch_bounds__(TFRT_TILE_TRIS)
 k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
                  const float *__restrict__ zp, const float *__restrict__ x1,
                  const float *__restrict__ y1, const float *__restrict__ z1,
                  const float *__restrict__ x2, const float *__restrict__ y2,
-                 const float *__restrict__ z2, int n_tri, float size_eps,
-                 float4 *__restrict__ packed) {
+                 const float *__restrict__ z2, int n_tri, float size_eps, float margin_ulps,
+                 float *__restrict__ packed) {
     __shared__ int s_cnt[3][TFRT_TILE_TRIS / 32];
+    __shared__ float s_scale[TFRT_TILE_TRIS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i = blockIdx.x * TFRT_TILE_TRIS + threadIdx.x;
-    // never-hit record (padding, degenerate triangles): S = 4, E = 0 => x = 4 > C => never valid
+    const bool real = i < n_tri;
+    float scale = 0.f;     // largest |coordinate| of this thread's triangle
+    // never-hit coefficients (padding, degenerate triangles): S = 4, E = 0 => x = 4 > C
     int k = 0;
     float n1 = 0.f, n2 = 0.f, dd = 0.f, nk = 0.f;
     float au1 = 0.f, au2 = 0.f, au0 = 4.f, bv1 = 0.f, bv2 = 0.f, bv0 = 0.f;
-    if (i < n_tri) {
+    if (real) {
         const double A[3] = {xp[i], yp[i], zp[i]};
         const double e1[3] = {x1[i] - A[0], y1[i] - A[1], z1[i] - A[2]};
         const double e2[3] = {x2[i] - A[0], y2[i] - A[1], z2[i] - A[2]};
         const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
                              e1[0] * e2[1] - e1[1] * e2[0]};
         const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+        for (int c = 0; c < 3; ++c)
+            scale = fmaxf(scale, (float)fmax(fabs(A[c]), fmax(fabs(A[c] + e1[c]), fabs(A[c] + e2[c]))));
+        if (!isfinite(scale)) scale = 0.f;
         if (nn > 0.0 && isfinite(nn)) {
             const double inv = 1.0 / nn;
             // a = (e2 x N)/|N|^2 : u = a.(P-A);  b = (N x e1)/|N|^2 : v = b.(P-A)
@@ -38,8 +45,13 @@ k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
             const double bv[3] = {(N[1] * e1[2] - N[2] * e1[1]) * inv,
                                   (N[2] * e1[0] - N[0] * e1[2]) * inv,
                                   (N[0] * e1[1] - N[1] * e1[0]) * inv};
-            const double ad = -(av[0] * A[0] + av[1] * A[1] + av[2] * A[2]) + (double)size_eps;
-            const double bd = -(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + (double)size_eps;
+            // inflation of this triangle in the search: the reference's size_epsilion plus the
+            // fp32 search margin (common.cuh); the fp64 evaluation of the winner applies the
+            // exact rule afterwards
+            const double eps_t = (double)size_eps +
+                                 fmin(tfrt_tri_margin(A, e1, e2, (double)margin_ulps), 0.25);
+            const double ad = -(av[0] * A[0] + av[1] * A[1] + av[2] * A[2]) + eps_t;
+            const double bd = -(bv[0] * A[0] + bv[1] * A[1] + bv[2] * A[2]) + eps_t;
             // dominant axis of the normal; plane scaled so that its k-coefficient is 1:
             //   P[k] = dd - m1 P[k1] - m2 P[k2]  for every P on the plane
             k = fabs(N[1]) > fabs(N[0]) ? 1 : 0;
@@ -51,20 +63,26 @@ k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
             // u = a.P + ad with P[k] eliminated (exact on the plane)
             const double u1 = av[k1] - av[k] * m1, u2 = av[k2] - av[k] * m2, u0 = ad + av[k] * dk;
             const double v1 = bv[k1] - bv[k] * m1, v2 = bv[k2] - bv[k] * m2, v0 = bd + bv[k] * dk;
-            // the kernel tests the planes S = 2(u+v) - C and E = u - v (see intersect3d.cu)
-            const double C = 1.0 + 3.0 * (double)size_eps;
-            au1 = (float)(2.0 * (u1 + v1)); au2 = (float)(2.0 * (u2 + v2));
-            au0 = (float)(2.0 * (u0 + v0) - C);
-            bv1 = (float)(u1 - v1); bv2 = (float)(u2 - v2); bv0 = (float)(u0 - v0);
+            // the kernel tests the planes S = 2(u+v) - C_t and E = u - v (see intersect3d.cu)
+            // against x = |E| + |S - |E|| <= C_t with C_t = 1 + 3 eps_t; x is homogeneous of
+            // degree one in (S, E), so both planes are scaled by C / C_t and the kernel compares
+            // every triangle with the one constant C = 1 + 3 size_eps
+            const double Ct = 1.0 + 3.0 * eps_t;
+            const double rho = (1.0 + 3.0 * (double)size_eps) / Ct;
+            au1 = (float)(rho * 2.0 * (u1 + v1)); au2 = (float)(rho * 2.0 * (u2 + v2));
+            au0 = (float)(rho * (2.0 * (u0 + v0) - Ct));
+            bv1 = (float)(rho * (u1 - v1)); bv2 = (float)(rho * (u2 - v2));
+            bv0 = (float)(rho * (u0 - v0));
         }
     }
-    // stable partition by k inside the tile
+    // stable partition by k inside the tile (padding threads take part in no group)
+    const int kk = real ? k : 3;
     int rank_in_warp = 0;
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
-        const unsigned m = __ballot_sync(0xffffffffu, k == g);
+        const unsigned m = __ballot_sync(0xffffffffu, kk == g);
         if (lane == 0) s_cnt[g][wid] = __popc(m);
-        if (k == g) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+        if (kk == g) rank_in_warp = __popc(m & ((1u << lane) - 1u));
     }
     __syncthreads();
     int total[3] = {0, 0, 0}, before = 0;
@@ -73,16 +91,52 @@ k_pack_triangles(const float *__restrict__ xp, const float *__restrict__ yp,
 #pragma unroll
         for (int w = 0; w < TFRT_TILE_TRIS / 32; ++w) {
             const int c = s_cnt[g][w];
-            if (g == k && w < wid) before += c;
+            if (g == kk && w < wid) before += c;
             total[g] += c;
         }
     }
-    const int pos = (k == 0 ? 0 : (k == 1 ? total[0] : total[0] + total[1])) + before + rank_in_warp;
-    float4 *o = packed + ((size_t)blockIdx.x * TFRT_TILE_TRIS + pos) * 3;
-    o[0] = make_float4(n1, n2, dd, __int_as_float(i));
-    o[1] = make_float4(au1, au2, au0, nk);
-    // group sizes of the tile ride in record 0 (k = 0 group size | k = 1 group size << 16)
-    o[2] = make_float4(bv1, bv2, bv0, __int_as_float(pos == 0 ? (total[0] | (total[1] << 16)) : 0));
+    const int pairs[3] = {(total[0] + 1) / 2, (total[1] + 1) / 2, (total[2] + 1) / 2};
+    const int n_pairs = pairs[0] + pairs[1] + pairs[2];
+    float *tile = packed + (size_t)blockIdx.x * TFRT_TILE_PAIRS * 24;
+    // writes one half (h = 0 / 1) of pair record `pair`
+    auto put = [&](int pair, int h, float m1_, float m2_, float dd_, float s1_, float s2_,
+                   float s0_, float e1_, float e2_, float e0_, float idx_, float nk_) {
+        float *r = tile + (size_t)pair * 24 + h;
+        r[0] = m1_;  r[2] = m2_;
+        r[4] = dd_;  r[6] = s1_;
+        r[8] = s2_;  r[10] = s0_;
+        r[12] = e1_; r[14] = e2_;
+        r[16] = e0_; r[18] = idx_;
+        r[20] = nk_;
+    };
+    if (real) {
+        const int rank = before + rank_in_warp;
+        const int pair = (k == 0 ? 0 : (k == 1 ? pairs[0] : pairs[0] + pairs[1])) + rank / 2;
+        put(pair, rank & 1, n1, n2, dd, au1, au2, au0, bv1, bv2, bv0, __int_as_float(i), nk);
+        // the last triangle of an odd group completes its pair with a never-hit half
+        if ((rank & 1) == 0 && rank == total[k] - 1)
+            put(pair, 1, 0.f, 0.f, 0.f, 0.f, 0.f, 4.f, 0.f, 0.f, 0.f, __int_as_float(i), 0.f);
+    }
+    // unused pair slots (never visited by the kernel: the header bounds the loops) stay defined
+    for (int pslot = n_pairs + threadIdx.x; pslot < TFRT_TILE_PAIRS; pslot += TFRT_TILE_TRIS)
+        for (int h = 0; h < 2; ++h)
+            put(pslot, h, 0.f, 0.f, 0.f, 0.f, 0.f, 4.f, 0.f, 0.f, 0.f, __int_as_float(0), 0.f);
+    __syncthreads();   // the header and the pad word go in after the records
+    // word 23 of the very first record carries the scene scale (largest |coordinate| of the
+    // mesh, zeroed by the host before this launch): the search derives its ray-start floor from it
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) scale = fmaxf(scale, __shfl_xor_sync(0xffffffffu, scale, off));
+    if (lane == 0) s_scale[wid] = scale;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TFRT_TILE_TRIS / 32; ++w) scale = fmaxf(scale, s_scale[w]);
+        atomicMax(reinterpret_cast<unsigned int *>(packed + 23), __float_as_uint(scale));
+    }
+    if (threadIdx.x < TFRT_TILE_PAIRS && !(blockIdx.x == 0 && threadIdx.x == 0))
+        tile[(size_t)threadIdx.x * 24 + 23] = 0.f;
+    if (threadIdx.x < TFRT_TILE_PAIRS)
+        tile[(size_t)threadIdx.x * 24 + 22] =
+            __int_as_float(threadIdx.x == 0 ? (pairs[0] | (pairs[1] << 8) | (pairs[2] << 16)) : 0);
 }
 
 // K3 forward: gather face corners, unit normal normalize((p2-p1) x (p3-p2))
@@ -166,16 +220,17 @@ __global__ void k_faces_backward(const float *__restrict__ vertices,
 
 extern "C" size_t tfrt_packed_floats(int32_t n_tri) {
     const size_t tiles = (size_t)tfrt_div_up(n_tri > 0 ? n_tri : 1, TFRT_TILE_TRIS);
-    return tiles * TFRT_TILE_TRIS * TFRT_TRI_FLOATS;
+    return tiles * TFRT_TILE_PAIRS * 2 * TFRT_TRI_FLOATS;
 }
 
 extern "C" int tfrt_pack_triangles(const float *const tri[9], int32_t n_tri, float size_eps,
-                                   float *packed, void *stream) {
-    TFRT_REQUIRE(n_tri >= 0 && packed, "tfrt_pack_triangles: bad arguments");
+                                   float margin_ulps, float *packed, void *stream) {
+    TFRT_REQUIRE(n_tri >= 0 && packed && margin_ulps >= 0.f, "tfrt_pack_triangles: bad arguments");
     if (n_tri == 0) return 0;
+    TFRT_CHECK_CUDA(cudaMemsetAsync(packed + 23, 0, sizeof(float), (cudaStream_t)stream));
     k_pack_triangles<<<tfrt_div_up(n_tri, TFRT_TILE_TRIS), TFRT_TILE_TRIS, 0, (cudaStream_t)stream>>>(
         tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], n_tri, size_eps,
-        reinterpret_cast<float4 *>(packed));
+        margin_ulps, packed);
     tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -22,7 +22,9 @@ import torch
 
 from . import geometry, kernels
 from . import operation as op
-from .autograd import TraceFunction, TracePlan
+import weakref
+
+from .autograd import TraceFunction, TracePlan, WorkspaceLease, run_trace
 from .materials import descriptor_of
 from .update import RecursivelyUpdatable
 
@@ -109,16 +111,21 @@ class OpticalSystemBase(RecursivelyUpdatable):
     """Holds sources, boundaries and materials (tfrt/engine.py:146-250).
 
     intersect_epsilion / size_epsilion / ray_start_epsilion have the reference's meaning
-    (tfrt/engine.py:160-179).  Their defaults here are fp32-appropriate (the reference's 1e-10
-    is below fp32 resolution at unit scale): 1e-10 on |det|, 1e-5 edge
-    inflation, 1e-4 ray-start exclusion.
+    (tfrt/engine.py:160-179) and are applied exactly, in fp64, to the hit the fp32 search
+    proposes: the search itself runs with scale-aware allowances on top of them
+    (`search_margin_ulps` units in the last place of the triangle coordinates on the edge
+    inflation, 4x that on the ray-start exclusion), and a proposal the exact rule rejects is
+    searched again in fp64.  So any values work, including the reference's
+    1e-10 defaults and scenes in millimetres or far from the origin; the defaults here (1e-10
+    on |det|, 1e-5 edge inflation, 1e-4 ray-start exclusion) keep the exact re-searches rare.
 
     ray_shard : None or (rank, world_size).  When set, `update()` keeps only this rank's
     contiguous block of the amalgamated source rays (multi-GPU ray sharding, parallel.py).
     """
 
     def __init__(self, manual_update_management=False, intersect_epsilion=1e-10,
-                 size_epsilion=1e-5, ray_start_epsilion=1e-4, ray_shard=None, **kwargs):
+                 size_epsilion=1e-5, ray_start_epsilion=1e-4, ray_shard=None,
+                 search_margin_ulps=kernels.DEFAULT_MARGIN_ULPS, **kwargs):
         self._sources = []
         self._read_only_sources = None
         self.source_handles = []
@@ -128,6 +135,7 @@ class OpticalSystemBase(RecursivelyUpdatable):
         self.intersect_epsilion = intersect_epsilion
         self.size_epsilion = size_epsilion
         self.ray_start_epsilion = ray_start_epsilion
+        self.search_margin_ulps = float(search_margin_ulps)
         self.ray_shard = ray_shard
         self.projection_results = {}
         super().__init__(**kwargs)
@@ -175,6 +183,21 @@ class OpticalSystemBase(RecursivelyUpdatable):
                 lo, hi = shard_range(n, *self.ray_shard)
                 merged = {k: v[lo:hi] for k, v in merged.items()}
             self._amalgamated_sources = merged
+        self._source_rows = None
+
+    def source_rows(self):
+        """The amalgamated 3D source rays as one (7,N) fp32 block [x_start .. z_end, wavelength]
+        (the layout the trace kernels read), built once per update()."""
+        rows = getattr(self, "_source_rows", None)
+        if rows is None:
+            f = self._amalgamated_sources
+            n = f["x_start"].shape[0]
+            cols = [f[k] for k in RAY_FIELDS_3D]
+            cols.append(f["wavelength"] if "wavelength" in f
+                        else torch.zeros(n, dtype=torch.float32, device=cols[0].device))
+            rows = torch.stack([c.to(torch.float32) for c in cols]).contiguous()
+            self._source_rows = rows
+        return rows
 
     def material_table(self, device):
         """Device table of kernel material descriptors for `self.materials` (cached)."""
@@ -182,6 +205,26 @@ class OpticalSystemBase(RecursivelyUpdatable):
             self._material_table = kernels.material_table(
                 [descriptor_of(m) for m in self._materials], device)
         return self._material_table
+
+    def materials_have_descriptors(self):
+        """Every entry of `materials` is a closed-form tensorflowraytrace_b200.materials.Material
+        (evaluated per ray inside the reaction kernel)."""
+        from .materials import Material
+        return all(isinstance(m["n"] if isinstance(m, dict) else m, Material)
+                   for m in self._materials)
+
+    def material_index_table(self, wavelength):
+        """Refractive indices of ARBITRARY material callables for the fused reaction kernel
+        (tfrt/operation.py:265-267 evaluates any `mat["n"](wavelength)`): every callable is
+        evaluated once, on the device, over the distinct wavelengths of the source set.  Returns
+        (n_table (n_materials, n_lambda) f64, lambda_index (N,) int32)."""
+        distinct, inverse = torch.unique(wavelength, return_inverse=True)
+        rows = []
+        for m in self._materials:
+            fn = m["n"] if isinstance(m, dict) else m
+            n = torch.as_tensor(fn(distinct), device=distinct.device)
+            rows.append(torch.broadcast_to(n.to(torch.float64), distinct.shape))
+        return torch.stack(rows).contiguous(), inverse.to(torch.int32)
 
     def _category_tensor(self, cat, like):
         """Constant int64 category labels, cached per (category, count, device)."""
@@ -298,7 +341,8 @@ class OpticalSystem3D(OpticalSystemBase):
             tri = torch.stack([m[k] for k in TRI_FIELDS]).to(torch.float32).contiguous()
             norm = m["norm"].to(torch.float32).contiguous()
             category = m["catagory"].to(torch.int32).contiguous()
-            packed = kernels.pack_triangles(tri.detach(), self.size_epsilion)
+            packed = kernels.pack_triangles(tri.detach(), self.size_epsilion,
+                                            self.search_margin_ulps)
             self._dev_cache = (tri, norm, category, packed)
         return self._dev_cache
 
@@ -313,13 +357,14 @@ class OpticalSystem3D(OpticalSystemBase):
              result["gather_trig"]) = self._intersection(
                 *[rays[k] for k in RAY_FIELDS_3D], *[self._merged[k] for k in TRI_FIELDS],
                 self.intersect_epsilion, self.size_epsilion, self.ray_start_epsilion,
-                _packed=self.merged_device_arrays()[3])
+                _packed=self.merged_device_arrays()[3], _margin_ulps=self.search_margin_ulps)
             result["norm"] = self._merged["norm"][result["gather_trig"]]
         return result
 
     @staticmethod
     def _intersection(rx1, ry1, rz1, rx2, ry2, rz2, xp, yp, zp, x1, y1, z1, x2, y2, z2,
-                      intersect_epsilion, size_epsilion, ray_start_epsilion, _packed=None):
+                      intersect_epsilion, size_epsilion, ray_start_epsilion, _packed=None,
+                      _margin_ulps=kernels.DEFAULT_MARGIN_ULPS):
         """The intersection seam (tfrt/engine.py:1102-1166): N rays x M triangles -> per-ray
         nearest hit.  The search runs in the CUDA kernel; the gathered values are then
         re-evaluated 1-to-1 in torch so they carry the reference's gradient (through ray_u
@@ -327,16 +372,21 @@ class OpticalSystem3D(OpticalSystemBase):
         rays = torch.stack([rx1, ry1, rz1, rx2, ry2, rz2]).detach()
         tri = torch.stack([xp, yp, zp, x1, y1, z1, x2, y2, z2]).detach()
         if _packed is None:
-            _packed = kernels.pack_triangles(tri, size_epsilion)
+            _packed = kernels.pack_triangles(tri, size_epsilion, _margin_ulps)
         raw = kernels.intersect3d(rays, tri, _packed, intersect_epsilion, size_epsilion,
-                                  ray_start_epsilion)
+                                  ray_start_epsilion, _margin_ulps)
         g = raw["gather_trig"]
+        # the 1-to-1 evaluation runs in fp64 on the fp32 fields, like the kernels' per-ray
+        # arithmetic, and is stored back as fp32
+        f64, f32 = torch.float64, torch.float32
         hit, _, ray_u, trig_u, trig_v = geometry.ray_triangle_hit(
-            torch.stack([rx1, ry1, rz1], 1), torch.stack([rx2, ry2, rz2], 1),
-            torch.stack([xp[g], yp[g], zp[g]], 1), torch.stack([x1[g], y1[g], z1[g]], 1),
-            torch.stack([x2[g], y2[g], z2[g]], 1), intersect_epsilion)
-        return (hit[:, 0], hit[:, 1], hit[:, 2], raw["valid"], ray_u, trig_u, trig_v,
-                raw["gather_ray"], g)
+            torch.stack([rx1, ry1, rz1], 1).to(f64), torch.stack([rx2, ry2, rz2], 1).to(f64),
+            torch.stack([xp[g], yp[g], zp[g]], 1).to(f64),
+            torch.stack([x1[g], y1[g], z1[g]], 1).to(f64),
+            torch.stack([x2[g], y2[g], z2[g]], 1).to(f64), intersect_epsilion)
+        hit = hit.to(f32)
+        return (hit[:, 0], hit[:, 1], hit[:, 2], raw["valid"], ray_u.to(f32), trig_u.to(f32),
+                trig_v.to(f32), raw["gather_ray"], g)
 
 
 class OpticalSystem2D(OpticalSystemBase):
@@ -571,8 +621,11 @@ class OpticalEngine:
         self.clear_ray_history()
         self.last_projection_result = {}
         self.last_trace = None     # kernels.Trace3D of the last fused trace (tape, live counts)
-        self.last_history_slots = {}
-        self.last_history_iterations = {}
+        self._history_slots = {}
+        self._history_iterations = {}
+        self._pending = None       # fused 3D trace enqueued, histories not materialised yet
+        self._workspace = None     # kernels.TraceWorkspace kept from trace to trace
+        self._lease_ref = None     # weak reference to the lease of the workspace's last user
 
         self.input_signature = set()
         self.output_signature = set()
@@ -641,24 +694,32 @@ class OpticalEngine:
         self._optical_system = val
 
     # ------------------------------------------------------------------ histories
+    # The fused 3D trace is enqueued by ray_trace() without waiting for the GPU; the sizes of the
+    # history sets are data dependent, so they are materialised (one wait for the counters, one
+    # small kernel per set, the autograd node) when a history property is first read.
     @property
     def active_rays(self):
+        self._materialise_pending()
         return ReadOnlySet(amalgamate(self._active_rays))
 
     @property
     def finished_rays(self):
+        self._materialise_pending()
         return ReadOnlySet(amalgamate(self._finished_rays))
 
     @property
     def dead_rays(self):
+        self._materialise_pending()
         return ReadOnlySet(amalgamate(self._dead_rays))
 
     @property
     def stopped_rays(self):
+        self._materialise_pending()
         return ReadOnlySet(amalgamate(self._stopped_rays))
 
     @property
     def all_rays(self):
+        self._materialise_pending()
         return ReadOnlySet(amalgamate(
             self._active_rays + self._finished_rays + self._dead_rays + self._stopped_rays))
 
@@ -666,7 +727,28 @@ class OpticalEngine:
     def unfinished_rays(self):
         return self._unfinished_rays
 
+    @property
+    def last_history_slots(self):
+        """Source-ray index of every row of each compiled history set of the last fused trace."""
+        self._materialise_pending()
+        return self._history_slots
+
+    @last_history_slots.setter
+    def last_history_slots(self, val):
+        self._history_slots = val
+
+    @property
+    def last_history_iterations(self):
+        """Iteration at which every row of each compiled history set was produced."""
+        self._materialise_pending()
+        return self._history_iterations
+
+    @last_history_iterations.setter
+    def last_history_iterations(self, val):
+        self._history_iterations = val
+
     def clear_ray_history(self):
+        self._pending = None
         self._active_rays = []
         self._finished_rays = []
         self._stopped_rays = []
@@ -725,11 +807,21 @@ class OpticalEngine:
 
     # ------------------------------------------------------------------ the trace loop
     def _fusable(self):
-        return (self.dimension in (2, 3) and not self.compile_technical_intersections
+        if not (self.dimension in (2, 3) and not self.compile_technical_intersections
                 and not self.compile_geometry_specific_result
                 and any(type(o) is op.StandardReaction for o in self._operations)
                 and all(type(o) in (op.StandardReaction, op.OldestAncestor) and o.active
-                        for o in self._operations))
+                        for o in self._operations)):
+            return False
+        # The 3D reaction kernel takes any {"n": callable} (closed-form materials are evaluated
+        # per ray, other callables through a table over the distinct wavelengths); the 2D kernel
+        # only knows the closed forms, other callables take the projection-at-a-time path.
+        if self.dimension == 2 and self.optical_system is not None:
+            reaction = next(o for o in self._operations if type(o) is op.StandardReaction)
+            if reaction.refractive_index_type == "index" and \
+                    not self.optical_system.materials_have_descriptors():
+                return False
+        return True
 
     def ray_trace(self, max_iterations=25):
         """Trace the optical system (tfrt/engine.py:2311-2330): iterate projection + reaction
@@ -753,6 +845,7 @@ class OpticalEngine:
         self._unfinished_rays = starting_rays
 
     def _ray_trace_fused(self, max_iterations):
+        """Enqueue the whole trace loop on the GPU (asynchronous); see _materialise_pending."""
         system = self.optical_system
         src_fields = system._amalgamated_sources
         if not bool(src_fields) or not bool(system._merged):
@@ -760,18 +853,19 @@ class OpticalEngine:
         reaction = next(o for o in self._operations if type(o) is op.StandardReaction)
         tri, norm, category, packed = system.merged_device_arrays()
         dev = tri.device
-        n = src_fields["x_start"].shape[0]
-        rows = [src_fields[k] for k in RAY_FIELDS_3D]
-        rows.append(src_fields["wavelength"] if "wavelength" in src_fields
-                    else torch.zeros(n, dtype=torch.float32, device=dev))
-        src = torch.stack([r.to(torch.float32) for r in rows]).contiguous()
+        src = system.source_rows()
 
         optical = system._amalgamated_optical
         kw = {}
         if reaction.refractive_index_type == "index":
             none = torch.zeros(0, dtype=torch.int32, device=dev)
             kw.update(mat_in=optical.get("mat_in", none), mat_out=optical.get("mat_out", none),
-                      materials=system.material_table(dev), n_materials=len(system.materials))
+                      n_materials=len(system.materials))
+            if system.materials_have_descriptors():
+                kw.update(materials=system.material_table(dev))
+            else:   # arbitrary callables: tabulated over the distinct wavelengths
+                n_table, lambda_index = system.material_index_table(src[6])
+                kw.update(n_table=n_table, lambda_index=lambda_index)
         else:
             none = torch.zeros(0, dtype=torch.float32, device=dev)
             kw.update(n_in=optical.get("n_in", none), n_out=optical.get("n_out", none))
@@ -788,6 +882,7 @@ class OpticalEngine:
             category=category, n_optical=system._optical_count, max_iterations=max_iterations,
             intersect_eps=system.intersect_epsilion, size_eps=system.size_epsilion,
             ray_start_eps=system.ray_start_epsilion, new_ray_length=self.new_ray_length,
+            margin_ulps=system.search_margin_ulps,
             dead_ray_length=self.dead_ray_length if bool(self.dead_ray_length) else None,
             compile=compile_sets, **kw)
         plan.packed = packed
@@ -801,10 +896,28 @@ class OpticalEngine:
             plan.n_grad_tri = system._optical_count + system._stop_count
         else:
             plan.n_grad_tri = max(system._optical_count, 1)
-        active, stopped, finished, dead = TraceFunction.apply(
-            tri, None if system._norm_is_geometric else norm, src, plan)
-        self.last_trace = plan.trace
 
+        # Reuse the previous trace's workspace (tape + scratch) unless an autograd graph can
+        # still read it: its lease is then still alive, and this trace gets a fresh one.
+        ws = self._workspace
+        if ws is not None and self._lease_ref is not None and self._lease_ref() is not None:
+            ws = None
+        norm_in = None if system._norm_is_geometric else norm
+        tr = run_trace(tri, norm_in, src, plan, workspace=ws)
+        plan.lease = WorkspaceLease(tr.ws)
+        self._workspace, self._lease_ref = tr.ws, weakref.ref(plan.lease)
+        self.last_trace = tr
+        self._pending = (tri, norm_in, src, plan, src_fields)
+        self.last_projection_result = {}
+
+    def _materialise_pending(self):
+        """Build the history sets of the pending fused trace in the reference's order (waits for
+        the trace's counters) and attach them to the autograd graph of the boundary parameters."""
+        if self._pending is None:
+            return
+        tri, norm_in, src, plan, src_fields = self._pending
+        self._pending = None
+        active, stopped, finished, dead = TraceFunction.apply(tri, norm_in, src, plan)
         inherit = [f for f in src_fields if f not in RAY_FIELDS_3D]
 
         def as_set(name, rays):
@@ -820,12 +933,12 @@ class OpticalEngine:
                                   ("finished", finished, self._finished_rays),
                                   ("stopped", stopped, self._stopped_rays),
                                   ("dead", dead, self._dead_rays)):
-            if name in compile_sets:
+            if name in plan.compile:
                 store.append(as_set(name, rays))
         # source-ray index / iteration of every row of each compiled history set
-        self.last_history_slots = dict(plan.slots)
-        self.last_history_iterations = dict(plan.iters)
-        self.last_projection_result = {}
+        self._history_slots = dict(plan.slots)
+        self._history_iterations = dict(plan.iters)
+        plan.lease = None     # from here on only the autograd node (if any) holds the lease
 
     def _ray_trace_fused_2d(self, max_iterations):
         """Whole 2D trace in one kernel launch (K4); histories are gathered from the
@@ -934,7 +1047,7 @@ class OpticalEngine:
                                   torch.cat(acc[name][1]) if acc[name][1] else empty)
 
         inherit = [f for f in src_fields if f not in kernels.RAY_FIELDS_2D]
-        self.last_history_slots, self.last_history_iterations = {}, {}
+        self._history_slots, self._history_iterations = {}, {}
         wanted = [(name, store) for name, flag, store in (
             ("active", self.compile_active_rays, self._active_rays),
             ("finished", self.compile_finished_rays, self._finished_rays),
@@ -957,8 +1070,8 @@ class OpticalEngine:
             for f in inherit:
                 out[f] = inherited[f][off:off + size]
             store.append(out)
-            self.last_history_slots[name] = slot_all[off:off + size]
-            self.last_history_iterations[name] = it_all[off:off + size]
+            self._history_slots[name] = slot_all[off:off + size]
+            self._history_iterations[name] = it_all[off:off + size]
             off += size
         self.last_projection_result = {}
 
@@ -1119,8 +1232,12 @@ class OpticalEngine:
         optical = proj_result["optical"]
         if reaction.refractive_index_type == "index":
             wavelength = rays["wavelength"]
+            if self.dimension == 3:
+                wavelength = wavelength.to(torch.float64)
             n_stack = torch.stack(
-                [(m["n"] if isinstance(m, dict) else m)(wavelength)
+                [torch.broadcast_to(torch.as_tensor(
+                    (m["n"] if isinstance(m, dict) else m)(wavelength),
+                    device=wavelength.device).to(wavelength.dtype), wavelength.shape)
                  for m in self.optical_system.materials])
             idx = torch.arange(wavelength.shape[0], device=wavelength.device)
             n_in = n_stack[optical["mat_in"].long(), idx]
@@ -1134,11 +1251,13 @@ class OpticalEngine:
                 rays["x_start"], rays["y_start"], rays["x_end"], rays["y_end"],
                 optical["norm"], n_in, n_out, self.new_ray_length)
         else:
-            (new_rays["x_start"], new_rays["y_start"], new_rays["z_start"], new_rays["x_end"],
-             new_rays["y_end"], new_rays["z_end"]) = geometry.snells_law_3D(
-                rays["x_start"], rays["y_start"], rays["z_start"], rays["x_end"],
-                rays["y_end"], rays["z_end"], optical["norm"], n_in, n_out,
-                self.new_ray_length)
+            # fp64 arithmetic on the fp32 fields (what the fused reaction kernel does), fp32 out
+            f64 = torch.float64
+            out = geometry.snells_law_3D(
+                *[rays[k].to(f64) for k in RAY_FIELDS_3D], optical["norm"].to(f64),
+                n_in.to(f64), n_out.to(f64), self.new_ray_length)
+            for k, v in zip(RAY_FIELDS_3D, out):
+                new_rays[k] = v.to(torch.float32)
         valid = torch.ones_like(rays["x_end"], dtype=torch.bool)
         return {"active": {"rays": new_rays, "valid": valid}}
 

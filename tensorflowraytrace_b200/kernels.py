@@ -83,27 +83,35 @@ def faces_backward(vertices, faces, update_map, g_tri, g_norm):
     return g_vertices
 
 
-def pack_triangles(tri, size_eps):
-    """tri: (9,T) f32 cuda (rows xp..z2) -> packed plane coefficients for the intersect kernel."""
+DEFAULT_MARGIN_ULPS = 4.0
+
+
+def pack_triangles(tri, size_eps, margin_ulps=DEFAULT_MARGIN_ULPS):
+    """tri: (9,T) f32 cuda (rows xp..z2) -> packed plane coefficients for the intersect kernel.
+    margin_ulps: fp32 search margin (include/tfrt_b200.h); the same value must be given to the
+    calls that use the packed records."""
     _require_cuda(tri)
     tri = _f32(tri)
     T = tri.shape[1]
     lib = _lib.load()
     packed = torch.empty((lib.tfrt_packed_floats(T),), dtype=torch.float32, device=tri.device)
     check(lib.tfrt_pack_triangles(ptr_array([tri[i] for i in range(9)], 9), T,
-                                  ctypes.c_float(size_eps), ptr(packed), _stream()),
+                                  ctypes.c_float(size_eps), ctypes.c_float(margin_ulps),
+                                  ptr(packed), _stream()),
           "tfrt_pack_triangles")
     return packed
 
 
-def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps):
+def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps,
+                margin_ulps=DEFAULT_MARGIN_ULPS, diag=None):
     """b1 seam: nearest valid hit per ray.  rays (6,N) f32, tri (9,T) f32.  Returns a dict with the
-    reference's field names (tfrt/engine.py:1026-1043, without `norm`)."""
+    reference's field names (tfrt/engine.py:1026-1043, without `norm`).  diag: optional (4,) int32
+    cuda tensor receiving the re-validation counters (include/tfrt_b200.h)."""
     _require_cuda(rays, tri, packed)
     rays, tri = _f32(rays), _f32(tri)
     N, T = rays.shape[1], tri.shape[1]
     dev = rays.device
-    hit = torch.empty((max(N, 1),), dtype=torch.int64, device=dev)
+    hit = torch.empty((N + 1,), dtype=torch.int64, device=dev)
     out = {k: torch.empty((N,), dtype=torch.float32, device=dev)
            for k in ("x", "y", "z", "ray_u", "trig_u", "trig_v")}
     valid = torch.empty((N,), dtype=torch.uint8, device=dev)
@@ -111,9 +119,9 @@ def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps):
     check(_lib.load().tfrt_intersect3d(
         ptr_array([rays[i] for i in range(6)], 6), N, ptr_array([tri[i] for i in range(9)], 9),
         ptr(packed), T, ctypes.c_float(intersect_eps), ctypes.c_float(size_eps),
-        ctypes.c_float(ray_start_eps), ptr(hit), ptr(out["x"]), ptr(out["y"]), ptr(out["z"]),
-        ptr(valid), ptr(out["ray_u"]), ptr(out["trig_u"]), ptr(out["trig_v"]), ptr(gather_trig),
-        _stream()), "tfrt_intersect3d")
+        ctypes.c_float(ray_start_eps), ctypes.c_float(margin_ulps), ptr(hit), ptr(out["x"]),
+        ptr(out["y"]), ptr(out["z"]), ptr(valid), ptr(out["ray_u"]), ptr(out["trig_u"]),
+        ptr(out["trig_v"]), ptr(gather_trig), ptr(diag), _stream()), "tfrt_intersect3d")
     out["valid"] = valid.bool()
     out["gather_trig"] = gather_trig.long()
     out["gather_ray"] = torch.arange(N, device=dev)
@@ -131,84 +139,152 @@ def material_table(descriptors, device):
     return torch.from_numpy(raw).to(device)
 
 
+class TraceWorkspace:
+    """Tape and scratch of a whole-loop trace for one (N rays, K iterations) shape: one device
+    allocation carved into the arrays of TfrtTrace3DArgs, plus a pinned host mirror of the
+    counters.  Reused from trace to trace by the engine, so a steady-state trace allocates
+    nothing (engine.OpticalEngine keeps a workspace only while no autograd graph still reads
+    its tape)."""
+
+    def __init__(self, N, K, device):
+        self.N, self.K, self.device = int(N), int(K), device
+        self.generation = 0           # bumped by every trace that binds this workspace
+        n1 = max(self.N, 1)
+        lib = _lib.load()
+        sync_bytes = int(lib.tfrt_trace3d_sync_bytes(self.N, self.K))
+        spec = [   # name, dtype, shape   (8-byte types first: every block stays aligned)
+            ("cur_d", torch.float64, (6, n1)),
+            ("hit", torch.int64, (n1,)),
+            ("sync_ws", torch.int64, ((sync_bytes + 7) // 8 + 2,)),
+            ("cur", torch.float32, (6, n1)),
+            ("tape_f", torch.float32, (K, 9, n1)),
+            ("tape_tri", torch.int32, (K, n1)),
+            ("tape_outpos", torch.int32, (K, n1)),
+            ("live", torch.int32, (K + 1, n1)),
+            ("cat_ids", torch.int32, (3, n1)),
+            ("counters", torch.int32, ((K + 1) * 4 + 4,)),      # + the 4 diag words
+            ("tape_status", torch.uint8, (K, n1)),
+        ]
+        total, offsets = 0, []
+        for _, dtype, shape in spec:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            offsets.append(total)
+            total += (nbytes + 15) // 16 * 16
+        self._buffer = torch.empty((total,), dtype=torch.uint8, device=device)
+        for (name, dtype, shape), off in zip(spec, offsets):
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            setattr(self, name, self._buffer[off:off + nbytes].view(dtype).view(shape))
+        self.diag = self.counters[(K + 1) * 4:]
+        self.counters_pinned = torch.empty(((K + 1) * 4 + 4,), dtype=torch.int32).pin_memory()
+        self.copied = torch.cuda.Event()
+
+
 class Trace3D:
-    """One whole-loop trace (b4 seam): owns the tape / workspace and exposes the histories."""
+    """One whole-loop trace (b4 seam): binds inputs to a workspace and exposes the histories."""
 
     def __init__(self, src, tri, norm, category, n_optical, max_iterations, *, packed=None,
                  mat_in=None, mat_out=None, n_in=None, n_out=None, materials=None, n_materials=0,
-                 intersect_eps=1e-10, size_eps=1e-10, ray_start_eps=1e-10, new_ray_length=1.0):
+                 n_table=None, lambda_index=None,
+                 intersect_eps=1e-10, size_eps=1e-10, ray_start_eps=1e-10, new_ray_length=1.0,
+                 margin_ulps=DEFAULT_MARGIN_ULPS, workspace=None):
         _require_cuda(src, tri, norm, category)   # norm may be None: geometric normals
         self.src = _f32(src)          # (7,N): x_start..z_end, wavelength
         self.tri = _f32(tri)          # (9,T)
         self.norm = None if norm is None else _f32(norm)        # (T,3)
-        self.category = category.to(torch.int32).contiguous()
+        self.category = category if (category.dtype == torch.int32 and category.is_contiguous()) \
+            else category.to(torch.int32).contiguous()
         dev = self.src.device
         N, T, K = self.src.shape[1], self.tri.shape[1], int(max_iterations)
         self.N, self.T, self.K = N, T, K
         self.size_eps = float(size_eps)
-        self.packed = packed if packed is not None else pack_triangles(self.tri, size_eps)
-        self.index_mode = 1 if materials is not None else 0
-        self.mat_in = None if mat_in is None else mat_in.to(torch.int32).contiguous()
-        self.mat_out = None if mat_out is None else mat_out.to(torch.int32).contiguous()
+        self.margin_ulps = float(margin_ulps)
+        self.packed = packed if packed is not None else pack_triangles(self.tri, size_eps, margin_ulps)
+        self.index_mode = 1 if (materials is not None or n_table is not None) else 0
+
+        def i32(t):
+            return None if t is None else (
+                t if (t.dtype == torch.int32 and t.is_contiguous()) else t.to(torch.int32).contiguous())
+
+        self.mat_in, self.mat_out = i32(mat_in), i32(mat_out)
         self.n_in = None if n_in is None else _f32(n_in)
         self.n_out = None if n_out is None else _f32(n_out)
         self.materials = materials
-        n1 = max(N, 1)
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.cur = torch.empty((6, n1), dtype=torch.float32, device=dev)
-        self.cur_d = torch.empty((6, n1), dtype=torch.float64, device=dev)
-        self.hit = torch.empty((n1,), dtype=torch.int64, device=dev)
-        self.tape_f = torch.empty((K, 9, n1), dtype=torch.float32, device=dev)
-        self.tape_tri = torch.empty((K, n1), **i32)
-        self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
-        self.tape_outpos = torch.empty((K, n1), **i32)
-        self.live = torch.empty((K + 1, n1), **i32)
-        self.cat_ids = torch.empty((3, n1), **i32)
-        self.block_counts = torch.empty((8 * ((n1 + 255) // 256),), **i32)
-        self.counters = torch.empty(((K + 1) * 4,), **i32)
+        self.n_table = None if n_table is None else n_table.to(torch.float64).contiguous()
+        self.lambda_index = i32(lambda_index)
+        ws = workspace
+        if ws is None or ws.N != N or ws.K != K or ws.device != dev:
+            ws = TraceWorkspace(N, K, dev)
+        self.ws = ws
+        ws.generation += 1
+        self.ws_generation = ws.generation
+        for name in ("cur", "cur_d", "hit", "tape_f", "tape_tri", "tape_status", "tape_outpos",
+                     "live", "cat_ids", "counters", "diag"):
+            setattr(self, name, getattr(ws, name))
         self._counters_host = None
 
         a = TfrtTrace3DArgs()
         a.n_rays, a.n_tri, a.n_optical, a.max_iterations = N, T, int(n_optical), K
         a.intersect_eps, a.size_eps = float(intersect_eps), float(size_eps)
         a.ray_start_eps, a.new_ray_length = float(ray_start_eps), float(new_ray_length)
+        a.margin_ulps = self.margin_ulps
         a.index_mode, a.n_materials = self.index_mode, int(n_materials)
+        a.n_lambda = 0 if self.n_table is None else int(self.n_table.shape[1])
+        src0, stride = self.src.data_ptr(), self.src.stride(0) * 4
         for i in range(7):
-            a.src[i] = self.src[i].data_ptr()
+            a.src[i] = src0 + i * stride
+        tri0, stride = self.tri.data_ptr(), self.tri.stride(0) * 4
         for i in range(9):
-            a.tri[i] = self.tri[i].data_ptr()
-        a.norm = 0 if self.norm is None else self.norm.data_ptr()
-        a.category = self.category.data_ptr()
-        a.mat_in = 0 if self.mat_in is None else self.mat_in.data_ptr()
-        a.mat_out = 0 if self.mat_out is None else self.mat_out.data_ptr()
-        a.n_in = 0 if self.n_in is None else self.n_in.data_ptr()
-        a.n_out = 0 if self.n_out is None else self.n_out.data_ptr()
-        a.materials = 0 if materials is None else materials.data_ptr()
+            a.tri[i] = tri0 + i * stride
+        p = lambda t: 0 if t is None else t.data_ptr()   # noqa: E731
+        a.norm, a.category = p(self.norm), self.category.data_ptr()
+        a.mat_in, a.mat_out, a.n_in, a.n_out = p(self.mat_in), p(self.mat_out), p(self.n_in), p(self.n_out)
+        a.materials, a.n_table, a.lambda_index = p(materials), p(self.n_table), p(self.lambda_index)
         a.packed = self.packed.data_ptr()
+        n1 = max(N, 1)
+        cur0, curd = ws.cur.data_ptr(), ws.cur_d.data_ptr()
         for i in range(6):
-            a.cur[i] = self.cur[i].data_ptr()
-        a.cur_d = self.cur_d.data_ptr()
-        a.hit, a.tape_f = self.hit.data_ptr(), self.tape_f.data_ptr()
-        a.tape_tri, a.tape_status = self.tape_tri.data_ptr(), self.tape_status.data_ptr()
-        a.tape_outpos, a.live = self.tape_outpos.data_ptr(), self.live.data_ptr()
+            a.cur[i] = cur0 + i * n1 * 4
+        a.cur_d = curd
+        a.hit, a.tape_f = ws.hit.data_ptr(), ws.tape_f.data_ptr()
+        a.tape_tri, a.tape_status = ws.tape_tri.data_ptr(), ws.tape_status.data_ptr()
+        a.tape_outpos, a.live = ws.tape_outpos.data_ptr(), ws.live.data_ptr()
+        cat0 = ws.cat_ids.data_ptr()
         for i in range(3):
-            a.cat_ids[i] = self.cat_ids[i].data_ptr()
-        a.block_counts, a.counters = self.block_counts.data_ptr(), self.counters.data_ptr()
+            a.cat_ids[i] = cat0 + i * n1 * 4
+        a.sync_ws = (ws.sync_ws.data_ptr() + 15) // 16 * 16
+        a.counters, a.diag = ws.counters.data_ptr(), ws.diag.data_ptr()
         self.args = a
 
     def forward(self):
-        """Enqueue the whole trace loop (asynchronous)."""
+        """Enqueue the whole trace loop, then the copy of the counters into pinned host memory
+        (all asynchronous: nothing here waits for the GPU)."""
         self._counters_host = None
         check(_lib.load().tfrt_trace3d_forward(ctypes.byref(self.args), _stream()),
               "tfrt_trace3d_forward")
+        self.ws.counters_pinned.copy_(self.ws.counters, non_blocking=True)
+        self.ws.copied.record()
         return self
 
     @property
     def counters_host(self):
-        """(K+1, 4) int32 on the host: one small D2H copy, the only sync of a trace."""
+        """(K+1, 4) int32 on the host.  Waits for the trace: the live / history counts are data
+        dependent, so this is the one synchronisation of a trace, paid when the histories are
+        materialised (not when the trace is enqueued)."""
         if self._counters_host is None:
-            self._counters_host = self.counters.cpu().numpy().reshape(self.K + 1, 4).copy()
+            self.ws.copied.synchronize()
+            both = self.ws.counters_pinned.numpy()
+            self._counters_host = both[: (self.K + 1) * 4].reshape(self.K + 1, 4).copy()
+            self._diag_host = both[(self.K + 1) * 4:].copy()
         return self._counters_host
+
+    @property
+    def diagnostics(self):
+        """Re-validation counters of the trace (include/tfrt_b200.h): dict with `revalidated`
+        (fp32 winners rejected by the exact fp64 rule and searched again), `gross` (rejections
+        far beyond fp32 rounding: a search defect, expected 0) and `research_hits`."""
+        self.counters_host
+        d = self._diag_host
+        return {"revalidated": int(d[0]), "gross": int(d[1]), "research_hits": int(d[2])}
 
     def live_counts(self):
         """Live rays entering each executed iteration (for the tests/s metric)."""
@@ -228,15 +304,16 @@ class Trace3D:
         n = self.history_count(w)
         dev = self.src.device
         rays = torch.empty((6, n), dtype=torch.float32, device=dev)
-        slot = torch.empty((n,), dtype=torch.int32, device=dev)
-        it = torch.empty((n,), dtype=torch.int32, device=dev)
+        meta = torch.empty((2, n), dtype=torch.int32, device=dev)
+        slot, it = meta[0], meta[1]
         if n:
             ch = np.ascontiguousarray(self.counters_host.reshape(-1))
             drl = -1.0 if dead_ray_length is None else float(dead_ray_length)
+            r0 = rays.data_ptr()
+            out = (ctypes.c_void_p * 6)(*[r0 + i * n * 4 for i in range(6)])
             check(_lib.load().tfrt_materialize3d(
                 ctypes.byref(self.args), ch.ctypes.data_as(ctypes.c_void_p), w,
-                ctypes.c_float(drl), ptr_array([rays[i] for i in range(6)], 6), ptr(slot),
-                ptr(it), _stream()), "tfrt_materialize3d")
+                ctypes.c_float(drl), out, ptr(slot), ptr(it), _stream()), "tfrt_materialize3d")
         return rays, slot, it
 
     def backward(self, g_hist, want_src_grad=False, dead_ray_length=None, n_grad_tri=0):

@@ -5,7 +5,10 @@ signature properties, exclusions) with the same names and meanings.
 `StandardReaction` (refraction / reflection / TIR with material look-up, tfrt/operation.py:200-307)
 is what the fused CUDA trace loop implements; `OpticalEngine.ray_trace` recognises it by type and
 runs the whole iteration loop on the GPU.  Its `main` is also available on its own (used by
-`OpticalEngine.single_pass`) and runs the same fused material + Snell kernel for one projection.
+`OpticalEngine.single_pass`, the projection-at-a-time path taken when other operations are in
+the list): there the reaction is the same formulas as differentiable torch ops on the GPU
+(`OpticalEngine._react_projection`, fp64 arithmetic on the fp32 fields in 3D), not the fused
+kernel.
 """
 
 import torch

@@ -65,11 +65,22 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
     return engine, params
 
 
-def rel_err(a, b):
+ATOL_FRACTION = 0.1
+
+
+def rel_err(a, b, floor=ATOL_FRACTION):
+    """Elementwise relative error with an absolute floor:  max_i |a_i - b_i| / (|b_i| + atol),
+    atol = `floor` x the largest |b|.  `rel_err(a, b) < rtol` is therefore the elementwise bound
+    |a_i - b_i| <= rtol |b_i| + rtol x 0.1 x max|b|: every entry is held to the north star's
+    relative tolerance against its own magnitude, and entries much smaller than the array's
+    scale (a coordinate that happens to be ~0, a gradient entry that cancels) against a tenth
+    of that scale."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-30)
-    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+    if not a.size:
+        return 0.0
+    atol = max(floor * np.max(np.abs(b)), 1e-30)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + atol)))
 
 
 # ----------------------------------------------------------------------------------------------

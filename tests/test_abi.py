@@ -38,12 +38,16 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.TfrtMaterial) == 8 + 7 * 8
     a = _lib.TfrtTrace3DArgs()
     assert ctypes.sizeof(a) % 8 == 0
-    assert _lib.TfrtTrace3DArgs.src.offset == 40
+    assert _lib.TfrtTrace3DArgs.src.offset == 48     # 12 leading 4-byte scalars
     lib = _lib.load()
     for code, mirror in enumerate(_lib.STRUCT_MIRRORS):
         assert lib.tfrt_struct_size(code) == ctypes.sizeof(mirror), mirror.__name__
-    assert _lib.load().tfrt_packed_floats(1) == 256 * 12
-    assert _lib.load().tfrt_packed_floats(257) == 512 * 12
+    # a tile of 256 triangles = 130 pair records of 24 floats (two spare pair slots complete
+    # axis groups of odd size)
+    assert _lib.load().tfrt_packed_floats(1) == 130 * 24
+    assert _lib.load().tfrt_packed_floats(257) == 2 * 130 * 24
+    assert _lib.load().tfrt_trace3d_sync_bytes(1000, 3) >= 4 * (2 * 3 + 4 * 4 * 3)
+    assert _lib.load().tfrt_source_hash().decode() == _build.source_hash()
 
 
 def test_sass_is_blackwell_native():

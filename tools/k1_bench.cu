@@ -13,7 +13,8 @@
 int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
                             const int32_t *n_live_ptr, int n_upper, const float *packed,
                             int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
-                            uint64_t *hit, int dir_mode, cudaStream_t stream);
+                            uint64_t *hit, int dir_mode, unsigned int *work_counter,
+                            float start_floor_ulps, cudaStream_t stream);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
@@ -48,19 +49,23 @@ int main(int argc, char **argv) {
     float *d_tri, *d_ray, *d_packed;
     uint64_t *d_hit;
     CK(cudaMalloc(&d_tri, tri.size() * 4)); CK(cudaMalloc(&d_ray, ray.size() * 4));
-    CK(cudaMalloc(&d_packed, tfrt_packed_floats(T) * 4)); CK(cudaMalloc(&d_hit, (size_t)N * 8));
+    CK(cudaMalloc(&d_packed, tfrt_packed_floats(T) * 4)); CK(cudaMalloc(&d_hit, ((size_t)N + 1) * 8));
     CK(cudaMemcpy(d_tri, tri.data(), tri.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ray, ray.data(), ray.size() * 4, cudaMemcpyHostToDevice));
     const float *trip[9], *rayp[6];
     for (int c = 0; c < 9; ++c) trip[c] = d_tri + (size_t)c * T;
     for (int c = 0; c < 6; ++c) rayp[c] = d_ray + (size_t)c * N;
-    if (tfrt_pack_triangles(trip, T, 1e-5f, d_packed, 0)) { printf("pack: %s\n", tfrt_last_error()); return 1; }
+    if (tfrt_pack_triangles(trip, T, 1e-5f, 0.f, d_packed, 0)) { printf("pack: %s\n", tfrt_last_error()); return 1; }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
+        // the launcher's contract: hits preset to ~0, work counter (the word after them) zero
+        CK(cudaMemsetAsync(d_hit, 0xff, (size_t)N * 8));
+        CK(cudaMemsetAsync(d_hit + N, 0, 8));
         CK(cudaEventRecord(e0));
-        if (tfrt_launch_intersect3d(rayp, nullptr, nullptr, N, d_packed, T, 1e-10f, 1e-4f, 1e-5f, d_hit, 0, 0)) {
+        if (tfrt_launch_intersect3d(rayp, nullptr, nullptr, N, d_packed, T, 1e-10f, 1e-4f, 1e-5f, d_hit, 0,
+                                    reinterpret_cast<unsigned int *>(d_hit + N), 0.f, 0)) {
             printf("launch: %s\n", tfrt_last_error()); return 1;
         }
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));

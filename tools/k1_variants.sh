@@ -7,18 +7,15 @@ cd "$(dirname "$0")/.."
 SRC="tools/k1_bench.cu tensorflowraytrace_b200/csrc/abi.cu tensorflowraytrace_b200/csrc/pack.cu tensorflowraytrace_b200/csrc/intersect3d.cu"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17"
 declare -A V
-V[base]=""
-V[mb1]="-DTFRT_K1_MINBLOCKS=1"
-V[u1]="-DTFRT_K1_UNROLL=1"
-V[u4]="-DTFRT_K1_UNROLL=4"
-V[r3]="-DTFRT_K1_FORCE_R2=3"
-V[r6]="-DTFRT_K1_FORCE_R2=6 -DTFRT_K1_MINBLOCKS=2"
-V[t256]="-DTFRT_K1_THREADS=256 -DTFRT_K1_MINBLOCKS=2"
-V[s2]="-DTFRT_K1_STAGES=2"
-V[s4]="-DTFRT_K1_STAGES=4"
-V[mb3]="-DTFRT_K1_MINBLOCKS=3"
-V[mb5]="-DTFRT_K1_MINBLOCKS=5"
-V[scalar]="-DTFRT_K1_SCALAR=1"
+# round-2 study of the triangle-pair layout (one ray x two triangles per packed instruction):
+# source order of the test, occupancy, ring depth, threads per CTA
+V[pair]=""
+V[pair_nr6]="-DTFRT_K1_FORCE_NR=6 -DTFRT_K1_MINBLOCKS=3"
+V[pair_nr10]="-DTFRT_K1_FORCE_NR=10 -DTFRT_K1_MINBLOCKS=2"
+V[pair_mb2]="-DTFRT_K1_MINBLOCKS=2"
+V[pair_mb4]="-DTFRT_K1_MINBLOCKS=4"
+V[pair_s4]="-DTFRT_K1_STAGES=4"
+V[pair_t256]="-DTFRT_K1_THREADS=256 -DTFRT_K1_MINBLOCKS=1"
 if [ "$1" = "run" ]; then
   for v in "${!V[@]}"; do printf "%-12s " $v; ./build/k1/$v ${2:-4194304} ${3:-100}; done | sort
   exit 0
