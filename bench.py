@@ -62,12 +62,18 @@ def parse_args():
                          "config 5); weak: every GPU traces the full ray count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-accel", action="store_true", help="skip the acceleration-grid leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0,
                     help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
 
-def make_scene(args, ray_count=None):
+DEVICE_SOURCE_CONFIGS = ("cfg3", "cfg5")     # rays born on the GPU at every step (Philox)
+
+
+def make_scene(args, ray_count=None, with_rays=True):
+    """The config's scene.  with_rays=False (lens-optimisation configs): meshes only -- the rays
+    are generated on the device (our arm) or, for a CPU sample, by `cpu_sample_rays`."""
     from tensorflowraytrace_b200 import scenes
     cfg = CONFIGS[args.config]
     kwargs = dict(cfg["kwargs"])
@@ -75,7 +81,34 @@ def make_scene(args, ray_count=None):
         kwargs["ray_count"] = int(ray_count)
     elif args.rays:
         kwargs["ray_count"] = int(args.rays)
-    return getattr(scenes, cfg["factory"])(**kwargs), cfg
+    if args.config in DEVICE_SOURCE_CONFIGS and not with_rays:
+        kwargs["with_rays"] = False
+    scene = getattr(scenes, cfg["factory"])(**kwargs)
+    scene.setdefault("ray_count", int(scene["sources"]["x_start"].shape[0]) if scene["sources"] else 0)
+    return scene, cfg
+
+
+def cpu_sample_rays(scene, n, epoch=2):
+    """The first n rays of the device-born source of a lens-optimisation scene
+    (scenes.lens_optimize_device_source), restated in NumPy from oracle/sampling.py (same Philox
+    counters, same transforms): the CPU arm traces a sample of exactly the rays the GPU arm
+    generates.  Returns a copy of the scene whose `sources` hold those n rays."""
+    from oracle import sampling
+    from tensorflowraytrace_b200 import scenes
+    L = scenes.LENS_SOURCE
+    seed = scene.get("seed", 1234)
+    base, rank = sampling.square(seed, 0, epoch, 0, n, L["object_size"], L["object_size"])
+    dirs, _ = sampling.sphere(seed, 1, epoch, 0, 0, n, scene["ray_count"], L["cone"], 1.0)
+    starts = np.stack([np.full(n, -L["source_distance"]), base[:, 0].astype(np.float64),
+                       base[:, 1].astype(np.float64)], axis=1)
+    out = dict(scene)
+    out["sources"] = scenes.make_rays(starts, dirs.astype(np.float64), L["wavelength"],
+                                      extra={"rank": rank.astype(np.float64)})
+    return out
+
+
+def scene_ray_count(scene):
+    return int(scene.get("ray_count") or scene["sources"]["x_start"].shape[0])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,6 +178,8 @@ def oracle_step(scene, n_rays, backward, threads):
     import helpers
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
+    if not scene["sources"]:
+        scene = cpu_sample_rays(scene, n_rays)
     if scene["dimension"] == 2:
         sub = dict(scene)
         sub["sources"] = {k: v[:n_rays] for k, v in scene["sources"].items()}
@@ -171,7 +206,7 @@ def size_cpu_sample(scene, backward, threads, target_s):
     """Pick a ray count whose oracle step takes about target_s seconds (probe, then scale)."""
     probe = 256
     dt, tests, _ = oracle_step(scene, probe, backward, threads)
-    n_total = scene["sources"]["x_start"].shape[0]
+    n_total = scene_ray_count(scene)
     n = int(probe * max(target_s / max(dt, 1e-3), 1.0))
     n = max(probe, min(n, 65536, n_total))
     return n
@@ -194,7 +229,9 @@ def reference_source_leg(scene, backward, threads, target_s=8.0, mem_bytes=6e9):
         ref = rr.import_reference(installed_only=True)
         T = scene_triangles(scene)
         per_ray = T * 8.0 * 150 * (scene["max_iterations"] if backward else 1)
-        n = int(max(8, min(mem_bytes / per_ray, 4096, scene["sources"]["x_start"].shape[0])))
+        n = int(max(8, min(mem_bytes / per_ray, 4096, scene_ray_count(scene))))
+        if not scene["sources"]:
+            scene = cpu_sample_rays(scene, n)
         dt, tests, live = rr.timed_reference_step(ref, scene, n, backward)        # warm-up / probe
         reps = int(max(1, min(5, target_s / max(dt, 1e-3))))
         total_s = total_tests = 0.0
@@ -204,7 +241,7 @@ def reference_source_leg(scene, backward, threads, target_s=8.0, mem_bytes=6e9):
             total_tests += tests
         return {"value": total_tests / total_s, "unit": UNIT, "cores": threads,
                 "kind": "reference source on a stand-in tensorflow",
-                "sample": f"first {n} of {scene['sources']['x_start'].shape[0]} rays x {T} triangles x "
+                "sample": f"first {n} of {scene_ray_count(scene)} rays x {T} triangles x "
                           f"{scene['max_iterations']} iterations, {'fwd+bwd (GradientTape)' if backward else 'fwd'}, "
                           f"{reps} step(s) of {total_s / reps:.2f} s; unmodified tfrt.engine / geometry / "
                           f"operation / boundaries from baseline/_ref, every tf op served by torch float64 "
@@ -221,7 +258,7 @@ def run_reference(args):
         return
     import torch
     threads = os.cpu_count() or 1
-    scene, cfg = make_scene(args)
+    scene, cfg = make_scene(args, with_rays=False)
     backward = cfg["backward"]
     T = scene_triangles(scene)
     n = size_cpu_sample(scene, backward, threads, target_s=max(2.0, 90.0 / max(args.steps + args.warmup, 1)))
@@ -233,7 +270,7 @@ def run_reference(args):
         total_s += dt
         total_tests += tests
     value = total_tests / total_s
-    sample = (f"first {n} of {scene['sources']['x_start'].shape[0]} rays x {T} triangles x "
+    sample = (f"first {n} of {scene_ray_count(scene)} rays x {T} triangles x "
               f"{scene['max_iterations']} iterations, {'fwd+bwd' if backward else 'fwd'}, "
               f"float64 dense (triangles x ray-chunk) restatement, torch CPU")
     line = {
@@ -254,7 +291,7 @@ def run_reference(args):
     }
     src_leg = reference_source_leg(scene, backward, threads)
     if src_leg is not None:
-        line["reference_source"] = src_leg
+        line["cpu_baseline"]["reference_source"] = src_leg
     print(json.dumps(line), flush=True)
 
 
@@ -271,7 +308,7 @@ def scene_triangles(scene):
 
 
 def l2_note(scene, world):
-    n = scene["sources"]["x_start"].shape[0] // max(world, 1)
+    n = scene_ray_count(scene) // max(world, 1)
     work = n * (28 + 24 + 48 + 8 + 49 * scene["max_iterations"])
     if work < 2 * (126 << 20):
         return (f"per-step working set {work / 2**20:.0f} MiB fits the 126 MB L2: L2 flushed "
@@ -281,7 +318,7 @@ def l2_note(scene, world):
 
 
 def bench_config(args, scene, world):
-    n = scene["sources"]["x_start"].shape[0]
+    n = scene_ray_count(scene)
     return {
         "workload": f"{args.config}: {scene['name']} -- {n} rays x {scene_triangles(scene)} "
                     f"{'segments+arcs' if scene['dimension'] == 2 else 'triangles'} x "
@@ -306,56 +343,94 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     rank, world, local = parallel.init_from_env()
     dev = torch.device("cuda", torch.cuda.current_device())
-    scene, cfg = make_scene(args)
+    device_rays = args.config in DEVICE_SOURCE_CONFIGS
+    scene, cfg = make_scene(args, with_rays=not device_rays)
     backward = cfg["backward"]
-    n_total = scene["sources"]["x_start"].shape[0]
+    n_total = scene_ray_count(scene)
     T = scene_triangles(scene)
     K = scene["max_iterations"]
+    shard = (rank, world) if (args.scaling == "strong" and world > 1) else None
+    build = scenes.build_engine_2d if scene["dimension"] == 2 else scenes.build_engine
 
-    # ---- this rank's rays, as pinned HOST buffers (the e2e path copies them every step)
-    if args.scaling == "strong":
-        lo, hi = parallel.shard_range(n_total, rank, world)
+    # ---- the engine of the device-resident legs
+    if device_rays:
+        # rays born on this rank's GPU at every system.update(), as the reference's optimiser
+        # regenerates them every step (tfrt/optimizer.py:217): counter-based sampling, so the
+        # ranks of a sharded job together trace exactly the rays one rank would
+        source = scenes.lens_optimize_device_source(n_total, scene["seed"])
+        engine, params, src = build(scene, source=source, ray_shard=shard,
+                                    compile_active_rays=False, compile_finished_rays=True)
+        host_fields = {k: v.detach() for k, v in src.items()}
     else:
-        lo, hi = 0, n_total
-    host = {}
-    for k, v in scene["sources"].items():
-        t = torch.from_numpy(np.ascontiguousarray(v[lo:hi]).astype(np.float32))
-        host[k] = t.pin_memory()
-    n_local = hi - lo
+        if shard is not None:
+            lo, hi = parallel.shard_range(n_total, rank, world)
+        else:
+            lo, hi = 0, n_total
+        scene_local = dict(scene)
+        scene_local["sources"] = {k: v[lo:hi] for k, v in scene["sources"].items()}
+        engine, params, src = build(scene_local, compile_active_rays=False,
+                                    compile_finished_rays=True)
+        host_fields = {k: torch.from_numpy(np.ascontiguousarray(v).astype(np.float32))
+                       for k, v in scene_local["sources"].items()}
+    n_local = int(next(iter(host_fields.values())).shape[0])
+
+    # ---- this rank's rays as pinned HOST buffers, and a second engine fed from them: the e2e leg
+    # copies them to the device every step through the public ManualSource API
+    host = {k: t.to("cpu", torch.float32).contiguous().pin_memory() for k, t in host_fields.items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
-
-    scene_local = dict(scene)
-    scene_local["sources"] = {k: v[lo:hi] for k, v in scene["sources"].items()}
-    if scene["dimension"] == 2:
-        engine, params, src = scenes.build_engine_2d(
-            scene_local, compile_active_rays=False, compile_finished_rays=True)
+    if device_rays:
+        from tensorflowraytrace_b200 import sources as tf_sources
+        e2e_src = tf_sources.ManualSource(3).feed({k: t.to(dev) for k, t in host.items()})
+        e2e_engine, e2e_params, _ = build(scene, source=e2e_src, compile_active_rays=False,
+                                          compile_finished_rays=True)
     else:
-        engine, params, src = scenes.build_engine(
-            scene_local, compile_active_rays=False, compile_finished_rays=True)
+        e2e_engine, e2e_params, e2e_src = engine, params, src
     errf = scenes.imaging_error(scene) if backward else None
     opt = optimizer.SGD_Optimizer(engine, params, errf, K) if backward else None
+    e2e_opt = opt if e2e_engine is engine else (
+        optimizer.SGD_Optimizer(e2e_engine, e2e_params, errf, K) if backward else None)
     acc = [None] * len(params)
     d2h_bytes = sum(p.numel() * 4 for p in params) + 4 if backward else 4
+    tally = {"tests": 0.0, "steps": 0, "check": None, "diag": {"revalidated": 0, "gross": 0}}
+
+    def account(eng, grads=None, err=None):
+        """Per-step bookkeeping from numbers the step has already brought to the host."""
+        tr = eng.last_trace
+        live = tr.live_counts()
+        tally["tests"] += float(sum(live)) * T
+        tally["steps"] += 1
+        tally["live"] = live
+        if hasattr(tr, "diagnostics"):
+            d = tr.diagnostics
+            tally["diag"]["revalidated"] += d["revalidated"]
+            tally["diag"]["gross"] += d["gross"]
+        if grads is not None:
+            tally["check"] = (grads, err)
 
     def step_resident():
-        """Inputs already in HBM: update + trace (+ loss + backward + all-reduce)."""
+        """Inputs already in HBM: update (rays regenerated on the device where the config says
+        so) + trace (+ loss + backward + all-reduce)."""
         if backward:
             grads, err = opt.process_gradient(acc)
+            account(engine, grads, err)
             return grads, err
         engine.optical_system.update()
         engine.ray_trace(K)
+        if scene["dimension"] == 3:
+            engine.finished_rays          # materialise: the trace's result
+            account(engine)
         return None, None
 
     def step_e2e():
         """Public API from HOST buffers: H2D of this step's rays, step, D2H of loss + grads."""
         for k, t in host.items():
-            src[k] = t.to(dev, non_blocking=True)
-        grads, err = step_resident()
+            e2e_src[k] = t.to(dev, non_blocking=True)
         if backward:
-            out = [g.cpu() for g in grads] + [err.cpu()]
-        else:
-            out = [engine.finished_rays["x_end"][:1].cpu()]
-        return out
+            grads, err = e2e_opt.process_gradient(acc)
+            return [g.cpu() for g in grads] + [err.cpu()]
+        e2e_engine.optical_system.update()
+        e2e_engine.ray_trace(K)
+        return [e2e_engine.finished_rays["x_end"][:1].cpu()]
 
     def barrier():
         if world > 1:
@@ -400,10 +475,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    live = engine.last_trace.live_counts()
-    tests_local = float(sum(live)) * T
-    tests_total = parallel.sum_over_ranks(tests_local)
-    rays_total = parallel.sum_over_ranks(n_local)
+    if scene["dimension"] == 2:
+        live = engine.last_trace.live_counts()
+        tally["live"] = live
+    tally.update(tests=0.0, steps=0)
+    tally["diag"] = {"revalidated": 0, "gross": 0}
 
     # clocks / throttle reasons are sampled on rank 0's GPU only: one nvidia-smi poller per rank
     # (NVML takes driver locks) can cost another rank a timed step on an 8-GPU box
@@ -418,15 +494,35 @@ def run_ours(args):
     k_ms, k_n = kernels.profile_read()
     kernels.profile_enable(False)
     clocks = sampler.stop() if sampler is not None else {}
+    live = tally["live"]
+    if scene["dimension"] == 2:
+        tests_local = float(sum(live)) * T * args.steps
+    else:
+        tests_local = tally["tests"]                 # summed over the timed steps
+    tests_total = parallel.sum_over_ranks(tests_local) / args.steps     # per step, whole job
+    rays_total = parallel.sum_over_ranks(n_local)
+    diag = {k: int(parallel.sum_over_ranks(v)) for k, v in tally["diag"].items()}
+    check = None
+    if tally["check"] is not None:
+        # loss and gradient checksums of the LAST timed step (already all-reduced: identical on
+        # every rank).  The rays are a function of (seed, update number) only, so these agree
+        # between N = 1 and N = 8 up to the fp32 summation order of the all-reduce.
+        grads, err = tally["check"]
+        g64 = [g.detach().double() for g in grads]
+        check = {"mean_error": float(err),
+                 "grad_sum": float(sum(g.sum() for g in g64)),
+                 "grad_l1": float(sum(g.abs().sum() for g in g64)),
+                 "update_number": int(max(args.warmup, 3) + args.steps)}
 
     # forward-only (update + trace), same inputs
     def step_forward():
         engine.optical_system.update()
         engine.ray_trace(K)
+        if scene["dimension"] == 3:
+            engine.finished_rays
     step_forward()
     fwd_seconds = timed(step_forward, args.steps)
 
-    # backward kernel share: time fwd+bwd minus fwd
     value = tests_total * args.steps / seconds
     line = {
         "metric": METRIC if backward else "ray_triangle_tests_per_s_fwd",
@@ -441,33 +537,47 @@ def run_ours(args):
                          "ms_per_step": 1e3 * fwd_seconds / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        # fp64 re-validation of the fp32 search's winners over the timed steps, all ranks:
+        # `revalidated` = proposals the exact rule rejected (searched again exactly; rounding at
+        # triangle edges), `gross` = rejections beyond rounding (a search defect; must be 0)
+        "revalidation": diag,
     }
+    if check is not None:
+        line["check"] = check
+    line["config"]["rays_origin"] = (
+        "regenerated on the device at every step by counter-based sampling kernels "
+        "(Philox4x32-10 keyed by seed and global ray index; each rank generates only its shard)"
+        if device_rays else "fixed NumPy scene, resident on the device")
     # ---- roofline of the dominant kernel (k_intersect3d), rank 0's launches
     if k_n > 0 and k_ms > 0:
-        tests_per_launch = tests_local * args.steps / k_n
+        tests_per_launch = tests_local / k_n
         achieved = FLOP_PER_TEST * tests_per_launch / (k_ms / k_n * 1e-3) / 1e12
+        launch_s = k_ms / k_n * 1e-3
+        nominal = 148 * 128 * 2 * 1.965e9
         line["roofline"] = {
-            "kernel": "k_intersect3d", "bound": "fp32_fma", "achieved": achieved,
-            "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
+            "kernel": "k_intersect3d", "bound": "fp32_fma",
+            # what the hardware does, first: the projected plane form EXECUTES 25 FLOP per test
+            # (10 FFMA + 1 FMUL + 3 FADD + 1 reciprocal = 14 FMA-pipe lane-slots, issued as 7
+            # packed f32x2 instructions, each testing one ray against two triangles)
+            "executed_flop_per_test": 25.0,
+            "frac_executed": 25.0 * tests_per_launch / launch_s / fp32_peak,
+            "frac_executed_of_nominal": 25.0 * tests_per_launch / launch_s / nominal,
+            "fma_pipe_slots_per_test": 14.0,
+            "fma_pipe_utilisation": 14.0 * tests_per_launch / launch_s / (fp32_peak / 2.0),
+            # the contract's figure: ALGORITHMIC count (45 FLOP per Moller-Trumbore test,
+            # SURVEY.md 8(d)) over the measured launch time; above 1 because the kernel needs
+            # fewer operations per test than the algorithmic count
+            "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+            "frac": achieved / (fp32_peak / 1e12),
+            "frac_of_nominal": achieved / (nominal / 1e12),
+            "flop_per_test": FLOP_PER_TEST,
             "traffic": intersect_traffic(n_local),
-            "traffic_source": "ncu dram__bytes_read+write of a 2 097 152-ray launch "
-                              "(profiles/r1_intersect3d_traffic.json) scaled per ray to this "
-                              "launch; DRAM is 0.03 % of peak, the kernel is FP32-issue bound",
+            "traffic_source": "ncu dram__bytes_read+write of one launch "
+                              "(profiles/r2_intersect3d_traffic.json, else round 1's) scaled per "
+                              "ray to this launch; DRAM is < 0.1 % of peak, the kernel is bound "
+                              "by FP32 issue / register-operand bandwidth",
             "launches": int(k_n), "avg_launch_ms": k_ms / k_n,
             "share_of_step": k_ms * 1e-3 / seconds,
-            "flop_per_test": FLOP_PER_TEST,
-            # `achieved` / `frac` use the ALGORITHMIC count (45 FLOP per Moller-Trumbore test,
-            # SURVEY.md 8(d)); the kernel's projected plane form executes 25 FLOP per test
-            # (10 FFMA + 1 FMUL + 3 FADD + 1 reciprocal), so `frac` can exceed 1 while the FMA
-            # pipe itself is ~70 % busy: both views are given
-            "executed_flop_per_test": 25.0,
-            "frac_executed": 25.0 * tests_per_launch / (k_ms / k_n * 1e-3) / fp32_peak,
-            # the kernel's projected plane form issues 10 FFMA + 1 FMUL + 3 FADD (as 14 packed
-            # f32x2 instructions per ray pair) + 1 MUFU.RCP per test: 14 FMA-pipe lane-slots, i.e.
-            # fewer than the algorithmic 45-FLOP Moller-Trumbore count the roofline is quoted on
-            "fma_pipe_slots_per_test": 14.0,
-            "fma_pipe_utilisation": 14.0 * tests_per_launch / (k_ms / k_n * 1e-3)
-                                    / (fp32_peak / 2.0),
             "peak_source": "measured in this run by tfrt_fp32_peak (register-only FFMA loop on "
                            "all SMs); MEASURED_PEAKS.json carries no fp32 figure. Nominal "
                            "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s",
@@ -504,6 +614,7 @@ def run_ours(args):
             engine.optical_system.update()
             engine.ray_trace(K)
             total = errf(engine).sum()
+            torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -526,11 +637,43 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):     # own warm-up: fresh device buffers every step
             step_e2e()                           # (the caching allocator settles after two)
         e2e_seconds = timed(step_e2e, args.steps)
-        line["e2e"] = {"value": tests_total * args.steps / e2e_seconds, "unit": UNIT,
+        if scene["dimension"] == 3:     # the fixed host rays' own live counts
+            e2e_tests = parallel.sum_over_ranks(
+                float(sum(e2e_engine.last_trace.live_counts())) * T)
+        else:
+            e2e_tests = tests_total
+        line["e2e"] = {"value": e2e_tests * args.steps / e2e_seconds, "unit": UNIT,
                        "h2d_bytes_per_step": int(parallel.sum_over_ranks(h2d_bytes)),
                        "d2h_bytes_per_step": int(d2h_bytes * world),
                        "ms_per_step": 1e3 * e2e_seconds / args.steps,
                        "rays_per_s": rays_total * args.steps / e2e_seconds}
+
+    # ---- optional acceleration mode, reported on its own: the same step
+    # with the search walking a device-built uniform grid instead of testing every triangle.  Its
+    # time is NEVER part of the tests/s metric above (that is the brute-force search).
+    if scene["dimension"] == 3 and not args.no_accel:
+        system = engine.optical_system
+        system.accel = "grid"
+        try:
+            for _ in range(3):
+                step_resident()
+            kernels.profile_enable(True)
+            kernels.profile_read()
+            grid_seconds = timed(step_resident, args.steps)
+            g_ms, g_n = kernels.profile_read()
+            kernels.profile_enable(False)
+            st = system.grid.stats()
+            line["accel_grid"] = {
+                "ms_per_step": 1e3 * grid_seconds / args.steps,
+                "speedup_over_brute_force_step": seconds / grid_seconds,
+                "rays_per_s": rays_total * args.steps / grid_seconds,
+                "search_kernel_ms_per_launch": (g_ms / g_n) if g_n else None,
+                "grid": st,
+                "note": "same hit indices and gradients as the brute-force search "
+                        "(tests/test_gpu_grid.py); optional mode, outside the tests/s metric"}
+        finally:
+            system.accel = None
+            system.update()
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample, same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -556,10 +699,14 @@ def run_ours(args):
 def intersect_traffic(n_rays):
     """DRAM bytes per k_intersect3d launch over n_rays rays, from the committed ncu capture."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_intersect3d_traffic.json")))
-        return float(t["dram_bytes_per_ray_per_launch"]) * float(n_rays)
+        for name in ("r2_intersect3d_traffic.json", "r1_intersect3d_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                t = json.load(open(path))
+                return float(t["dram_bytes_per_ray_per_launch"]) * float(n_rays)
     except Exception:
-        return None
+        pass
+    return None
 
 
 def measured_peaks():

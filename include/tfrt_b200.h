@@ -122,7 +122,27 @@ int tfrt_intersect3d(const float *const ray[6], int32_t n_rays, const float *con
                      const float *packed, int32_t n_tri, float intersect_eps, float size_eps,
                      float ray_start_eps, float margin_ulps, uint64_t *hit_ws, float *x, float *y,
                      float *z, uint8_t *valid, float *ray_u, float *trig_u, float *trig_v,
-                     int32_t *gather_trig, int32_t *diag, void *stream);
+                     int32_t *gather_trig, int32_t *diag, const void *grid,
+                     int32_t grid_max_cells, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optional spatial acceleration of the search: a uniform grid over the
+ * triangles, built on the device (no host round trip) by tfrt_grid_build after every
+ * tfrt_pack_triangles, walked per ray with a 3-D DDA.  Every candidate is tested with the
+ * brute-force kernel's own arithmetic and the winner is the same lexicographic minimum of
+ * (bits(t), index), so a search through the grid returns the hit words the brute-force search
+ * returns; what follows (re-validation, reaction, gradients) is shared.  Triangles much larger
+ * than the typical one are kept out of the grid and tested by every ray.  Pass the workspace as
+ * `grid` (with the same max_cells) to tfrt_intersect3d / TfrtTrace3DArgs; NULL = brute force, the
+ * path the tests/s metric is quoted on.
+ * tfrt_grid_stats (synchronises): out[8] = dims x, y, z, cells, (cell, triangle) entries, large
+ * triangles, entries that did not fit (0 in a valid grid), typical triangle extent x 1e6.
+ */
+size_t tfrt_grid_bytes(int32_t n_tri, int32_t max_cells);
+int tfrt_grid_build(const float *const tri[9], const float *packed, int32_t n_tri, float size_eps,
+                    float margin_ulps, int32_t max_cells, void *grid_ws, void *stream);
+int tfrt_grid_stats(const void *grid_ws, int32_t n_tri, int32_t max_cells, int64_t *out_host,
+                    void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * b4  whole-loop seam: OpticalEngine.ray_trace (tfrt/engine.py:2311-2330) with
@@ -143,6 +163,7 @@ typedef struct {
                                0: ("value") per-triangle n_in / n_out */
     int32_t n_materials;
     int32_t n_lambda;       /* columns of n_table */
+    int32_t grid_max_cells; /* the value given to tfrt_grid_build (when `grid` is set) */
 
     const float *src[7];    /* x_start,y_start,z_start,x_end,y_end,z_end,wavelength; N each */
     const float *tri[9];    /* xp,yp,zp,x1,y1,z1,x2,y2,z2; T each */
@@ -162,6 +183,8 @@ typedef struct {
                                wavelengths of the source set; takes precedence over `materials` */
     const int32_t *lambda_index; /* N: column of n_table for every source ray */
     const float *packed;    /* tfrt_pack_triangles output */
+    const void *grid;       /* optional tfrt_grid_build workspace: the search walks the grid
+                               instead of testing every triangle (same hits); NULL = brute force */
 
     /* workspace + history ("tape"), all caller-allocated */
     float *cur[6];          /* N each: working ray state per slot: start (3) and
@@ -188,8 +211,8 @@ typedef struct {
 
 size_t tfrt_trace3d_sync_bytes(int32_t n_rays, int32_t max_iterations);
 
-/* Enqueues 1 + 2 K kernels (set-up, then search + reaction per iteration); no memsets, no host
- * round trip: the live counts stay on the device. */
+/* Enqueues 1 + 3 K kernels (set-up, then search + re-validation + reaction per iteration); no
+ * memsets, no host round trip: the live counts stay on the device. */
 int tfrt_trace3d_forward(const TfrtTrace3DArgs *args, void *stream);
 
 /* Materialise one history set in the reference's order (concat over iterations of the
@@ -297,6 +320,30 @@ int tfrt_trace2d_forward(const TfrtTrace2DArgs *args, void *stream);
 int tfrt_trace2d_backward(const TfrtTrace2DArgs *fwd, const float *g_tape, double *g_acc,
                           float *const g_seg[4], float *const g_arc[5], float *const g_src[4],
                           void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rays born on the device: the sampling the reference's sources repeat at every system.update()
+ * (tfrt/optimizer.py:217; tfrt/distributions.py:1361-1392 squares, :1726-1850 spheres).
+ * Counter-based: sample i of a distribution is Philox4x32-10 keyed by (seed, stream) at counter
+ * (global index, draw, epoch), so a rank that generates indices [first, first + n) of a sharded
+ * source reproduces that slice of the single-rank stream bit for bit.  `epoch` numbers the updates
+ * of one distribution object, `stream` the objects.  All outputs are fp32, computed in fp64.
+ *
+ * tfrt_sample_uniform: out[i] = lo + (hi - lo) U_i, variable `which` of the sample.
+ * tfrt_sample_square : RandomUniformSquare -- points (n,2) in [-x_size,x_size] x [-y_size,y_size],
+ *                      ranks (n,2) = points / max(x_size, y_size).
+ * tfrt_sample_sphere : unit vectors about +x times `radius`, points (n,3), ranks (n,2) =
+ *                      (phi, theta mod 2 pi).  mode 0 RandomUniformSphere, 1 RandomLambertianSphere,
+ *                      2 StaticUniformSphere (golden spiral; `total` = the distribution's
+ *                      sample_count), 3 StaticLambertianSphere.
+ */
+int tfrt_sample_uniform(uint32_t seed, uint32_t stream, uint32_t epoch, uint32_t which,
+                        int64_t first, int32_t n, double lo, double hi, float *out, void *stream_);
+int tfrt_sample_square(uint32_t seed, uint32_t stream, uint32_t epoch, int64_t first, int32_t n,
+                       double x_size, double y_size, float *points, float *ranks, void *stream_);
+int tfrt_sample_sphere(uint32_t seed, uint32_t stream, uint32_t epoch, int32_t mode, int64_t first,
+                       int32_t n, int64_t total, double angular_size, double radius, float *points,
+                       float *ranks, void *stream_);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (roofline denominators): run an FFMA-only loop on every SM and return the

@@ -17,7 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libtfrt_b200.so")
 
-SOURCES = ["abi.cu", "pack.cu", "intersect3d.cu", "trace3d.cu", "backward3d.cu", "trace2d.cu"]
+SOURCES = ["abi.cu", "pack.cu", "intersect3d.cu", "trace3d.cu", "backward3d.cu", "trace2d.cu",
+           "sources.cu", "grid3d.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

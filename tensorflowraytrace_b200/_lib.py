@@ -33,6 +33,7 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("index_mode", ctypes.c_int32),
         ("n_materials", ctypes.c_int32),
         ("n_lambda", ctypes.c_int32),
+        ("grid_max_cells", ctypes.c_int32),
         ("src", c_void_p * 7),
         ("tri", c_void_p * 9),
         ("norm", c_void_p),
@@ -45,6 +46,7 @@ class TfrtTrace3DArgs(ctypes.Structure):
         ("n_table", c_void_p),
         ("lambda_index", c_void_p),
         ("packed", c_void_p),
+        ("grid", c_void_p),
         ("cur", c_void_p * 6),
         ("cur_d", c_void_p),
         ("hit", c_void_p),
@@ -114,10 +116,11 @@ EXPORTED_SYMBOLS = [
     "tfrt_last_error", "tfrt_abi_version", "tfrt_source_hash", "tfrt_struct_size",
     "tfrt_faces_forward", "tfrt_faces_backward",
     "tfrt_packed_floats", "tfrt_pack_triangles",
-    "tfrt_intersect3d",
+    "tfrt_intersect3d", "tfrt_grid_bytes", "tfrt_grid_build", "tfrt_grid_stats",
     "tfrt_trace3d_sync_bytes", "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
     "tfrt_trace3d_backward",
     "tfrt_intersect2d", "tfrt_trace2d_forward", "tfrt_trace2d_backward",
+    "tfrt_sample_uniform", "tfrt_sample_square", "tfrt_sample_sphere",
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
@@ -163,8 +166,15 @@ def load():
     lib.tfrt_struct_size.argtypes = [ctypes.c_int]
     lib.tfrt_packed_floats.restype = ctypes.c_size_t
     lib.tfrt_packed_floats.argtypes = [ctypes.c_int32]
+    lib.tfrt_grid_bytes.restype = ctypes.c_size_t
+    lib.tfrt_grid_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
     lib.tfrt_trace3d_sync_bytes.restype = ctypes.c_size_t
     lib.tfrt_trace3d_sync_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    u32, i32, i64, f64 = ctypes.c_uint32, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    lib.tfrt_sample_uniform.argtypes = [u32, u32, u32, u32, i64, i32, f64, f64, c_void_p, c_void_p]
+    lib.tfrt_sample_square.argtypes = [u32, u32, u32, i64, i32, f64, f64, c_void_p, c_void_p, c_void_p]
+    lib.tfrt_sample_sphere.argtypes = [u32, u32, u32, i32, i64, i32, i64, f64, f64, c_void_p,
+                                       c_void_p, c_void_p]
     lib.tfrt_launch_count.restype = ctypes.c_longlong
     lib.tfrt_launch_count.argtypes = [ctypes.c_int]
     if lib.tfrt_abi_version() != ABI_VERSION:

@@ -49,7 +49,7 @@ def run_trace(tri, norm, src, plan, workspace=None):
         n_table=plan.n_table, lambda_index=plan.lambda_index,
         intersect_eps=plan.intersect_eps, size_eps=plan.size_eps,
         ray_start_eps=plan.ray_start_eps, new_ray_length=plan.new_ray_length,
-        margin_ulps=plan.margin_ulps, workspace=workspace)
+        margin_ulps=plan.margin_ulps, workspace=workspace, grid=plan.grid)
     tr.forward()
     plan.trace = tr
     return tr
@@ -132,6 +132,7 @@ class TracePlan:
         self.materials, self.n_materials = kw.get("materials"), kw.get("n_materials", 0)
         self.n_table, self.lambda_index = kw.get("n_table"), kw.get("lambda_index")
         self.margin_ulps = kw.get("margin_ulps", kernels.DEFAULT_MARGIN_ULPS)
+        self.grid = kw.get("grid")     # optional kernels.TriangleGrid (acceleration mode)
         self.lease = None
         self.intersect_eps = kw["intersect_eps"]
         self.size_eps = kw["size_eps"]

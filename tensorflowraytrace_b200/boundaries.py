@@ -457,10 +457,24 @@ class TriangleBoundaryBase(BoundaryBase):
             self._mesh.save(filename, **kwargs)
 
     def update_vertices_from_mesh(self):
-        if self._mesh is not None:
-            self._vertices = as_field(self._mesh.points)
-            self._faces = torch.from_numpy(unpack_faces(self._mesh.faces)).to(
-                dtype=torch.int32, device=self._vertices.device)
+        """(Re-)read vertices and faces from the mesh (tfrt/boundaries.py:871-888).  The device
+        copies are kept when the mesh arrays are bit-identical to the ones uploaded last time
+        (a static boundary is re-read at every system.update(); comparing a few KB on the host
+        is cheaper than a host-to-device copy and a kernel)."""
+        if self._mesh is None:
+            return False
+        points = np.ascontiguousarray(np.asarray(self._mesh.points))
+        faces = np.asarray(self._mesh.faces)
+        cached = getattr(self, "_mesh_upload", None)
+        if (cached is not None and self._vertices is not None and self._faces is not None
+                and cached[0].shape == points.shape and cached[1].shape == faces.shape
+                and np.array_equal(cached[0], points) and np.array_equal(cached[1], faces)):
+            return False
+        self._vertices = as_field(points)
+        self._faces = torch.from_numpy(unpack_faces(faces)).to(
+            dtype=torch.int32, device=self._vertices.device)
+        self._mesh_upload = (points.copy(), faces.copy())
+        return True
 
     def update_fields_from_vertices(self):
         """vertices -> xp..z2 + unit norm through the K3 kernel; differentiable w.r.t. the
@@ -476,6 +490,7 @@ class TriangleBoundaryBase(BoundaryBase):
             self[k] = tri[i]
         self["norm"] = norm
         self._geometric_norm = norm   # the fused trace may re-derive it from the corners in fp64
+        self._tri_block = tri         # (9,F): the geometry fields are its rows (merged as a block)
 
     def has_geometric_norm(self):
         """True while the `norm` field is the one computed from the vertices (not overridden)."""
@@ -483,8 +498,9 @@ class TriangleBoundaryBase(BoundaryBase):
 
     def update_from_mesh(self):
         if self._mesh is not None:
-            self.update_vertices_from_mesh()
-            self.update_fields_from_vertices()
+            changed = self.update_vertices_from_mesh()
+            if changed or "xp" not in self._fields or getattr(self, "_tri_block", None) is None:
+                self.update_fields_from_vertices()
 
     def update_mesh_from_vertices(self):
         if self._vertices is not None and self._mesh is not None:
@@ -577,7 +593,15 @@ class ParametricTriangleBoundary(TriangleBoundaryBase):
         return self._vectors
 
     def _flip_norm(self, mesh):
-        mesh.faces = np.ascontiguousarray(unpack_faces(mesh.faces)[:, ::-1])
+        """Reverse the winding of every face (tfrt/boundaries.py:1059-1065).  The faces are
+        written back in the layout the mesh object uses: (F,3) for TriangleMesh, pyvista's
+        packed [3, i, j, k, ...] for anything else (a pyvista.PolyData would misread (F,3))."""
+        flipped = np.ascontiguousarray(unpack_faces(mesh.faces)[:, ::-1])
+        if isinstance(mesh, TriangleMesh):
+            mesh.faces = flipped
+        else:
+            mesh.faces = np.hstack(
+                [np.full((flipped.shape[0], 1), 3, dtype=flipped.dtype), flipped]).ravel()
         return mesh
 
     def update_vertices_from_mesh(self):

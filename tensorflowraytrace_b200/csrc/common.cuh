@@ -82,24 +82,33 @@ static inline int tfrt_div_up(long long a, long long b) { return (int)((a + b - 
 // fp32 hit point near it), converted to barycentric units by the steepest barycentric gradient
 // (1 / smallest altitude).  Scale-aware: a mesh in millimetres or far from the origin gets a
 // proportionally larger margin.  A, e1 = B - A, e2 = C - A in fp64.
-__host__ __device__ inline double tfrt_tri_margin(const double A[3], const double e1[3],
-                                                  const double e2[3], double ulps) {
-    double scale = 0.0;
+__host__ __device__ inline double tfrt_tri_scale(const double A[3], const double e1[3],
+                                                 const double e2[3]) {
+    double scale = 0.0;          // largest |coordinate| of the three vertices
     for (int c = 0; c < 3; ++c) {
         const double a = fabs(A[c]), b = fabs(A[c] + e1[c]), d = fabs(A[c] + e2[c]);
         scale = fmax(scale, fmax(a, fmax(b, d)));
     }
+    return scale;
+}
+
+// steepest barycentric gradient = 1 / smallest altitude:
+// |grad u| = |e2| / |N|, |grad v| = |e1| / |N|, |grad w| = |e2 - e1| / |N|
+__host__ __device__ inline double tfrt_tri_bary_gradient(const double e1[3], const double e2[3]) {
     const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
                          e1[0] * e2[1] - e1[1] * e2[0]};
     const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
     if (!(nn > 0.0)) return 0.0;
-    // |grad u| = |e2| / |N|, |grad v| = |e1| / |N|, |grad w| = |e2 - e1| / |N|
     const double l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
     const double l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
     const double d0 = e2[0] - e1[0], d1 = e2[1] - e1[1], d2 = e2[2] - e1[2];
     const double l3 = d0 * d0 + d1 * d1 + d2 * d2;
-    const double g = sqrt(fmax(l1, fmax(l2, l3)) / nn);
-    return ulps * 1.1920928955078125e-7 * scale * g;
+    return sqrt(fmax(l1, fmax(l2, l3)) / nn);
+}
+
+__host__ __device__ inline double tfrt_tri_margin(const double A[3], const double e1[3],
+                                                  const double e2[3], double ulps) {
+    return ulps * 1.1920928955078125e-7 * tfrt_tri_scale(A, e1, e2) * tfrt_tri_bary_gradient(e1, e2);
 }
 
 // ---------------------------------------------------------------------------------------------

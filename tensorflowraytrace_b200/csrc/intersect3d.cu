@@ -221,8 +221,10 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                 D[2][i] = dir_mode ? ez[slot] : ez[slot] - az;
                 // shift the origin along the ray by the search's start exclusion (in units of
                 // |D|, like ray_u): t_shifted >= 0 <=> ray_u >= start
+                // (explicit operation order: the grid search of grid3d.cu shifts its rays with the
+                // same expression and must get the same bits)
                 const float start = fmaxf(ray_start_eps, start_floor * rsqrtf(
-                    D[0][i] * D[0][i] + D[1][i] * D[1][i] + D[2][i] * D[2][i]));
+                    fmaf(D[2][i], D[2][i], fmaf(D[1][i], D[1][i], __fmul_rn(D[0][i], D[0][i])))));
                 O[0][i] = fmaf(start, D[0][i], ax);
                 O[1][i] = fmaf(start, D[1][i], ay);
                 O[2][i] = fmaf(start, D[2][i], az);

@@ -14,8 +14,8 @@
 // Per-ray arithmetic here is fp64 on fp32 inputs (O(rays) work, negligible next to the
 // O(rays x triangles) intersection); results are stored fp32.
 //
-// Launches of one trace: k_trace_init, then per iteration k_intersect3d (intersect3d.cu) and
-// k_react3d -- 1 + 2 K launches, no memsets, no host round trip.
+// Launches of one trace: k_trace_init, then per iteration k_intersect3d (intersect3d.cu),
+// k_validate3d and k_react3d -- 1 + 3 K launches, no memsets, no host round trip.
 #include "common.cuh"
 
 int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
@@ -23,6 +23,13 @@ int tfrt_launch_intersect3d(const float *const ray[6], const int32_t *live,
                             int n_tri, float intersect_eps, float ray_start_eps, float size_eps,
                             uint64_t *hit, int dir_mode, unsigned int *work_counter,
                             float start_floor_ulps, cudaStream_t stream);
+
+int tfrt_launch_grid_intersect3d(const float *const ray[6], const int32_t *live,
+                                 const int32_t *n_live_ptr, int n_upper, const float *packed,
+                                 int n_tri, const void *grid_ws, int max_cells,
+                                 float intersect_eps, float ray_start_eps, float size_eps,
+                                 uint64_t *hit, int dir_mode, float start_floor_ulps,
+                                 cudaStream_t stream);
 
 namespace {
 
@@ -197,9 +204,11 @@ __device__ int block_research(bool fail, const double S[3], const double E[3],
 }
 
 // Re-validation of the fp32 search's winner with the reference's exact rule in fp64.
-// Returns true when the winner stands.  `gross` is set when it fails by more than the search's
-// own rounding allowance (4 x the pack-time margin scaled by the ray's obliquity): that is a
-// search defect, not rounding, and tests assert it never happens.
+// Returns true when the winner stands.  `gross` is set when it fails by more than rounding can
+// explain: the fp32 hit point is uncertain by a few ulps of the coordinates involved (the
+// triangle's and the ray origin's), amplified by 1 / |cos incidence| for an oblique ray; a
+// proposal whose fp64 hit lies farther than 16 search margins of that from the triangle (or from
+// the ray-start threshold) is a search defect, not rounding, and tests assert it never happens.
 __device__ __forceinline__ bool revalidate(const HitEval &e, const ValidRule &rule,
                                            const double S[3], const double E[3],
                                            const double A[3], const double B[3],
@@ -214,14 +223,17 @@ __device__ __forceinline__ bool revalidate(const HitEval &e, const ValidRule &ru
     const double mD = fabs(m[0] * D[0] + m[1] * D[1] + m[2] * D[2]);
     const double mm = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
     const double dn = sqrt(D[0] * D[0] + D[1] * D[1] + D[2] * D[2]);
-    const double obliq = mD > 0.0 ? fmax(1.0, mm * dn / mD) : 1e30;       // 1 / |cos incidence|
-    // position scale of the test: the triangle's coordinates and the ray origin's
-    const double base = tfrt_tri_margin(A, e1, e2, fmax(margin_ulps, 4.0));
-    const double o = fmax(fabs(S[0]), fmax(fabs(S[1]), fabs(S[2])));
-    const double a = fmax(fabs(A[0]), fmax(fabs(A[1]), fabs(A[2])));
-    const double slack = 4.0 * base * obliq * fmax(1.0, o / fmax(a, 1e-300));
-    gross = !e.den_ok || e.u < -(rule.size_eps + slack) || e.v < -(rule.size_eps + slack) ||
-            e.u + e.v > 1.0 + rule.size_eps + 2.0 * slack || e.t < 0.5 * rule.ray_start_eps;
+    if (!(mD > 0.0) || !(dn > 0.0)) return false;         // parallel / null ray: all rounding
+    const double obliq = fmax(1.0, mm * dn / mD);         // 1 / |cos incidence|
+    const double scale = fmax(tfrt_tri_scale(A, e1, e2),
+                              fmax(fabs(S[0]), fmax(fabs(S[1]), fabs(S[2]))));
+    // distance the fp32 hit point may be off, with a wide safety factor
+    const double dist = 16.0 * fmax(margin_ulps, 4.0) * 1.1920928955078125e-7 * scale * obliq;
+    const double slack_b = dist * tfrt_tri_bary_gradient(e1, e2);     // in barycentric units
+    const double slack_t = dist / dn;                                 // in ray-parameter units
+    gross = !e.den_ok || e.u < -(rule.size_eps + slack_b) || e.v < -(rule.size_eps + slack_b) ||
+            e.u + e.v > 1.0 + rule.size_eps + 2.0 * slack_b ||
+            e.t < 0.5 * rule.ray_start_eps - slack_t;
     return false;
 }
 
@@ -329,34 +341,24 @@ __device__ __forceinline__ void snell3d(const double S[3], const double H[3], co
     }
 }
 
-__global__ void __launch_bounds__(kReactThreads) k_react3d(ReactParams P) {
-    __shared__ int s_bid;
-    __shared__ int s_warp[4][kReactWarps];
-    __shared__ unsigned long long s_excl[2];
+// Stage A of an iteration's O(rays) work: evaluate the search's winner in fp64, apply the
+// reference's exact rule, and search again (exactly) for the rare rays whose winner fails it.
+// Leaves hit[p] = validated winner (key 0) or "no hit".  A kernel of its own, so that CTAs that
+// have to search again delay nobody: the compaction of k_react3d is an ordered chain over CTAs
+// (look-back), and a CTA that took tens of microseconds there would stall every CTA behind it.
+__global__ void __launch_bounds__(kReactThreads) k_validate3d(ReactParams P) {
     __shared__ ResearchSmem s_research;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_live = P.counters_k[0];
-    const int n_blocks = (n_live + kReactThreads - 1) / kReactThreads;
-    if (tid == 0) s_bid = (int)atomicAdd(P.ticket, 1u);
-    __syncthreads();
-    const int bid = s_bid;
-    if (n_blocks == 0) {   // nothing live: the loop has ended (tfrt/engine.py:2324-2330)
-        if (bid == 0 && tid < 4) P.counters_next[tid] = tid == 0 ? 0 : P.counters_k[tid];
-        return;
-    }
-    if (bid >= n_blocks) return;   // whole CTA idle (uniform)
-    const int p = bid * kReactThreads + tid;
+    if (blockIdx.x * kReactThreads >= n_live) return;   // whole CTA idle (uniform)
+    const int p = blockIdx.x * kReactThreads + threadIdx.x;
     const size_t N = (size_t)P.n_rays;
     const ValidRule rule{P.intersect_eps, P.size_eps, P.ray_start_eps};
-
-    // ---- stage A: evaluate and re-validate the search's winner in fp64
-    int slot = -1, tri = -1;
+    int tri = -1;
     double S[3] = {0, 0, 0}, E[3] = {0, 0, 0};
     bool fail = false;
     if (p < n_live) {
-        slot = P.live[p];
+        const int slot = P.live[p];
         const uint64_t hit = P.hit[p];
-        P.hit[p] = ~0ull;                       // preset for the next iteration's atomicMin merge
         // working state = (start, direction) in fp64; end = start + direction
         for (int c = 0; c < 3; ++c) {
             S[c] = P.cur_d[c * N + slot];
@@ -375,15 +377,48 @@ __global__ void __launch_bounds__(kReactThreads) k_react3d(ReactParams P) {
             }
         }
     }
-    {   // rare: exact fp64 search for the rays whose winner was rejected
-        SearchMesh mesh;
-        mesh.tri = P.tri; mesh.packed = P.packed; mesh.n_tri = P.n_tri; mesh.n_tiles = P.n_tiles;
-        mesh.w_one = P.w_one;
-        const int found = block_research(fail, S, E, mesh, rule, s_research);
-        if (fail) {
-            tri = found;
-            if (found >= 0) atomicAdd(&P.diag[2], 1);
+    SearchMesh mesh;
+    mesh.tri = P.tri; mesh.packed = P.packed; mesh.n_tri = P.n_tri; mesh.n_tiles = P.n_tiles;
+    mesh.w_one = P.w_one;
+    const int found = block_research(fail, S, E, mesh, rule, s_research);
+    if (fail) {
+        tri = found;
+        if (found >= 0) atomicAdd(&P.diag[2], 1);
+        P.hit[p] = tri >= 0 ? (uint64_t)(uint32_t)tri : ~0ull;
+    }
+}
+
+// Stage B + C: classification, fused material-index + Snell reaction, tape, and the
+// order-preserving compaction of the live set (single pass, decoupled look-back).
+__global__ void __launch_bounds__(kReactThreads) k_react3d(ReactParams P) {
+    __shared__ int s_bid;
+    __shared__ int s_warp[4][kReactWarps];
+    __shared__ unsigned long long s_excl[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_live = P.counters_k[0];
+    const int n_blocks = (n_live + kReactThreads - 1) / kReactThreads;
+    if (tid == 0) s_bid = (int)atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const int bid = s_bid;
+    if (n_blocks == 0) {   // nothing live: the loop has ended (tfrt/engine.py:2324-2330)
+        if (bid == 0 && tid < 4) P.counters_next[tid] = tid == 0 ? 0 : P.counters_k[tid];
+        return;
+    }
+    if (bid >= n_blocks) return;   // whole CTA idle (uniform)
+    const int p = bid * kReactThreads + tid;
+    const size_t N = (size_t)P.n_rays;
+
+    int slot = -1, tri = -1;
+    double S[3] = {0, 0, 0}, E[3] = {0, 0, 0};
+    if (p < n_live) {
+        slot = P.live[p];
+        const uint64_t hit = P.hit[p];            // validated by k_validate3d
+        P.hit[p] = ~0ull;                         // preset for the next iteration's atomicMin merge
+        for (int c = 0; c < 3; ++c) {
+            S[c] = P.cur_d[c * N + slot];
+            E[c] = S[c] + P.cur_d[(3 + c) * N + slot];
         }
+        if ((uint32_t)(hit >> 32) < TFRT_NOHIT_KEY) tri = (int)(uint32_t)hit;
     }
 
     // ---- stage B: classification, reaction, tape
@@ -642,16 +677,22 @@ extern "C" int tfrt_intersect3d(const float *const ray[6], int32_t n_rays,
                                 float intersect_eps, float size_eps, float ray_start_eps,
                                 float margin_ulps, uint64_t *hit_ws, float *x, float *y, float *z,
                                 uint8_t *valid, float *ray_u, float *trig_u, float *trig_v,
-                                int32_t *gather_trig, int32_t *diag, void *stream) {
+                                int32_t *gather_trig, int32_t *diag, const void *grid,
+                                int32_t grid_max_cells, void *stream) {
     TFRT_REQUIRE(n_rays >= 0 && n_tri > 0 && packed && hit_ws, "tfrt_intersect3d: bad arguments");
     if (n_rays == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     k_seam_init<<<tfrt_div_up(n_rays + 1, 256), 256, 0, st>>>(hit_ws, n_rays, diag);
-    int rc = tfrt_launch_intersect3d(ray, nullptr, nullptr, n_rays, packed, n_tri, intersect_eps,
-                                     kSearchStartFraction * ray_start_eps, size_eps, hit_ws,
-                                     /*dir_mode=*/0,
-                                     reinterpret_cast<unsigned int *>(hit_ws + n_rays),
-                                     kStartFloorPerMargin * margin_ulps, st);
+    int rc = grid
+        ? tfrt_launch_grid_intersect3d(ray, nullptr, nullptr, n_rays, packed, n_tri, grid,
+                                       grid_max_cells, intersect_eps,
+                                       kSearchStartFraction * ray_start_eps, size_eps, hit_ws,
+                                       /*dir_mode=*/0, kStartFloorPerMargin * margin_ulps, st)
+        : tfrt_launch_intersect3d(ray, nullptr, nullptr, n_rays, packed, n_tri, intersect_eps,
+                                  kSearchStartFraction * ray_start_eps, size_eps, hit_ws,
+                                  /*dir_mode=*/0,
+                                  reinterpret_cast<unsigned int *>(hit_ws + n_rays),
+                                  kStartFloorPerMargin * margin_ulps, st);
     if (rc) return rc;
     SearchMesh M;
     for (int c = 0; c < 9; ++c) M.tri.c[c] = tri[c];
@@ -720,10 +761,16 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
         const int32_t *live_k = a->live + (size_t)k * N;
         const int32_t *counters_k = a->counters + k * 4;
         const float *cur_c[6] = {a->cur[0], a->cur[1], a->cur[2], a->cur[3], a->cur[4], a->cur[5]};
-        int rc = tfrt_launch_intersect3d(cur_c, live_k, counters_k, N, a->packed, a->n_tri,
-                                         a->intersect_eps, kSearchStartFraction * a->ray_start_eps,
-                                         a->size_eps, a->hit, /*dir_mode=*/1, work_counters + k,
-                                         kStartFloorPerMargin * a->margin_ulps, st);
+        int rc = a->grid
+            ? tfrt_launch_grid_intersect3d(cur_c, live_k, counters_k, N, a->packed, a->n_tri,
+                                           a->grid, a->grid_max_cells, a->intersect_eps,
+                                           kSearchStartFraction * a->ray_start_eps, a->size_eps,
+                                           a->hit, /*dir_mode=*/1,
+                                           kStartFloorPerMargin * a->margin_ulps, st)
+            : tfrt_launch_intersect3d(cur_c, live_k, counters_k, N, a->packed, a->n_tri,
+                                      a->intersect_eps, kSearchStartFraction * a->ray_start_eps,
+                                      a->size_eps, a->hit, /*dir_mode=*/1, work_counters + k,
+                                      kStartFloorPerMargin * a->margin_ulps, st);
         if (rc) return rc;
         ReactParams P;
         P.n_tri = a->n_tri; P.n_optical = a->n_optical; P.index_mode = a->index_mode;
@@ -753,8 +800,9 @@ extern "C" int tfrt_trace3d_forward(const TfrtTrace3DArgs *a, void *stream) {
         P.ticket = tickets + k;
         P.diag = a->diag;
         P.n_rays = N;
+        k_validate3d<<<n_blocks, kReactThreads, 0, st>>>(P);
         k_react3d<<<n_blocks, kReactThreads, 0, st>>>(P);
-        tfrt_note_launch(1);
+        tfrt_note_launch(2);
     }
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -12,8 +12,13 @@ Mirrored classes (same constructor arguments, `update()`, `angles` / `points` / 
 The CDF / image / precompiled distributions (tfrt/distributions.py:2123-3195) are out of scope
 (host-side pre-processing that never runs inside the trace loop).
 
-Random distributions draw from a per-object `torch.Generator`; `seed_all(seed, rank)` gives
-every process of a multi-GPU job its own stream so that ray shards are independent.
+Random distributions on a CUDA device are counter-based (csrc/sources.cu): sample i of an object
+is Philox4x32-10 keyed by (seed, object stream) at counter (global index i, variable, update
+number), so the draws do not depend on the launch shape, and a distribution told to hold only
+one rank's shard (`set_shard(rank, world_size)`) produces exactly that slice of the single-rank
+stream -- N ranks together trace the rays one rank would.  `seed_all(seed)` seeds the objects
+created from then on.  (On a CPU device -- host-side use only -- draws come from a torch
+generator.)
 """
 
 import itertools
@@ -32,16 +37,17 @@ _SEED = {"base": 0x5EED, "next": 0}
 
 
 def seed_all(seed, rank=0):
-    """Seed the generators of distributions created from now on; `rank` offsets the stream so
-    the ranks of a sharded job sample different rays."""
-    _SEED["base"] = int(seed) * 1_000_003 + int(rank) * 7919
+    """Seed the distributions created from now on.  Every rank of a sharded job passes the SAME
+    seed (the streams are indexed by global sample number; `rank` is accepted for backward
+    compatibility and ignored by the counter-based generator)."""
+    _SEED["base"] = int(seed)
     _SEED["next"] = 0
+    _SEED["rank"] = int(rank)
 
 
-def _new_generator(device):
+def _new_generator(device, stream):
     g = torch.Generator(device=device)
-    g.manual_seed(_SEED["base"] + _SEED["next"])
-    _SEED["next"] += 1
+    g.manual_seed(_SEED["base"] * 1_000_003 + _SEED.get("rank", 0) * 7919 + stream)
     return g
 
 
@@ -50,16 +56,63 @@ def _f(x, device=None):
 
 
 class _Sampler:
-    """Shared plumbing: device, generator, uniform samples."""
+    """Shared plumbing: device, counter-based random stream, optional shard of the samples."""
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        inner = cls.__dict__.get("update")
+        if inner is not None:
+            def update(self, _inner=inner):
+                self._begin_update()
+                return _inner(self)
+            update.__doc__ = inner.__doc__
+            cls.update = update
 
     def _init_sampler(self, generator=None, device=None):
         self._device = torch.device(device) if device is not None else default_device()
         self._generator = generator
+        self._seed = (generator.initial_seed() if generator is not None else _SEED["base"]) & 0xFFFFFFFF
+        self._stream = _SEED["next"] & 0xFFFFFFFF
+        _SEED["next"] += 1
+        self._epoch, self._draw, self._depth = 0, 0, 0
+        self._shard = None
+
+    def _begin_update(self):
+        """A new update = a new epoch of this object's stream (nested update wrappers of one
+        class hierarchy count once)."""
+        self._epoch += 1
+        self._draw = 0
+
+    # ---- sharding: hold only the samples of one rank
+    supports_shard = False
+
+    def set_shard(self, rank, world_size):
+        """Keep only rank `rank`'s contiguous block of the samples from the next update() on.
+        Returns False when this distribution cannot generate a slice on its own."""
+        if not self.supports_shard:
+            return False
+        self._shard = None if world_size <= 1 else (int(rank), int(world_size))
+        return True
+
+    def _local_range(self, n):
+        if self._shard is None:
+            return 0, int(n)
+        from .parallel import shard_range
+        return shard_range(int(n), *self._shard)
 
     def _uniform(self, n, lo=0.0, hi=1.0):
+        """Uniform samples of this object's next variable, for the local range of `n` samples."""
+        first, stop = self._local_range(n)
+        which = self._draw
+        self._draw += 1
+        if self._device.type == "cuda":
+            from . import kernels
+            return kernels.sample_uniform(self._seed, self._stream, self._epoch, which, first,
+                                          stop - first, lo, hi, self._device)
         if self._generator is None:
-            self._generator = _new_generator(self._device)
-        return lo + (hi - lo) * torch.rand(int(n), generator=self._generator, device=self._device)
+            self._generator = _new_generator(self._device, self._stream)
+        u = torch.rand(int(n), generator=self._generator, device=self._device)[first:stop]
+        return lo + (hi - lo) * u
 
     def _linspace(self, lo, hi, n):
         return torch.linspace(float(lo), float(hi), int(n), device=self._device)
@@ -297,11 +350,24 @@ class StaticUniformSquare(SquareBase):
 
 
 class RandomUniformSquare(SquareBase):
-    def _make_points(self):
+    """x_res * y_res uniform points (tfrt/distributions.py:1379-1392); one fused sampling kernel
+    on a CUDA device."""
+
+    supports_shard = True
+
+    def update(self):
         n = self.x_res * self.y_res
+        if self._device.type == "cuda":
+            from . import kernels
+            first, stop = self._local_range(n)
+            self._points, self._ranks = kernels.sample_square(
+                self._seed, self._stream, self._epoch, first, stop - first, self.x_size,
+                self.y_size, self._device)
+            return
         x = self._uniform(n, -self.x_size, self.x_size)
         y = self._uniform(n, -self.y_size, self.y_size)
         self._points = torch.stack([x, y], dim=1)
+        self._ranks = self._points / max(self.x_size, self.y_size)
 
 
 class ThetaMod:
@@ -396,6 +462,27 @@ class SphereBase(ThetaMod, BasePointDistributionBase):
              sin_phi * torch.sin(self._theta)], dim=1)
         self._ranks = torch.stack([self._phi, torch.remainder(self._theta, 2 * PI)], dim=1)
 
+    def set_shard(self, rank, world_size):
+        # a slice is generated by the fused device sampler only (default theta window)
+        if not (self._device.type == "cuda" and self.theta_start == 0.0
+                and self.theta_end == 2 * PI):
+            return False
+        return super().set_shard(rank, world_size)
+
+    def _fused(self, mode):
+        """One sampling kernel for points and ranks (csrc/sources.cu) on a CUDA device with the
+        default theta window; returns False when the torch path has to be taken."""
+        if not (self._device.type == "cuda" and self.theta_start == 0.0
+                and self.theta_end == 2 * PI):
+            return False
+        from . import kernels
+        first, stop = self._local_range(self.sample_count)
+        self._points, self._ranks = kernels.sample_sphere(
+            self._seed, self._stream, self._epoch, mode, first, stop - first, self.sample_count,
+            self.angular_size, self.radius, self._device)
+        self._phi, self._theta = self._ranks[:, 0], self._ranks[:, 1]
+        return True
+
     def _golden_theta(self):
         idx = torch.arange(self.sample_count, dtype=torch.float64, device=self._device) + 0.5
         theta = GOLDEN_ANGLE_FACTOR * idx
@@ -408,14 +495,22 @@ class SphereBase(ThetaMod, BasePointDistributionBase):
 class StaticUniformSphere(SphereBase):
     """Golden spiral, uniform in solid angle (tfrt/distributions.py:1726-1748)."""
 
+    supports_shard = True
+
     def update(self):
+        if self._fused("static_uniform"):
+            return
         cos_phi = torch.linspace(1.0, math.cos(self.angular_size), self.sample_count,
                                  dtype=torch.float64, device=self._device)
         self._finish(cos_phi, self._golden_theta())
 
 
 class RandomUniformSphere(SphereBase):
+    supports_shard = True
+
     def update(self):
+        if self._fused("random_uniform"):
+            return
         cos_phi = self._uniform(self.sample_count, math.cos(self.angular_size), 1.0)
         self._finish(cos_phi, GOLDEN_ANGLE_FACTOR * self._uniform(self.sample_count))
 
@@ -423,14 +518,22 @@ class RandomUniformSphere(SphereBase):
 class StaticLambertianSphere(SphereBase):
     """cos^2(phi) uniform: Lambertian about +x (tfrt/distributions.py:1778-1811)."""
 
+    supports_shard = True
+
     def update(self):
+        if self._fused("static_lambertian"):
+            return
         c2 = torch.linspace(1.0, math.cos(self.angular_size) ** 2, self.sample_count,
                             dtype=torch.float64, device=self._device)
         self._finish(torch.sqrt(c2), self._golden_theta())
 
 
 class RandomLambertianSphere(SphereBase):
+    supports_shard = True
+
     def update(self):
+        if self._fused("random_lambertian"):
+            return
         c2 = self._uniform(self.sample_count, math.cos(self.angular_size) ** 2, 1.0)
         self._finish(torch.sqrt(c2), GOLDEN_ANGLE_FACTOR * self._uniform(self.sample_count))
 

@@ -121,11 +121,21 @@ class OpticalSystemBase(RecursivelyUpdatable):
 
     ray_shard : None or (rank, world_size).  When set, `update()` keeps only this rank's
     contiguous block of the amalgamated source rays (multi-GPU ray sharding, parallel.py).
+
+    accel : None (default: every ray is tested against every boundary, the brute-force search
+    the reference performs) or "grid" (3D): a uniform grid over the triangles is rebuilt on the
+    device at every update() and the search walks it -- same hit indices, same gradients, far
+    fewer tests (csrc/grid3d.cu); `grid_max_cells` bounds its size.
     """
 
     def __init__(self, manual_update_management=False, intersect_epsilion=1e-10,
                  size_epsilion=1e-5, ray_start_epsilion=1e-4, ray_shard=None,
-                 search_margin_ulps=kernels.DEFAULT_MARGIN_ULPS, **kwargs):
+                 search_margin_ulps=kernels.DEFAULT_MARGIN_ULPS, accel=None,
+                 grid_max_cells=kernels.DEFAULT_GRID_MAX_CELLS, **kwargs):
+        if accel not in (None, "grid"):
+            raise ValueError("OpticalSystem: accel must be None or 'grid'.")
+        self.accel = accel
+        self.grid_max_cells = int(grid_max_cells)
         self._sources = []
         self._read_only_sources = None
         self.source_handles = []
@@ -136,6 +146,8 @@ class OpticalSystemBase(RecursivelyUpdatable):
         self.size_epsilion = size_epsilion
         self.ray_start_epsilion = ray_start_epsilion
         self.search_margin_ulps = float(search_margin_ulps)
+        self._sources_native_shard = False
+        self._ray_shard = None
         self.ray_shard = ray_shard
         self.projection_results = {}
         super().__init__(**kwargs)
@@ -162,7 +174,25 @@ class OpticalSystemBase(RecursivelyUpdatable):
             assert each.dimension == self.dimension
             self.source_handles.append(each.update)
         self._sources = new
+        self._apply_ray_shard()
         self.refresh_update_handles()
+
+    @property
+    def ray_shard(self):
+        return self._ray_shard
+
+    @ray_shard.setter
+    def ray_shard(self, val):
+        self._ray_shard = None if val is None else (int(val[0]), int(val[1]))
+        self._apply_ray_shard()
+
+    def _apply_ray_shard(self):
+        """A single source that can generate its own shard does (rays born on this rank's GPU
+        only); otherwise update() slices the amalgamated rays."""
+        self._sources_native_shard = False
+        srcs = getattr(self, "_sources", None) or []
+        if self._ray_shard is not None and len(srcs) == 1 and hasattr(srcs[0], "set_ray_shard"):
+            self._sources_native_shard = bool(srcs[0].set_ray_shard(*self._ray_shard))
 
     @property
     def materials(self):
@@ -177,7 +207,7 @@ class OpticalSystemBase(RecursivelyUpdatable):
     def _amalgamate_sources(self):
         if bool(self._sources):
             merged = amalgamate(self._sources)
-            if self.ray_shard is not None and merged:
+            if self.ray_shard is not None and merged and not self._sources_native_shard:
                 from .parallel import shard_range
                 n = next(iter(merged.values())).shape[0]
                 lo, hi = shard_range(n, *self.ray_shard)
@@ -280,14 +310,86 @@ class OpticalSystem3D(OpticalSystemBase):
 
     def _update(self):
         self._amalgamate_sources()
-        if bool(self._optical):
-            self._amalgamated_optical = amalgamate(self._optical)
-        if bool(self._stop):
-            self._amalgamated_stop = amalgamate(self._stop)
-        if bool(self._target):
-            self._amalgamated_target = amalgamate(self._target)
-        self._merge_boundaries()
+        if not self._merge_blocks():
+            if bool(self._optical):
+                self._amalgamated_optical = amalgamate(self._optical)
+            if bool(self._stop):
+                self._amalgamated_stop = amalgamate(self._stop)
+            if bool(self._target):
+                self._amalgamated_target = amalgamate(self._target)
+            self._merge_boundaries()
         self.clear_read_only()
+
+    def _cached_cat(self, key, parts):
+        """torch.cat of per-boundary fields that rarely change (materials): reused while the
+        very same tensors are handed in."""
+        cache = self.__dict__.setdefault("_cat_cache", {})
+        ids = tuple((id(t), t._version) for t in parts)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == ids:
+            return hit[2]
+        out = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        cache[key] = (ids, list(parts), out)     # the parts are kept alive: ids stay unique
+        return out
+
+    def _merge_blocks(self):
+        """Fast form of amalgamate + _merge_boundaries (tfrt/engine.py:906-918, 971-1018) when
+        every boundary keeps its geometry as one (9,F) block (all triangle boundaries of this
+        package do): ONE concatenation builds the merged geometry in the layout the kernels
+        read, and the per-field views the reference's API exposes are rows / slices of it.
+        Returns False when some boundary is not block-based (the field-by-field path runs)."""
+        groups = ((OPTICAL, "optical", self._optical), (STOP, "stop", self._stop),
+                  (TARGET, "target", self._target))
+        blocks, norms, counts = [], [], []
+        for _, _, items in groups:
+            n = 0
+            for b in items:
+                if not bool(b):
+                    continue
+                blk = getattr(b, "_tri_block", None)
+                f = getattr(b, "_fields", None)
+                if blk is None or f is None or f.get("xp") is None or \
+                        f["xp"].data_ptr() != blk.data_ptr() or f["xp"].shape[0] != blk.shape[1] \
+                        or blk.dtype != torch.float32 or f.get("norm") is None:
+                    return False
+                blocks.append(blk)
+                norms.append(f["norm"])
+                n += blk.shape[1]
+            counts.append(n)
+        if not blocks:
+            return False
+        tri = blocks[0] if len(blocks) == 1 else torch.cat(blocks, 1)
+        norm = norms[0] if len(norms) == 1 else torch.cat(norms, 0)
+        self._optical_count, self._stop_count, self._target_count = counts
+        lo = 0
+        for (cat, name, items), n in zip(groups, counts):
+            d = {}
+            if n:
+                for i, k in enumerate(TRI_FIELDS):
+                    d[k] = tri[i, lo:lo + n]
+                d["norm"] = norm[lo:lo + n]
+                live = [b for b in items if bool(b)]
+                extra = set(live[0].keys()) - set(TRI_FIELDS) - {"norm"}
+                for b in live[1:]:
+                    extra &= set(b.keys())
+                for k in extra:
+                    d[k] = self._cached_cat((name, k), [b[k] for b in live])
+                d["catagory"] = self._category_tensor(cat, d["xp"])
+            setattr(self, "_amalgamated_" + name, d)
+            lo += n
+        merged = {k: tri[i] for i, k in enumerate(TRI_FIELDS)}
+        merged["norm"] = norm
+        merged["catagory"] = self._cached_cat(
+            ("merged", "catagory"),
+            [d["catagory"] for d in (self._amalgamated_optical, self._amalgamated_stop,
+                                     self._amalgamated_target) if bool(d)])
+        self._merged = merged
+        self._norm_is_geometric = all(
+            getattr(b, "has_geometric_norm", lambda: False)()
+            for b in list(self._optical) + list(self._stop) + list(self._target) if bool(b))
+        self._merged_tri_block = tri
+        self._dev_cache = None
+        return True
 
     def _boundary_property(name, store, handles, cache):  # noqa: N805  (class-body helper)
         def getter(self):
@@ -329,6 +431,7 @@ class OpticalSystem3D(OpticalSystemBase):
         self._norm_is_geometric = all(
             getattr(b, "has_geometric_norm", lambda: False)()
             for b in list(self._optical) + list(self._stop) + list(self._target) if bool(b))
+        self._merged_tri_block = None
         self._dev_cache = None
 
     # ------------------------------------------------------------------ kernel-side views
@@ -338,13 +441,31 @@ class OpticalSystem3D(OpticalSystemBase):
         plane records for the intersection kernel are rebuilt once per update()."""
         if self._dev_cache is None:
             m = self._merged
-            tri = torch.stack([m[k] for k in TRI_FIELDS]).to(torch.float32).contiguous()
+            blk = getattr(self, "_merged_tri_block", None)
+            if blk is not None and m["xp"].data_ptr() == blk.data_ptr():
+                tri = blk if blk.is_contiguous() else blk.contiguous()
+            else:
+                tri = torch.stack([m[k] for k in TRI_FIELDS]).to(torch.float32).contiguous()
             norm = m["norm"].to(torch.float32).contiguous()
-            category = m["catagory"].to(torch.int32).contiguous()
+            ckey = (self._optical_count, self._stop_count, self._target_count, tri.device)
+            c32 = self.__dict__.setdefault("_category32_cache", {})
+            if ckey not in c32:      # labels are a function of the three counts only
+                c32[ckey] = m["catagory"].to(torch.int32).contiguous()
+            category = c32[ckey]
             packed = kernels.pack_triangles(tri.detach(), self.size_epsilion,
                                             self.search_margin_ulps)
+            self._grid = None
+            if self.accel == "grid":
+                self._grid = kernels.TriangleGrid(tri.detach(), packed, self.size_epsilion,
+                                                  self.search_margin_ulps, self.grid_max_cells)
             self._dev_cache = (tri, norm, category, packed)
         return self._dev_cache
+
+    @property
+    def grid(self):
+        """The acceleration grid of the current merged triangles (None in brute-force mode)."""
+        self.merged_device_arrays()
+        return getattr(self, "_grid", None)
 
     def intersect(self, rays):
         """Nearest valid intersection of each ray with the merged triangles
@@ -357,14 +478,15 @@ class OpticalSystem3D(OpticalSystemBase):
              result["gather_trig"]) = self._intersection(
                 *[rays[k] for k in RAY_FIELDS_3D], *[self._merged[k] for k in TRI_FIELDS],
                 self.intersect_epsilion, self.size_epsilion, self.ray_start_epsilion,
-                _packed=self.merged_device_arrays()[3], _margin_ulps=self.search_margin_ulps)
+                _packed=self.merged_device_arrays()[3], _margin_ulps=self.search_margin_ulps,
+                _grid=self.grid)
             result["norm"] = self._merged["norm"][result["gather_trig"]]
         return result
 
     @staticmethod
     def _intersection(rx1, ry1, rz1, rx2, ry2, rz2, xp, yp, zp, x1, y1, z1, x2, y2, z2,
                       intersect_epsilion, size_epsilion, ray_start_epsilion, _packed=None,
-                      _margin_ulps=kernels.DEFAULT_MARGIN_ULPS):
+                      _margin_ulps=kernels.DEFAULT_MARGIN_ULPS, _grid=None):
         """The intersection seam (tfrt/engine.py:1102-1166): N rays x M triangles -> per-ray
         nearest hit.  The search runs in the CUDA kernel; the gathered values are then
         re-evaluated 1-to-1 in torch so they carry the reference's gradient (through ray_u
@@ -374,7 +496,7 @@ class OpticalSystem3D(OpticalSystemBase):
         if _packed is None:
             _packed = kernels.pack_triangles(tri, size_epsilion, _margin_ulps)
         raw = kernels.intersect3d(rays, tri, _packed, intersect_epsilion, size_epsilion,
-                                  ray_start_epsilion, _margin_ulps)
+                                  ray_start_epsilion, _margin_ulps, grid=_grid)
         g = raw["gather_trig"]
         # the 1-to-1 evaluation runs in fp64 on the fp32 fields, like the kernels' per-ray
         # arithmetic, and is stored back as fp32
@@ -882,7 +1004,7 @@ class OpticalEngine:
             category=category, n_optical=system._optical_count, max_iterations=max_iterations,
             intersect_eps=system.intersect_epsilion, size_eps=system.size_epsilion,
             ray_start_eps=system.ray_start_epsilion, new_ray_length=self.new_ray_length,
-            margin_ulps=system.search_margin_ulps,
+            margin_ulps=system.search_margin_ulps, grid=system.grid,
             dead_ray_length=self.dead_ray_length if bool(self.dead_ray_length) else None,
             compile=compile_sets, **kw)
         plan.packed = packed

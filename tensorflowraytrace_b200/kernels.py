@@ -17,7 +17,12 @@ HISTORY = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream as a raw handle (torch's fast accessor: this is called for every
+    launch, and torch.cuda.current_stream() costs ~15 us of Python)."""
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:  # pragma: no cover
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _require_cuda(*tensors):
@@ -102,11 +107,46 @@ def pack_triangles(tri, size_eps, margin_ulps=DEFAULT_MARGIN_ULPS):
     return packed
 
 
+DEFAULT_GRID_MAX_CELLS = 1 << 21
+
+
+class TriangleGrid:
+    """Uniform grid over a packed triangle set (csrc/grid3d.cu), built on the device: the
+    optional acceleration structure of the nearest-hit search.  Same hits as the brute-force
+    search; not the path the tests/s metric is quoted on."""
+
+    def __init__(self, tri, packed, size_eps, margin_ulps=DEFAULT_MARGIN_ULPS,
+                 max_cells=DEFAULT_GRID_MAX_CELLS):
+        _require_cuda(tri, packed)
+        tri = _f32(tri)
+        self.n_tri, self.max_cells = int(tri.shape[1]), int(max_cells)
+        lib = _lib.load()
+        self.workspace = torch.empty((lib.tfrt_grid_bytes(self.n_tri, self.max_cells),),
+                                     dtype=torch.uint8, device=tri.device)
+        check(lib.tfrt_grid_build(ptr_array([tri[i] for i in range(9)], 9), ptr(packed),
+                                  self.n_tri, ctypes.c_float(size_eps),
+                                  ctypes.c_float(margin_ulps), self.max_cells,
+                                  ptr(self.workspace), _stream()), "tfrt_grid_build")
+
+    def data_ptr(self):
+        return self.workspace.data_ptr()
+
+    def stats(self):
+        """dict: dims, cells, entries, large triangles, overflow, typical extent (waits)."""
+        out = (ctypes.c_int64 * 8)()
+        check(_lib.load().tfrt_grid_stats(ptr(self.workspace), self.n_tri, self.max_cells, out,
+                                          _stream()), "tfrt_grid_stats")
+        return {"dims": (int(out[0]), int(out[1]), int(out[2])), "cells": int(out[3]),
+                "entries": int(out[4]), "large": int(out[5]), "overflow": int(out[6]),
+                "typical_extent": out[7] * 1e-6}
+
+
 def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps,
-                margin_ulps=DEFAULT_MARGIN_ULPS, diag=None):
+                margin_ulps=DEFAULT_MARGIN_ULPS, diag=None, grid=None):
     """b1 seam: nearest valid hit per ray.  rays (6,N) f32, tri (9,T) f32.  Returns a dict with the
     reference's field names (tfrt/engine.py:1026-1043, without `norm`).  diag: optional (4,) int32
-    cuda tensor receiving the re-validation counters (include/tfrt_b200.h)."""
+    cuda tensor receiving the re-validation counters (include/tfrt_b200.h).  grid: optional
+    TriangleGrid of the same triangles (the search walks it instead of testing them all)."""
     _require_cuda(rays, tri, packed)
     rays, tri = _f32(rays), _f32(tri)
     N, T = rays.shape[1], tri.shape[1]
@@ -121,7 +161,9 @@ def intersect3d(rays, tri, packed, intersect_eps, size_eps, ray_start_eps,
         ptr(packed), T, ctypes.c_float(intersect_eps), ctypes.c_float(size_eps),
         ctypes.c_float(ray_start_eps), ctypes.c_float(margin_ulps), ptr(hit), ptr(out["x"]),
         ptr(out["y"]), ptr(out["z"]), ptr(valid), ptr(out["ray_u"]), ptr(out["trig_u"]),
-        ptr(out["trig_v"]), ptr(gather_trig), ptr(diag), _stream()), "tfrt_intersect3d")
+        ptr(out["trig_v"]), ptr(gather_trig), ptr(diag),
+        ctypes.c_void_p(0 if grid is None else grid.data_ptr()),
+        0 if grid is None else grid.max_cells, _stream()), "tfrt_intersect3d")
     out["valid"] = valid.bool()
     out["gather_trig"] = gather_trig.long()
     out["gather_ray"] = torch.arange(N, device=dev)
@@ -137,6 +179,43 @@ def material_table(descriptors, device):
             arr[i].c[j] = float(coef[j]) if j < len(coef) else 0.0
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
     return torch.from_numpy(raw).to(device)
+
+
+# ==============================================================================================
+# rays born on the device (csrc/sources.cu)
+
+def sample_uniform(seed, stream, epoch, which, first, n, lo, hi, device):
+    """(n,) f32: lo + (hi - lo) U for the global sample indices first .. first + n - 1."""
+    out = torch.empty((int(n),), dtype=torch.float32, device=device)
+    check(_lib.load().tfrt_sample_uniform(seed, stream, epoch, which, int(first), int(n),
+                                          float(lo), float(hi), ptr(out), _stream()),
+          "tfrt_sample_uniform")
+    return out
+
+
+def sample_square(seed, stream, epoch, first, n, x_size, y_size, device):
+    """RandomUniformSquare on the device: (points (n,2), ranks (n,2))."""
+    points = torch.empty((int(n), 2), dtype=torch.float32, device=device)
+    ranks = torch.empty((int(n), 2), dtype=torch.float32, device=device)
+    check(_lib.load().tfrt_sample_square(seed, stream, epoch, int(first), int(n), float(x_size),
+                                         float(y_size), ptr(points), ptr(ranks), _stream()),
+          "tfrt_sample_square")
+    return points, ranks
+
+
+SPHERE_MODES = {"random_uniform": 0, "random_lambertian": 1, "static_uniform": 2,
+                "static_lambertian": 3}
+
+
+def sample_sphere(seed, stream, epoch, mode, first, n, total, angular_size, radius, device):
+    """Sphere distributions on the device: (points (n,3), ranks (n,2) = (phi, theta))."""
+    points = torch.empty((int(n), 3), dtype=torch.float32, device=device)
+    ranks = torch.empty((int(n), 2), dtype=torch.float32, device=device)
+    check(_lib.load().tfrt_sample_sphere(seed, stream, epoch, SPHERE_MODES[mode], int(first),
+                                         int(n), int(total), float(angular_size), float(radius),
+                                         ptr(points), ptr(ranks), _stream()),
+          "tfrt_sample_sphere")
+    return points, ranks
 
 
 class TraceWorkspace:
@@ -186,8 +265,9 @@ class Trace3D:
                  mat_in=None, mat_out=None, n_in=None, n_out=None, materials=None, n_materials=0,
                  n_table=None, lambda_index=None,
                  intersect_eps=1e-10, size_eps=1e-10, ray_start_eps=1e-10, new_ray_length=1.0,
-                 margin_ulps=DEFAULT_MARGIN_ULPS, workspace=None):
+                 margin_ulps=DEFAULT_MARGIN_ULPS, workspace=None, grid=None):
         _require_cuda(src, tri, norm, category)   # norm may be None: geometric normals
+        self.grid = grid
         self.src = _f32(src)          # (7,N): x_start..z_end, wavelength
         self.tri = _f32(tri)          # (9,T)
         self.norm = None if norm is None else _f32(norm)        # (T,3)
@@ -240,6 +320,8 @@ class Trace3D:
         a.mat_in, a.mat_out, a.n_in, a.n_out = p(self.mat_in), p(self.mat_out), p(self.n_in), p(self.n_out)
         a.materials, a.n_table, a.lambda_index = p(materials), p(self.n_table), p(self.lambda_index)
         a.packed = self.packed.data_ptr()
+        a.grid = 0 if grid is None else grid.data_ptr()
+        a.grid_max_cells = 0 if grid is None else grid.max_cells
         n1 = max(N, 1)
         cur0, curd = ws.cur.data_ptr(), ws.cur_d.data_ptr()
         for i in range(6):

@@ -138,20 +138,30 @@ def config2(ray_count=65536, step_count=13):
     }
 
 
-def lens_optimize_config(ray_count, step_count, seed=1234, name="cfg3"):
+LENS_SOURCE = dict(source_distance=4.0, magnification=2.0, object_size=0.2,
+                   cone=math.pi / 16.0, wavelength=YELLOW)
+
+
+def lens_optimize_config(ray_count, step_count, seed=1234, name="cfg3", with_rays=True):
     """Imaging-lens optimisation scene (dev/simple_3d_optimize.py:22-89, 128-140):
     undense angular source at x=-4, lens at x=0..0.2, target at x=8, per-ray goal
-    = -(magnification * object_size) * rank."""
-    rng = np.random.default_rng(seed)
-    source_distance, magnification, object_size = 4.0, 2.0, 0.2
-    base, rank = random_uniform_square(object_size, ray_count, rng)
-    dirs = random_uniform_sphere(math.pi / 16.0, ray_count, rng)
-    starts = np.stack([np.full(ray_count, -source_distance), base[:, 0], base[:, 1]], axis=1)
-    sources = make_rays(starts, dirs, YELLOW, extra={"rank": rank})
+    = -(magnification * object_size) * rank.  with_rays=False leaves the source rays out (the
+    caller generates them on the device, `lens_optimize_device_source`)."""
+    source_distance, magnification, object_size = (
+        LENS_SOURCE["source_distance"], LENS_SOURCE["magnification"], LENS_SOURCE["object_size"])
+    sources = {}
+    if with_rays:
+        rng = np.random.default_rng(seed)
+        base, rank = random_uniform_square(object_size, ray_count, rng)
+        dirs = random_uniform_sphere(LENS_SOURCE["cone"], ray_count, rng)
+        starts = np.stack([np.full(ray_count, -source_distance), base[:, 0], base[:, 1]], axis=1)
+        sources = make_rays(starts, dirs, YELLOW, extra={"rank": rank})
     tv, tf_ = mesh_tools.plane_mesh((source_distance * magnification, 0.0, 0.0), 50.0, axis=0)
     return {
         "name": f"{name}_lens_optimize_{ray_count}rays_hex{step_count}",
         "dimension": 3,
+        "ray_count": int(ray_count),
+        "seed": int(seed),
         "sources": sources,
         "surfaces": lens_surfaces(step_count),
         "targets": [static_mesh(tv, tf_)],
@@ -162,12 +172,31 @@ def lens_optimize_config(ray_count, step_count, seed=1234, name="cfg3"):
     }
 
 
-def config3(ray_count=1048576, step_count=41, seed=1234):
-    return lens_optimize_config(ray_count, step_count, seed, "cfg3")
+def config3(ray_count=1048576, step_count=41, seed=1234, with_rays=True):
+    return lens_optimize_config(ray_count, step_count, seed, "cfg3", with_rays)
 
 
-def config5(ray_count=16777216, step_count=91, seed=1234):
-    return lens_optimize_config(ray_count, step_count, seed, "cfg5")
+def config5(ray_count=16777216, step_count=91, seed=1234, with_rays=True):
+    return lens_optimize_config(ray_count, step_count, seed, "cfg5", with_rays)
+
+
+def lens_optimize_device_source(ray_count, seed=1234):
+    """The source of the lens-optimisation scene as the reference's scripts build it
+    (dev/simple_3d_optimize.py:22-57): an undense AngularSource pairing RandomUniformSquare base
+    points (in the y-z plane at x = -4) with RandomUniformSphere directions, the base points'
+    ranks published as the `rank` field.  Everything is sampled on the GPU, afresh at every
+    update() like the reference's (tfrt/optimizer.py:217), by the counter-based kernels of
+    csrc/sources.cu, so a rank of a sharded job generates only -- and exactly -- its rays."""
+    from . import distributions as D
+    from . import sources
+    D.seed_all(seed)
+    base = D.RandomUniformSquare(LENS_SOURCE["object_size"], int(ray_count),
+                                 LENS_SOURCE["object_size"], 1)
+    ang = D.RandomUniformSphere(LENS_SOURCE["cone"], int(ray_count))
+    return sources.AngularSource(
+        3, (-LENS_SOURCE["source_distance"], 0.0, 0.0), (1.0, 0.0, 0.0), ang, base,
+        [LENS_SOURCE["wavelength"]], dense=False,
+        extra_fields={"rank": ("base_point", base, "ranks")})
 
 
 def config4(ray_count=4194304, theta_res=100, z_res=250, seed=4321, max_iterations=16):
@@ -398,7 +427,7 @@ def triangle_count(scene):
 
 # ----------------------------------------------------------------------------- public-API build
 
-def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, **engine_kwargs):
+def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, source=None, **engine_kwargs):
     """Instantiate a scene through the public API (boundaries / sources / OpticalSystem3D /
     OpticalEngine with one StandardReaction), the way the reference's scripts do
     (dev/simple_3d_optimize.py:69-120).  Returns (engine, parameters, source).
@@ -406,6 +435,8 @@ def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, **engine_kwarg
     ray_slice : optional slice of the source rays (parity sub-samples).
     ray_shard : optional (rank, world_size) for multi-GPU ray sharding.
     eps       : optional dict intersect_epsilion / size_epsilion / ray_start_epsilion.
+    source    : optional source object used instead of a ManualSource fed with scene["sources"]
+                (e.g. `lens_optimize_device_source`: rays born on the device at every update).
     """
     from . import boundaries, engine as eng, materials, operation, sources
 
@@ -424,8 +455,11 @@ def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, **engine_kwarg
         return [boundaries.ManualTriangleBoundary(
             mesh=boundaries.TriangleMesh(m["vertices"], m["faces"])) for m in lst]
 
-    src = sources.ManualSource(3)
-    src.feed({k: (v if ray_slice is None else v[ray_slice]) for k, v in scene["sources"].items()})
+    if source is not None:
+        src = source
+    else:
+        src = sources.ManualSource(3)
+        src.feed({k: (v if ray_slice is None else v[ray_slice]) for k, v in scene["sources"].items()})
 
     system = eng.OpticalSystem3D(ray_shard=ray_shard, **(eps or {}))
     system.optical = optical
@@ -434,7 +468,7 @@ def build_engine(scene, ray_slice=None, ray_shard=None, eps=None, **engine_kwarg
     system.sources = [src]
     system.materials = [{"n": materials.BY_NAME[name]} for name in scene["materials"]]
     system.update()
-    inherit = {k for k in scene["sources"] if k not in
+    inherit = {k for k in src.keys() if k not in
                ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")}
     engine = eng.OpticalEngine(3, [operation.StandardReaction()],
                                simple_ray_inheritance=inherit, **engine_kwargs)

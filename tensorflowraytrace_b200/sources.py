@@ -161,6 +161,32 @@ class SourceBase(RecursivelyUpdatable):
             self.update()
         return {field: data.clone() for field, data in self.items()}
 
+    # ------------------------------------------------------------------ multi-GPU ray sharding
+    def set_ray_shard(self, rank, world_size):
+        """Ask the source to generate only rank `rank`'s contiguous block of its rays (from the
+        next update() on) instead of all of them.  Returns True when it can: its distributions
+        are then sampled for that slice only -- counter-based, so the ranks of a job together
+        produce exactly the rays a single rank would (csrc/sources.cu).  False: the caller
+        slices the full ray set itself (OpticalSystemBase._amalgamate_sources)."""
+        return False
+
+    def _extra_domains_block_shard(self):
+        """Extra fields must follow a distribution (a 3-tuple naming an object's attribute, e.g.
+        its ranks) or be scalars: a fixed full-length array could not be sliced here."""
+        for items in self._extra_fields.values():
+            if len(items) == 2:
+                v = items[1]
+                if callable(v):
+                    return True
+                t = torch.as_tensor(v) if not torch.is_tensor(v) else v
+                if t.dim() > 0 and t.shape[0] > 1:
+                    return True
+        return False
+
+    def _shardable_wavelengths(self):
+        w = getattr(self, "_wavelengths", None)
+        return w is None or w.dim() == 0 or w.shape[0] <= 1
+
     # ------------------------------------------------------------------ dict protocol
     @property
     def extra_fields(self):
@@ -350,6 +376,15 @@ class PointSource(_DirectedSource):
     def _generate_update_handles(self):
         return [self._angular_distribution.update]
 
+    def set_ray_shard(self, rank, world_size):
+        # rays = angles (x a single wavelength): shard the angular distribution
+        if not self._shardable_wavelengths() or self._extra_domains_block_shard():
+            return False
+        if not getattr(self._angular_distribution, "set_shard", lambda *a: False)(rank, world_size):
+            return False
+        self.resize()
+        return True
+
     @property
     def center(self):
         return self._center
@@ -396,6 +431,20 @@ class AngularSource(_DirectedSource):
 
     def _generate_update_handles(self):
         return [self._angular_distribution.update, self._base_point_distribution.update]
+
+    def set_ray_shard(self, rank, world_size):
+        # paired (undense) base points and angles: shard both distributions alike
+        if self.dense or not self._shardable_wavelengths() or self._extra_domains_block_shard():
+            return False
+        dists = (self._angular_distribution, self._base_point_distribution)
+        if not all(getattr(d, "supports_shard", False) for d in dists):
+            return False
+        if not all(d.set_shard(rank, world_size) for d in dists):
+            for d in dists:
+                d.set_shard(0, 1)
+            return False
+        self.resize()
+        return True
 
     @property
     def center(self):

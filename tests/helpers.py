@@ -68,9 +68,11 @@ def oracle_from_scene(scene, ray_slice=None, requires_grad=False, eps=EPS, round
 ATOL_FRACTION = 0.1
 
 
-def rel_err(a, b, floor=ATOL_FRACTION):
+def rel_err(a, b, floor=ATOL_FRACTION, scale=None):
     """Elementwise relative error with an absolute floor:  max_i |a_i - b_i| / (|b_i| + atol),
-    atol = `floor` x the largest |b|.  `rel_err(a, b) < rtol` is therefore the elementwise bound
+    atol = `floor` x the largest |b| (or x `scale`, the coordinate scale of the scene, when the
+    array is one coordinate of points whose other coordinates are larger: fp32 fields carry an
+    absolute error of an ulp of the scene's coordinates).  `rel_err(a, b) < rtol` is therefore the elementwise bound
     |a_i - b_i| <= rtol |b_i| + rtol x 0.1 x max|b|: every entry is held to the north star's
     relative tolerance against its own magnitude, and entries much smaller than the array's
     scale (a coordinate that happens to be ~0, a gradient entry that cancels) against a tenth
@@ -79,7 +81,7 @@ def rel_err(a, b, floor=ATOL_FRACTION):
     b = np.asarray(b, dtype=np.float64)
     if not a.size:
         return 0.0
-    atol = max(floor * np.max(np.abs(b)), 1e-30)
+    atol = max(floor * max(np.max(np.abs(b)), scale or 0.0), 1e-30)
     return float(np.max(np.abs(a - b) / (np.abs(b) + atol)))
 
 

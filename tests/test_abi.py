@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.TfrtMaterial) == 8 + 7 * 8
     a = _lib.TfrtTrace3DArgs()
     assert ctypes.sizeof(a) % 8 == 0
-    assert _lib.TfrtTrace3DArgs.src.offset == 48     # 12 leading 4-byte scalars
+    assert _lib.TfrtTrace3DArgs.src.offset == 56     # 13 leading 4-byte scalars, padded to 8
     lib = _lib.load()
     for code, mirror in enumerate(_lib.STRUCT_MIRRORS):
         assert lib.tfrt_struct_size(code) == ctypes.sizeof(mirror), mirror.__name__

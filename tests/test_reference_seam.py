@@ -84,13 +84,20 @@ def test_reference_engine_with_the_cuda_seam_reproduces_the_reference(name):
         s = getattr(eng, set_name + "_rays")
         assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
         for f in helpers.RAY_FIELDS:
-            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"],
+                                   scale=_coordinate_scale(want, set_name, helpers.RAY_FIELDS)) < 1e-5, (set_name, f)
         checked += 1
     assert checked >= 2
     if grads is not None:
         assert abs(float(error.sum().detach()) - float(want["loss"])) < 1e-5 * float(want["loss"])
         for i, g in enumerate(grads):
             assert helpers.rel_err(g.numpy(), want[f"grad_{i}"]) < 1e-4, i
+
+
+def _coordinate_scale(want, set_name, fields):
+    """Largest |coordinate| of a ray set: what an fp32 field's absolute error is relative to."""
+    return max(float(np.max(np.abs(want[f"{set_name}_{f}"]))) if want[f"{set_name}_{f}"].size else 0.0
+               for f in fields if f.endswith(("_start", "_end")))
 
 
 def _cuda_intersect_2d():
@@ -155,7 +162,8 @@ def test_reference_2d_engine_with_the_cuda_seam_reproduces_the_reference(name):
         s = getattr(eng, set_name + "_rays")
         assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
         for f in helpers.RAY_FIELDS_2D:
-            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"],
+                                   scale=_coordinate_scale(want, set_name, helpers.RAY_FIELDS_2D)) < 1e-5, (set_name, f)
         checked += 1
     assert checked >= 2
 
@@ -199,4 +207,5 @@ def test_reference_2d_engine_with_per_geometry_cuda_seams(name):
         s = getattr(eng, set_name + "_rays")
         assert np.array_equal(s["slot"].numpy().astype(np.int64), want[f"{set_name}_slot"]), set_name
         for f in helpers.RAY_FIELDS_2D:
-            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"]) < 1e-5, (set_name, f)
+            assert helpers.rel_err(s[f].numpy(), want[f"{set_name}_{f}"],
+                                   scale=_coordinate_scale(want, set_name, helpers.RAY_FIELDS_2D)) < 1e-5, (set_name, f)
