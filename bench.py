@@ -606,6 +606,8 @@ def run_ours(args):
                     "us_per_trace is the public-API call (system.update + ray_trace, host "
                     "bookkeeping included), us_per_trace_kernel_only the C-ABI launch alone "
                     "(status memset + k_trace2d_forward)"}
+    if scene["dimension"] == 2 and rank == 0 and world == 1:
+        line["two_d_at_scale"] = two_d_at_scale(torch, scenes, not args.no_cpu_baseline)
     if backward:
         # the backward leg (loss + K2 + K3 backward + all-reduce) timed on its own with CUDA
         # events around autograd, forward outside the timed span
@@ -694,6 +696,52 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def two_d_at_scale(torch, scenes, with_cpu):
+    """the four sizes of the reference's own scaling script
+    (dev/performance.py:77-86: 10 / 10 000 beam points x 6 wavelengths, 10 / 1 000 segments, 2
+    iterations), through the public API (update + ray_trace + finished rays) and as the bare
+    C-ABI launch, beside the CPU port of the reference's algorithm (oracle/engine2d.py)."""
+    rows = []
+    for beams, points in ((10, 11), (10000, 11), (10, 1001), (10000, 1001)):
+        scene = scenes.performance_2d(beams, points)
+        engine, _, _ = scenes.build_engine_2d(scene, compile_active_rays=False)
+
+        def api():
+            engine.optical_system.update()
+            engine.ray_trace(2)
+            return engine.finished_rays["x_end"]
+
+        for _ in range(3):
+            api()
+        torch.cuda.synchronize()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            api()
+        torch.cuda.synchronize()
+        api_s = (time.perf_counter() - t0) / reps
+        tr = engine.last_trace
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tr.forward()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            tr.forward()
+        e1.record()
+        torch.cuda.synchronize()
+        row = {"rays": beams * 6, "segments": points - 1 + 1, "iterations": 2,
+               "us_per_trace_public_api": 1e6 * api_s,
+               "us_per_trace_kernel_only": 1e3 * e0.elapsed_time(e1) / reps}
+        if with_cpu and beams * (points - 1) <= 2_500_000:
+            import helpers
+            t0 = time.perf_counter()
+            eng, _ = helpers.oracle2d_from_scene(scene, compile_active_rays=False)
+            eng.ray_trace(2)
+            row["cpu_port_us_per_trace"] = 1e6 * (time.perf_counter() - t0)
+        rows.append(row)
+    return rows
 
 
 def intersect_traffic(n_rays):

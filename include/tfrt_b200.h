@@ -239,7 +239,8 @@ int tfrt_materialize3d(const TfrtTrace3DArgs *args, const int32_t *counters_host
 typedef struct {
     const float *g_hist[4][6];
     double *g_acc;            /* T*12 */
-    float *g_ray_ws;          /* 6*N workspace (per-slot running cotangent of the live ray) */
+    float *g_ray_ws;          /* unused (kept for layout compatibility; may be NULL): the running
+                                 cotangent of a ray now lives in registers */
     float *g_tri_out[9];
     float *g_norm_out;
     float *g_src[6];
@@ -251,6 +252,9 @@ typedef struct {
                                  every finished ray into the few target triangles. */
 } TfrtTrace3DBwdArgs;
 
+/* One launch walks every ray's iterations in reverse (plus a memset and the fp64 -> fp32
+ * rounding of the accumulators); the iteration counts are read on the device, `counters_host` is
+ * ignored (may be NULL). */
 int tfrt_trace3d_backward(const TfrtTrace3DArgs *fwd, const int32_t *counters_host,
                           const TfrtTrace3DBwdArgs *bwd, void *stream);
 

@@ -27,15 +27,13 @@ namespace {
 constexpr int kBwdThreads = 256;
 
 struct BwdParams {
-    int n_rays, k, is_last, index_mode, n_grad_tri;
-    int n_live;
-    int active_offset;          // position of this iteration's first ray in the active history
+    int n_rays, n_iters, index_mode, n_grad_tri;
     double new_ray_length, dead_ray_length;
-    const int32_t *live;        // live[k]
-    const float *tape_f;        // tape_f + k*9*N
-    const int32_t *tape_tri;
-    const uint8_t *tape_status;
-    const int32_t *tape_outpos;
+    const int32_t *counters;    // (K+1)*4 device counters of the forward pass
+    const float *tape_f;        // K*9*N
+    const int32_t *tape_tri;    // K*N
+    const uint8_t *tape_status; // K*N
+    const int32_t *tape_outpos; // K*N
     const float *g_hist[4][6];
     const float *tri[9];
     const float *norm;
@@ -46,7 +44,6 @@ struct BwdParams {
     const double *n_table;      // optional tabulated indices (see TfrtTrace3DArgs)
     const int32_t *lambda_index;
     int n_lambda;
-    float *g_ray[6];            // running cotangent of the ray entering iteration k+1 / k
     double *g_acc;              // T*12
     float *g_src[6];            // written at k == 0 when non-null
 };
@@ -72,21 +69,43 @@ __device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double
     }
 }
 
+// One thread per source ray walks its iterations in reverse (a ray is live for a prefix
+// 0 .. k_last of the iterations); the running cotangent of the ray stays in registers, the
+// tape is read slot-indexed (coalesced), and each iteration's triangle cotangents are combined
+// across the lanes that hit the same triangle before the fp64 atomics.  One launch per trace.
 __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
-    const int p = blockIdx.x * kBwdThreads + threadIdx.x;
+    const int slot = blockIdx.x * kBwdThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const size_t N = (size_t)P.n_rays;
+    const int K = P.n_iters;
+    const bool mine = slot < P.n_rays;
+    // last iteration this ray took part in (-1: never; not possible for a source ray)
+    int k_last = -1;
+    if (mine) {
+        for (int k = K - 1; k >= 0; --k)
+            if (P.tape_status[(size_t)k * N + slot] != 255) { k_last = k; break; }
+    }
+    int k_top = k_last;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) k_top = max(k_top, __shfl_xor_sync(0xffffffffu, k_top, off));
+    // position of iteration k's first ray in the active history = rays that reacted before k
+    long long active_before = 0;
+    for (int j = 0; j <= k_top; ++j) active_before += P.counters[(j + 1) * 4 + 0];
+    double gSn[3] = {0, 0, 0}, gEn[3] = {0, 0, 0};   // cotangent of the ray leaving iteration k
+
+    for (int k = k_top; k >= 0; --k) {
+    active_before -= P.counters[(k + 1) * 4 + 0];
+    const int active_offset = (int)active_before;
     bool contributes = false;
     int tri = -1;
     double acc[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) acc[c] = 0.0;
 
-    if (p < P.n_live) {
-        const int slot = P.live[p];
-        const int status = P.tape_status[slot];
-        tri = P.tape_tri[slot];
-        const float *tf = P.tape_f;
+    if (mine && k <= k_last) {
+        const int status = P.tape_status[(size_t)k * N + slot];
+        tri = P.tape_tri[(size_t)k * N + slot];
+        const float *tf = P.tape_f + (size_t)k * 9 * N;
         const double S[3] = {tf[0 * N + slot], tf[1 * N + slot], tf[2 * N + slot]};
         const double Pt[3] = {tf[3 * N + slot], tf[4 * N + slot], tf[5 * N + slot]};
         const double t = tf[6 * N + slot], u = tf[7 * N + slot], v = tf[8 * N + slot];
@@ -94,7 +113,8 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
         // cotangent of this iteration's history record (start, projected end)
         double ghS[3] = {0, 0, 0}, ghP[3] = {0, 0, 0};
         {
-            const int pos = P.tape_outpos[slot] + (status == TFRT_STATUS_ACTIVE ? P.active_offset : 0);
+            const int pos = P.tape_outpos[(size_t)k * N + slot] +
+                            (status == TFRT_STATUS_ACTIVE ? active_offset : 0);
             const float *const *g = P.g_hist[status];
             for (int c = 0; c < 3; ++c) {
                 if (g[c]) ghS[c] = g[c][pos];
@@ -125,11 +145,8 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
             double gSd[3] = {ghS[0], ghS[1], ghS[2]};
             double gnA[3] = {0, 0, 0}, gnB[3] = {0, 0, 0}, gnC[3] = {0, 0, 0};   // via the normal
             if (status == TFRT_STATUS_ACTIVE) {
-                double gSn[3], gEn[3];
-                for (int c = 0; c < 3; ++c) {
-                    gSn[c] = P.is_last ? 0.0 : (double)P.g_ray[c][slot];
-                    gEn[c] = P.is_last ? 0.0 : (double)P.g_ray[3 + c][slot];
-                }
+                // (gSn, gEn): cotangent of the reacted ray, left by iteration k + 1 of this slot
+                // (zero when that iteration was not executed)
                 double gw[3];
                 for (int c = 0; c < 3; ++c) {
                     gw[c] = P.new_ray_length * gEn[c];
@@ -252,9 +269,9 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
             contributes = tri < P.n_grad_tri;
         }
         for (int c = 0; c < 3; ++c) {
-            P.g_ray[c][slot] = (float)gS[c];
-            P.g_ray[3 + c][slot] = (float)gE[c];
-            if (P.k == 0 && P.g_src[c]) {
+            gSn[c] = gS[c];
+            gEn[c] = gE[c];
+            if (k == 0 && P.g_src[c]) {
                 P.g_src[c][slot] = (float)gS[c];
                 P.g_src[3 + c][slot] = (float)gE[c];
             }
@@ -263,17 +280,19 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
 
     // warp-aggregated fp64 atomics into the per-triangle accumulators
     const unsigned active = __ballot_sync(0xffffffffu, contributes);
-    if (active == 0) return;
-    const int key = contributes ? tri : -1 - lane;   // non-contributors never match anybody
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    bool is_leader = false;
-    aggregate_peers(peers, lane, acc, is_leader);
-    if (contributes && is_leader) {
-        double *dst = P.g_acc + (size_t)tri * 12;
+    if (active != 0) {
+        const int key = contributes ? tri : -1 - lane;   // non-contributors never match anybody
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        bool is_leader = false;
+        aggregate_peers(peers, lane, acc, is_leader);
+        if (contributes && is_leader) {
+            double *dst = P.g_acc + (size_t)tri * 12;
 #pragma unroll
-        for (int c = 0; c < 12; ++c)
-            if (acc[c] != 0.0) atomicAdd(dst + c, acc[c]);
+            for (int c = 0; c < 12; ++c)
+                if (acc[c] != 0.0) atomicAdd(dst + c, acc[c]);
+        }
     }
+    }   // iterations, in reverse
 }
 
 __global__ void k_finish_tri_grads(const double *__restrict__ g_acc, int n_tri, float *o0,
@@ -292,37 +311,25 @@ __global__ void k_finish_tri_grads(const double *__restrict__ g_acc, int n_tri, 
 
 extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch,
                                      const TfrtTrace3DBwdArgs *b, void *stream) {
-    TFRT_REQUIRE(a && ch && b, "tfrt_trace3d_backward: null argument");
-    TFRT_REQUIRE(b->g_acc && b->g_ray_ws && b->g_norm_out, "tfrt_trace3d_backward: null workspace");
+    (void)ch;   // the iteration counts are read on the device: the call needs no host copy
+    TFRT_REQUIRE(a && b, "tfrt_trace3d_backward: null argument");
+    TFRT_REQUIRE(b->g_acc && b->g_norm_out, "tfrt_trace3d_backward: null workspace");
     for (int c = 0; c < 9; ++c)
         TFRT_REQUIRE(b->g_tri_out[c], "tfrt_trace3d_backward: null g_tri_out[%d]", c);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = a->n_rays, K = a->max_iterations, T = a->n_tri;
     TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_acc, 0, sizeof(double) * 12 * (size_t)T, st));
     if (N > 0) {
-        TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_ray_ws, 0, sizeof(float) * 6 * (size_t)N, st));
         for (int c = 0; c < 6; ++c)
             if (b->g_src[c]) TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_src[c], 0, sizeof(float) * N, st));
-    }
-    // active-history offsets per iteration
-    long long active_before = 0;
-    for (int k = 0; k < K; ++k) active_before += ch[(k + 1) * 4 + 0];
-    for (int k = K - 1; k >= 0; --k) {
-        active_before -= ch[(k + 1) * 4 + 0];
-        const int n_live = ch[k * 4 + 0];
-        if (n_live <= 0) continue;
         BwdParams P;
-        P.n_rays = N; P.k = k; P.is_last = (k == K - 1); P.index_mode = a->index_mode;
-        P.n_live = n_live;
+        P.n_rays = N; P.n_iters = K; P.index_mode = a->index_mode;
         P.n_grad_tri = b->n_grad_tri > 0 ? b->n_grad_tri : T;
-        P.active_offset = (int)active_before;
         P.new_ray_length = a->new_ray_length;
         P.dead_ray_length = b->dead_ray_length;
-        P.live = a->live + (size_t)k * N;
-        P.tape_f = a->tape_f + (size_t)k * 9 * N;
-        P.tape_tri = a->tape_tri + (size_t)k * N;
-        P.tape_status = a->tape_status + (size_t)k * N;
-        P.tape_outpos = a->tape_outpos + (size_t)k * N;
+        P.counters = a->counters;
+        P.tape_f = a->tape_f; P.tape_tri = a->tape_tri;
+        P.tape_status = a->tape_status; P.tape_outpos = a->tape_outpos;
         for (int w = 0; w < 4; ++w)
             for (int c = 0; c < 6; ++c) P.g_hist[w][c] = b->g_hist[w][c];
         for (int c = 0; c < 9; ++c) P.tri[c] = a->tri[c];
@@ -330,12 +337,9 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         P.mat_in = a->mat_in; P.mat_out = a->mat_out; P.n_in = a->n_in; P.n_out = a->n_out;
         P.materials = a->materials;
         P.n_table = a->n_table; P.lambda_index = a->lambda_index; P.n_lambda = a->n_lambda;
-        for (int c = 0; c < 6; ++c) {
-            P.g_ray[c] = b->g_ray_ws + (size_t)c * N;
-            P.g_src[c] = b->g_src[c];
-        }
+        for (int c = 0; c < 6; ++c) P.g_src[c] = b->g_src[c];
         P.g_acc = b->g_acc;
-        k_backward3d<<<tfrt_div_up(n_live, kBwdThreads), kBwdThreads, 0, st>>>(P);
+        k_backward3d<<<tfrt_div_up(N, kBwdThreads), kBwdThreads, 0, st>>>(P);
         tfrt_note_launch(1);
     }
     k_finish_tri_grads<<<tfrt_div_up(T, 256), 256, 0, st>>>(

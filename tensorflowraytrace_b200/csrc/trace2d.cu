@@ -11,10 +11,14 @@
 //   StandardReaction.main (2D)             tfrt/operation.py:255-307
 //   geometry.snells_law_2D                 tfrt/geometry.py:565-653
 //
-// The 2D workloads of the reference are tiny (config 1: 1 000 rays x 3 segments x 3
-// iterations) and launch-latency bound, so the design goal is ONE launch per trace, not FMA
-// throughput: a thread owns one source ray and follows it through every iteration (rays never
-// split or interact), scanning all segments and arcs each time.  All arithmetic is fp64 on the
+// The 2D workloads of the reference are small (config 1: 1 000 rays x 3 segments x 3
+// iterations; dev/performance.py:77-86 goes up to 10 000 rays x 1 001 segments) and
+// launch-latency bound, so the design goal is ONE launch per trace: a ray is followed through
+// every iteration (rays never split or interact) by a group of LANES threads (1, 4 or 32, chosen
+// from the ray and boundary counts) that share the scan over the boundaries -- each lane takes
+// every LANES-th segment / arc, then the group reduces to the nearest hit with shuffles (lowest
+// index on exact ties) -- so a trace of few rays over many boundaries still fills the machine.
+// The boundaries are staged once per CTA in shared memory when they fit.  All arithmetic is fp64 on the
 // fp32 inputs -- the reference's own precision -- so the nearest-hit choice needs no near-tie
 // allowance.  The per-(iteration, slot) tape feeds the backward kernel, which walks the
 // iterations in reverse with the closed-form VJPs derived in DESIGN.md section 6.
@@ -113,30 +117,55 @@ struct Geo2D {
     double eps, size_eps, start_eps;
 };
 
-// nearest segment and nearest arc (strict '<' on an ascending scan = lowest index on ties),
-// then _seg_or_arc: with both valid the segment wins iff seg_u < arc_u.
+// nearest segment and nearest arc.  The LANES threads of a group share the scan (lane `sub`
+// takes boundaries sub, sub + LANES, ...; strict '<' on an ascending scan = lowest index on ties
+// within a lane), then reduce to the lexicographic minimum of (u, index): the lowest index on
+// exact ties, the behaviour of the reference's CPU argmin.  Then _seg_or_arc: with both valid
+// the segment wins iff seg_u < arc_u.  Every lane of the group returns the same result.
+template <int LANES>
 __device__ __forceinline__ Nearest2D nearest2d(const Geo2D &G, double xs, double ys, double xe,
-                                               double ye) {
+                                               double ye, int sub) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     Nearest2D n;
     n.seg_valid = n.arc_valid = false;
     n.seg = n.arc = 0;
     n.seg_u = n.arc_u = inf;
     n.seg_v = n.arc_v = 0.0;
-    for (int i = 0; i < G.n_seg; ++i) {
-        const SegHit h = seg_test(xs, ys, xe, ye, __ldg(G.seg[0] + i), __ldg(G.seg[1] + i),
-                                  __ldg(G.seg[2] + i), __ldg(G.seg[3] + i), G.eps, G.size_eps,
-                                  G.start_eps);
+    for (int i = sub; i < G.n_seg; i += LANES) {
+        const SegHit h = seg_test(xs, ys, xe, ye, G.seg[0][i], G.seg[1][i], G.seg[2][i],
+                                  G.seg[3][i], G.eps, G.size_eps, G.start_eps);
         if (h.valid && h.u < n.seg_u) {
             n.seg_valid = true; n.seg = i; n.seg_u = h.u; n.seg_v = h.v;
         }
     }
-    for (int i = 0; i < G.n_arc; ++i) {
-        const ArcHit h = arc_test(xs, ys, xe, ye, __ldg(G.arc[0] + i), __ldg(G.arc[1] + i),
-                                  __ldg(G.arc[2] + i), __ldg(G.arc[3] + i), __ldg(G.arc[4] + i),
-                                  G.eps, G.start_eps);
+    for (int i = sub; i < G.n_arc; i += LANES) {
+        const ArcHit h = arc_test(xs, ys, xe, ye, G.arc[0][i], G.arc[1][i], G.arc[2][i],
+                                  G.arc[3][i], G.arc[4][i], G.eps, G.start_eps);
         if (h.valid && h.u < n.arc_u) {
             n.arc_valid = true; n.arc = i; n.arc_u = h.u; n.arc_v = h.v;
+        }
+    }
+    if (LANES > 1) {
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) {
+            {
+                const double ou = __shfl_xor_sync(0xffffffffu, n.seg_u, off);
+                const double ov = __shfl_xor_sync(0xffffffffu, n.seg_v, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, n.seg, off);
+                const int ok = __shfl_xor_sync(0xffffffffu, (int)n.seg_valid, off);
+                if (ok && (!n.seg_valid || ou < n.seg_u || (ou == n.seg_u && oi < n.seg))) {
+                    n.seg_valid = true; n.seg = oi; n.seg_u = ou; n.seg_v = ov;
+                }
+            }
+            {
+                const double ou = __shfl_xor_sync(0xffffffffu, n.arc_u, off);
+                const double ov = __shfl_xor_sync(0xffffffffu, n.arc_v, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, n.arc, off);
+                const int ok = __shfl_xor_sync(0xffffffffu, (int)n.arc_valid, off);
+                if (ok && (!n.arc_valid || ou < n.arc_u || (ou == n.arc_u && oi < n.arc))) {
+                    n.arc_valid = true; n.arc = oi; n.arc_u = ou; n.arc_v = ov;
+                }
+            }
         }
     }
     if (n.seg_valid && n.arc_valid) {
@@ -147,13 +176,35 @@ __device__ __forceinline__ Nearest2D nearest2d(const Geo2D &G, double xs, double
     return n;
 }
 
+// Copy the boundaries into shared memory (when the launcher reserved room for them) and point
+// the geometry at the copies.  Called by every thread of the CTA.
+__device__ __forceinline__ void stage_boundaries(Geo2D &G, float *smem, int staged) {
+    if (!staged) return;
+    float *dst = smem;
+    for (int c = 0; c < 4; ++c) {
+        if (G.n_seg) {
+            for (int i = threadIdx.x; i < G.n_seg; i += blockDim.x) dst[i] = G.seg[c][i];
+            G.seg[c] = dst;
+            dst += G.n_seg;
+        }
+    }
+    for (int c = 0; c < 5; ++c) {
+        if (G.n_arc) {
+            for (int i = threadIdx.x; i < G.n_arc; i += blockDim.x) dst[i] = G.arc[c][i];
+            G.arc[c] = dst;
+            dst += G.n_arc;
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ double seg_norm(const Geo2D &G, int i) {   // tfrt/engine.py:580-586
-    return atan2((double)__ldg(G.seg[3] + i) - (double)__ldg(G.seg[1] + i),
-                 (double)__ldg(G.seg[2] + i) - (double)__ldg(G.seg[0] + i)) + kPi / 2.0;
+    return atan2((double)G.seg[3][i] - (double)G.seg[1][i],
+                 (double)G.seg[2][i] - (double)G.seg[0][i]) + kPi / 2.0;
 }
 
 __device__ __forceinline__ double arc_norm(const Geo2D &G, int i, double arc_u) {   // :666-670
-    const double r = __ldg(G.arc[4] + i);
+    const double r = G.arc[4][i];
     return floored_mod((r < 0.0 ? arc_u + kPi : arc_u) + kPi, kTwoPi) - kPi;
 }
 
@@ -234,8 +285,13 @@ struct Fwd2D {
     int32_t *live_counts;
 };
 
-__global__ void __launch_bounds__(kThreads2D) k_trace2d_forward(Fwd2D P) {
-    const int slot = blockIdx.x * kThreads2D + threadIdx.x;
+template <int LANES>
+__global__ void __launch_bounds__(kThreads2D) k_trace2d_forward(Fwd2D P, int staged) {
+    extern __shared__ float s_boundaries[];
+    stage_boundaries(P.G, s_boundaries, staged);
+    // LANES consecutive threads follow one ray; all of them carry its state, lane 0 writes
+    const int slot = (blockIdx.x * kThreads2D + threadIdx.x) / LANES;
+    const int sub = threadIdx.x % LANES;
     const size_t N = (size_t)P.n_rays;
     bool live = slot < P.n_rays;
     double xs = 0, ys = 0, xe = 0, ye = 0;
@@ -243,11 +299,15 @@ __global__ void __launch_bounds__(kThreads2D) k_trace2d_forward(Fwd2D P) {
         xs = P.src[0][slot]; ys = P.src[1][slot]; xe = P.src[2][slot]; ye = P.src[3][slot];
     }
     for (int k = 0; k < P.K; ++k) {
-        const unsigned m = __ballot_sync(0xffffffffu, live);
+        const unsigned m = __ballot_sync(0xffffffffu, live && sub == 0);
         if (m == 0) break;
         if ((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(&P.live_counts[k], __popc(m));
+        // (a group is live or dead as a whole; dead groups of a live warp take part in the
+        // shuffles of nearest2d with no boundaries to scan)
+        Geo2D G = P.G;
+        if (!live) { G.n_seg = 0; G.n_arc = 0; }
+        const Nearest2D n = nearest2d<LANES>(G, xs, ys, xe, ye, sub);
         if (!live) continue;
-        const Nearest2D n = nearest2d(P.G, xs, ys, xe, ye);
         int status = TFRT_STATUS_DEAD, hit = TFRT_HIT2D_NONE;
         double px = xe, py = ye, ray_u = 0.0, bnd_u = 0.0;
         if (n.seg_valid || n.arc_valid) {
@@ -262,13 +322,15 @@ __global__ void __launch_bounds__(kThreads2D) k_trace2d_forward(Fwd2D P) {
             status = is_arc ? category_of(idx, P.n_arc_optical, P.n_arc_stop)
                             : category_of(idx, P.n_seg_optical, P.n_seg_stop);
         }
-        float *tf = P.tape_f + (size_t)k * 4 * N;
-        tf[slot] = (float)xs; tf[N + slot] = (float)ys;
-        tf[2 * N + slot] = (float)px; tf[3 * N + slot] = (float)py;
-        double *td = P.tape_d + (size_t)k * 2 * N;
-        td[slot] = ray_u; td[N + slot] = bnd_u;
-        P.tape_hit[(size_t)k * N + slot] = hit;
-        P.tape_status[(size_t)k * N + slot] = (uint8_t)status;
+        if (sub == 0) {
+            float *tf = P.tape_f + (size_t)k * 4 * N;
+            tf[slot] = (float)xs; tf[N + slot] = (float)ys;
+            tf[2 * N + slot] = (float)px; tf[3 * N + slot] = (float)py;
+            double *td = P.tape_d + (size_t)k * 2 * N;
+            td[slot] = ray_u; td[N + slot] = bnd_u;
+            P.tape_hit[(size_t)k * N + slot] = hit;
+            P.tape_status[(size_t)k * N + slot] = (uint8_t)status;
+        }
         if (status != TFRT_STATUS_ACTIVE) {
             live = false;
             continue;
@@ -447,15 +509,23 @@ __global__ void k_finish2d(const double *g_acc, int n_seg, int n_arc, float *s0,
 }
 
 // b1-2D seam: one projection, both geometries reported separately like the reference
+template <int LANES>
 __global__ void __launch_bounds__(kThreads2D)
 k_intersect2d(Geo2D G, const float *rx1, const float *ry1, const float *rx2, const float *ry2,
               int n_rays, float *sx, float *sy, float *su, float *sv, float *sn,
               uint8_t *seg_valid, int32_t *gather_segment, float *ax, float *ay, float *au,
-              float *av, float *an, uint8_t *arc_valid, int32_t *gather_arc) {
-    const int i = blockIdx.x * kThreads2D + threadIdx.x;
-    if (i >= n_rays) return;
-    const double xs = rx1[i], ys = ry1[i], xe = rx2[i], ye = ry2[i];
-    const Nearest2D n = nearest2d(G, xs, ys, xe, ye);
+              float *av, float *an, uint8_t *arc_valid, int32_t *gather_arc, int staged) {
+    extern __shared__ float s_boundaries[];
+    stage_boundaries(G, s_boundaries, staged);
+    const int i = (blockIdx.x * kThreads2D + threadIdx.x) / LANES;
+    const int sub = threadIdx.x % LANES;
+    const bool mine = i < n_rays;
+    double xs = 0, ys = 0, xe = 0, ye = 0;
+    if (mine) { xs = rx1[i]; ys = ry1[i]; xe = rx2[i]; ye = ry2[i]; }
+    Geo2D Gs = G;
+    if (!mine) { Gs.n_seg = 0; Gs.n_arc = 0; }
+    const Nearest2D n = nearest2d<LANES>(Gs, xs, ys, xe, ye, sub);
+    if (!mine || sub != 0) return;
     if (G.n_seg > 0) {
         // entries of rays without a valid hit are unspecified (tfrt/engine.py:528-533)
         const double u = isfinite(n.seg_u) ? n.seg_u : 0.0;
@@ -499,6 +569,20 @@ Fwd2D make_fwd(const TfrtTrace2DArgs *a) {
     P.tape_f = a->tape_f; P.tape_d = a->tape_d; P.tape_hit = a->tape_hit;
     P.tape_status = a->tape_status; P.live_counts = a->live_counts;
     return P;
+}
+
+// Threads per ray: as many as it takes to fill the machine while every lane keeps a worthwhile
+// share of the boundaries.
+int lanes_for(long long n_rays, long long n_boundaries) {
+    long long lanes = 1;
+    while (lanes < 32 && n_rays * lanes < 148LL * 1024 && n_boundaries / (2 * lanes) >= 8) lanes *= 2;
+    return lanes <= 1 ? 1 : (lanes <= 4 ? 4 : 32);
+}
+
+// dynamic shared memory needed to stage the boundaries (0: leave them in global memory)
+size_t staged_bytes(int n_seg, int n_arc) {
+    const size_t bytes = sizeof(float) * (4 * (size_t)n_seg + 5 * (size_t)n_arc);
+    return bytes <= 160 * 1024 ? bytes : 0;
 }
 
 int check2d(const TfrtTrace2DArgs *a, const char *who) {
@@ -549,9 +633,24 @@ extern "C" int tfrt_intersect2d(const float *const ray[4], int32_t n_rays,
         if (seg_out) so[c] = seg_out[c];
         if (arc_out) ao[c] = arc_out[c];
     }
-    k_intersect2d<<<tfrt_div_up(n_rays, kThreads2D), kThreads2D, 0, (cudaStream_t)stream>>>(
-        G, ray[0], ray[1], ray[2], ray[3], n_rays, so[0], so[1], so[2], so[3], so[4], seg_valid,
-        gather_segment, ao[0], ao[1], ao[2], ao[3], ao[4], arc_valid, gather_arc);
+    const int lanes = lanes_for(n_rays, (long long)n_seg + n_arc);
+    const size_t smem = staged_bytes(n_seg, n_arc);
+    const int grid = tfrt_div_up((long long)n_rays * lanes, kThreads2D);
+#define TFRT_LAUNCH2D(L)                                                                        \
+    do {                                                                                        \
+        if (smem > 48 * 1024)                                                                   \
+            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_intersect2d<L>,                              \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                 (int)smem));                                   \
+        k_intersect2d<L><<<grid, kThreads2D, smem, (cudaStream_t)stream>>>(                     \
+            G, ray[0], ray[1], ray[2], ray[3], n_rays, so[0], so[1], so[2], so[3], so[4],       \
+            seg_valid, gather_segment, ao[0], ao[1], ao[2], ao[3], ao[4], arc_valid, gather_arc, \
+            smem > 0 ? 1 : 0);                                                                  \
+    } while (0)
+    if (lanes == 1) TFRT_LAUNCH2D(1);
+    else if (lanes == 4) TFRT_LAUNCH2D(4);
+    else TFRT_LAUNCH2D(32);
+#undef TFRT_LAUNCH2D
     tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -564,7 +663,21 @@ extern "C" int tfrt_trace2d_forward(const TfrtTrace2DArgs *a, void *stream) {
     TFRT_CHECK_CUDA(cudaMemsetAsync(a->live_counts, 0, sizeof(int32_t) * K, st));
     if (N == 0) return 0;
     TFRT_CHECK_CUDA(cudaMemsetAsync(a->tape_status, 0xff, K * N, st));
-    k_trace2d_forward<<<tfrt_div_up(a->n_rays, kThreads2D), kThreads2D, 0, st>>>(make_fwd(a));
+    const int lanes = lanes_for(a->n_rays, (long long)a->n_seg + a->n_arc);
+    const size_t smem = staged_bytes(a->n_seg, a->n_arc);
+    const int grid = tfrt_div_up((long long)a->n_rays * lanes, kThreads2D);
+#define TFRT_LAUNCH2D(L)                                                                        \
+    do {                                                                                        \
+        if (smem > 48 * 1024)                                                                   \
+            TFRT_CHECK_CUDA(cudaFuncSetAttribute(k_trace2d_forward<L>,                          \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                 (int)smem));                                   \
+        k_trace2d_forward<L><<<grid, kThreads2D, smem, st>>>(make_fwd(a), smem > 0 ? 1 : 0);    \
+    } while (0)
+    if (lanes == 1) TFRT_LAUNCH2D(1);
+    else if (lanes == 4) TFRT_LAUNCH2D(4);
+    else TFRT_LAUNCH2D(32);
+#undef TFRT_LAUNCH2D
     tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -461,6 +461,22 @@ class OpticalSystem3D(OpticalSystemBase):
             self._dev_cache = (tri, norm, category, packed)
         return self._dev_cache
 
+    def grad_triangle_count(self):
+        """How many leading triangles of the merged set can receive cotangents: all of them when
+        a target boundary is differentiable, optical + stop when a stop is, else the optical
+        ones (skipping the others removes the atomics of every finished ray into the few target
+        triangles).  Decided from the boundaries' own fields: the merged block requires grad as
+        a whole as soon as one boundary does."""
+        def needs_grad(items):
+            return any(bool(b) and any(torch.is_tensor(v) and v.requires_grad
+                                       for v in (b[k] for k in b.keys()))
+                       for b in items)
+        if needs_grad(self._target):
+            return 0
+        if needs_grad(self._stop):
+            return self._optical_count + self._stop_count
+        return max(self._optical_count, 1)
+
     @property
     def grid(self):
         """The acceleration grid of the current merged triangles (None in brute-force mode)."""
@@ -1010,14 +1026,7 @@ class OpticalEngine:
         plan.packed = packed
         # stop / target boundaries that do not require grad need no cotangents (merged order is
         # optical -> stop -> target, so they are the tail of the triangle list)
-        def needs_grad(d):
-            return bool(d) and any(torch.is_tensor(v) and v.requires_grad for v in d.values())
-        if needs_grad(system._amalgamated_target):
-            plan.n_grad_tri = 0
-        elif needs_grad(system._amalgamated_stop):
-            plan.n_grad_tri = system._optical_count + system._stop_count
-        else:
-            plan.n_grad_tri = max(system._optical_count, 1)
+        plan.n_grad_tri = system.grad_triangle_count()
 
         # Reuse the previous trace's workspace (tape + scratch) unless an autograd graph can
         # still read it: its lease is then still alive, and this trace gets a fresh one.

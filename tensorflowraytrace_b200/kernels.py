@@ -415,13 +415,12 @@ class Trace3D:
             for i in range(6):
                 b.g_hist[w][i] = g[i].data_ptr()
         g_acc = torch.empty((self.T * 12,), dtype=torch.float64, device=dev)
-        g_ray_ws = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev)
         g_tri = torch.empty((9, self.T), dtype=torch.float32, device=dev)
         g_norm = torch.empty((self.T, 3), dtype=torch.float32, device=dev)
         g_src = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev) if want_src_grad else None
         b.dead_ray_length = -1.0 if dead_ray_length is None else float(dead_ray_length)
         b.n_grad_tri = int(n_grad_tri)
-        b.g_acc, b.g_ray_ws = g_acc.data_ptr(), g_ray_ws.data_ptr()
+        b.g_acc = g_acc.data_ptr()
         for i in range(9):
             b.g_tri_out[i] = g_tri[i].data_ptr()
         b.g_norm_out = g_norm.data_ptr()

@@ -299,6 +299,25 @@ def config1(ray_count=1000):
                     optical_segments=[wedge], target_segments=[target])
 
 
+def performance_2d(beam_count=10, point_count=11):
+    """The scene of the reference's dev/performance.py:17-86 (its own scaling test: 10 or 10 000
+    beam points x 6 wavelengths against an acrylic interface of 10 or 1 000 segments, 2
+    iterations): a beam along +x from x = -1 onto a polyline interface near x = 0.1 (gently
+    curved here, so that neighbouring segments are not collinear), target segment at x = 10.
+    Rays = beam points x RAINBOW_6 (dense source, tfrt/sources.py:206-315)."""
+    y = np.linspace(-1.4987, 1.5013, beam_count)
+    yy = np.repeat(y, 6)
+    wl = np.tile(np.asarray(RAINBOW_6), beam_count)
+    src = rays_2d(np.stack([np.full(yy.shape[0], -1.0), yy], 1), np.zeros(yy.shape[0]), wl)
+    py = np.linspace(-2.0, 2.0, point_count)
+    px = 0.1 + 0.05 * np.cos(py)
+    seg = np.stack([px[:-1], py[:-1], px[1:], py[1:]], 1)
+    interface = {"segments": seg, "mat_in": 1, "mat_out": 0}
+    target = {"segments": np.array([[10.0, -5.0, 10.0, 5.0]])}
+    return _scene2d(f"performance_2d_{yy.shape[0]}rays_{seg.shape[0]}segments", src, 2,
+                    optical_segments=[interface], target_segments=[target])
+
+
 def arc_lens_2d(ray_count=600):
     """The arc lens of dev/single_pass.py:34-57: one optical arc (centre (5,0), radius 5, from
     3pi/4 to 5pi/4), a parallel beam of six wavelengths from x = -1; plus a target segment."""

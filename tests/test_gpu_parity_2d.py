@@ -198,3 +198,32 @@ def test_unfused_2d_matches_fused():
             continue
         b = torch.zeros_like(a) if b is None else b
         assert float((a - b).abs().max()) < 5e-3 * scale    # fp32 torch glue vs fp64 kernel
+
+
+# --------------------------------------------------------------------------- 2D at scale
+@pytest.mark.parametrize("beams,points", [(10, 11), (10, 1001), (2000, 1001), (10000, 11)])
+def test_2d_at_scale_matches_the_oracle(beams, points):
+    """the sizes of the reference's own scaling script
+    (dev/performance.py:77-86: 10 / 10 000 beam points x 6 wavelengths against 10 / 1 000
+    segments, 2 iterations).  Few rays over many segments are scanned by 32 threads per ray, the
+    boundaries staged in shared memory; whatever the thread layout, the nearest hit (lowest index
+    on ties) and the refracted rays must be the oracle's."""
+    scene = scenes.performance_2d(beams, points)
+    engine, _, _ = scenes.build_engine_2d(scene, eps=helpers.EPS, compile_dead_rays=True)
+    engine.ray_trace(2)
+    oracle, _ = helpers.oracle2d_from_scene(scene, compile_dead_rays=True)
+    oracle.ray_trace(2)
+    n = beams * 6
+    assert engine.last_trace.live_counts()[0] == n == oracle.live_counts[0]
+    assert engine.last_trace.live_counts() == oracle.live_counts
+    for name in ("active", "finished", "dead"):
+        e, o = getattr(engine, name + "_rays"), getattr(oracle, name + "_rays")
+        n_o = o["x_start"].shape[0] if bool(o) else 0
+        n_e = e["x_start"].shape[0] if bool(e) else 0
+        assert n_e == n_o, name
+        if n_o == 0:
+            continue
+        scale = max(float(np.max(np.abs(o[f].numpy()))) for f in helpers.RAY_FIELDS_2D)
+        for f in helpers.RAY_FIELDS_2D + ("wavelength",):
+            assert helpers.rel_err(e[f].detach().cpu().numpy(), o[f].numpy(), scale=scale) < 1e-5, (name, f)
+    assert (engine.finished_rays["x_end"] - 10.0).abs().max() < 1e-4
