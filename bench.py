@@ -416,8 +416,8 @@ def run_ours(args):
             return grads, err
         engine.optical_system.update()
         engine.ray_trace(K)
+        engine.finished_rays              # materialise: the trace's result
         if scene["dimension"] == 3:
-            engine.finished_rays          # materialise: the trace's result
             account(engine)
         return None, None
 
@@ -518,8 +518,7 @@ def run_ours(args):
     def step_forward():
         engine.optical_system.update()
         engine.ray_trace(K)
-        if scene["dimension"] == 3:
-            engine.finished_rays
+        engine.finished_rays
     step_forward()
     fwd_seconds = timed(step_forward, args.steps)
 
@@ -596,16 +595,32 @@ def run_ours(args):
             tr2.forward()
         e1.record()
         torch.cuda.synchronize()
+        kernel_us = 1e3 * e0.elapsed_time(e1) / reps
+        # OpticalEngine.ray_trace alone (system already updated, histories not read): the call
+        # enqueues the launch and returns; wall clock including the drain of the GPU
+        import time as _time
+        for _ in range(20):
+            engine.ray_trace(K)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(200):
+            engine.ray_trace(K)
+        torch.cuda.synchronize()
+        call_us = 1e6 * (_time.perf_counter() - t0) / 200
         line["roofline"] = {
             "kernel": "k_trace2d_forward", "bound": "latency", "achieved": None, "peak": None,
             "unit": "us/trace", "frac": None, "traffic": None,
             "us_per_trace": 1e6 * fwd_seconds / args.steps,
-            "us_per_trace_kernel_only": 1e3 * e0.elapsed_time(e1) / reps,
+            "us_per_ray_trace_call": call_us,
+            "us_per_trace_kernel_only": kernel_us,
             "note": "config 1 (1 000 rays x 3 segments x 3 iterations) is launch-latency bound "
                     "(SURVEY.md 8(d)): one kernel launch per trace, fp64 arithmetic; "
-                    "us_per_trace is the public-API call (system.update + ray_trace, host "
-                    "bookkeeping included), us_per_trace_kernel_only the C-ABI launch alone "
-                    "(status memset + k_trace2d_forward)"}
+                    "us_per_trace is system.update + ray_trace + reading finished_rays through "
+                    "the public API (L2 flushed before each), us_per_ray_trace_call the "
+                    "OpticalEngine.ray_trace call alone on an updated system (200 back-to-back "
+                    "calls, wall clock with the GPU drained; histories are built when first "
+                    "read), us_per_trace_kernel_only the C-ABI launch alone (status memset + "
+                    "k_trace2d_forward)"}
     if scene["dimension"] == 2 and rank == 0 and world == 1:
         line["two_d_at_scale"] = two_d_at_scale(torch, scenes, not args.no_cpu_baseline)
     if backward:

@@ -232,13 +232,14 @@ int tfrt_materialize3d(const TfrtTrace3DArgs *args, const int32_t *counters_host
  * b5  gradient seam: tape.gradient(error, parameters) (tfrt/optimizer.py:216-220) restricted to
  * the trace: cotangents of the materialised history -> cotangents of triangle fields / norm /
  * source rays.  g_hist[which][6] are cotangents of the arrays produced by tfrt_materialize3d
- * (NULL where absent).  g_tri (T,9)+g_norm (T,3) are accumulated in fp64 into g_acc (T*12
- * doubles, zeroed by the call), then written to fp32 g_tri_out[9] (T each) and g_norm_out (T,3).
+ * (NULL where absent).  Per triangle six fp64 sums (the corner cotangents are per-triangle linear
+ * maps of them) are accumulated in g_acc -- a workspace of T 128-byte rows (T*16 doubles, 128-byte
+ * aligned, initialised by the call) -- then mapped to fp32 g_tri_out[9] (T each) and g_norm_out (T,3).
  * g_src[6] (N each, may be NULL) receives d/d(source start,end).
  */
 typedef struct {
     const float *g_hist[4][6];
-    double *g_acc;            /* T*12 */
+    double *g_acc;            /* T*16 doubles, 128-byte aligned */
     float *g_ray_ws;          /* unused (kept for layout compatibility; may be NULL): the running
                                  cotangent of a ray now lives in registers */
     float *g_tri_out[9];

@@ -148,24 +148,34 @@ class TracePlan:
 
 class Trace2DFunction(torch.autograd.Function):
     """Whole-loop 2D trace (K4).  Inputs: seg (4,S) or None, arc (5,A) or None, src (5,N), and a
-    `plan` dict with the non-tensor configuration (kernels.Trace2D keyword arguments + counts +
-    max_iterations).  Output: the tape (K,4,N) f32 -- ray start and projected end per (iteration,
-    source ray) -- from which the engine gathers the reference-ordered history sets with plain
-    torch indexing (so their cotangents scatter back into this tape's cotangent)."""
+    `plan` dict: either {"trace": kernels.Trace2D already run (the engine enqueues it in
+    ray_trace), "lease": WorkspaceLease} or the non-tensor configuration (kernels.Trace2D keyword
+    arguments + counts + max_iterations), in which case the trace runs here.  Output: the tape
+    (K,4,N) f32 -- ray start and projected end per (iteration, source ray) -- from which the
+    engine gathers the reference-ordered history sets with plain torch indexing (so their
+    cotangents scatter back into this tape's cotangent)."""
 
     @staticmethod
     def forward(ctx, seg, arc, src, plan):
-        tr = kernels.Trace2D(src, seg, arc, plan["counts"], plan["max_iterations"],
-                             **plan["kwargs"])
-        tr.forward()
-        plan["trace"] = tr
+        tr = plan.get("trace")
+        if tr is None:
+            tr = kernels.Trace2D(src, seg, arc, plan["counts"], plan["max_iterations"],
+                                 **plan["kwargs"])
+            tr.forward()
+            plan["trace"] = tr
         ctx.trace = tr
+        ctx.generation = tr.generation
+        ctx.lease = plan.get("lease")   # keeps the tape from being reused while this graph lives
         ctx.src_shape = src.shape
         return tr.tape_f[:, :, : tr.N]
 
     @staticmethod
     def backward(ctx, g_tape):
         tr = ctx.trace
+        if tr.generation != ctx.generation:
+            raise RuntimeError(
+                "tensorflowraytrace_b200: the tape of this 2D trace was overwritten by a later "
+                "trace that reused it")
         want_src = ctx.needs_input_grad[2]
         g_full = g_tape
         if g_full.shape[2] != tr.tape_f.shape[2]:     # N == 0 padding

@@ -18,13 +18,40 @@
 //       kappa = (g_H.D)/(m.D) ; g_A = (1-u-v) kappa m ; g_B = u kappa m ; g_C = v kappa m
 //       g_S += (1-t)(g_H - kappa m) ;  g_E = t (g_H - kappa m)
 //
-// Triangle cotangents are accumulated in fp64 with warp-aggregated atomics (lanes that hit the
-// same triangle are combined first), then rounded once to fp32.
+// Every triangle cotangent of a hit is a per-triangle linear map of SIX per-ray scalars: the corner
+// cotangents of the hit point are (1-u-v) kappa m, u kappa m, v kappa m with m a constant of the
+// triangle, and the cotangent of its normal reaches the corners through the constant Jacobian of
+// n = m/|m|.  So a hit adds six numbers -- (1-u-v) kappa, u kappa, v kappa and the 3-vector g_m
+// (or g_n when the caller supplies normals) -- with warp-aggregated fp64 atomics (lanes that hit
+// the same triangle are combined first) into one 64-byte row per triangle; k_finish_tri_grads
+// applies the per-triangle maps once and rounds to fp32.  The triangle corners are read from a
+// 48-byte record next to that row (three 16-byte loads instead of nine scattered ones), written
+// by k_backward_prepare, which also zeroes the sums.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kBwdThreads = 256;
+constexpr int kRowDoubles = 16;   // 128-byte row per triangle: doubles 0-5 sums, bytes 64-111 corners
+constexpr int kSums = 6;
+
+// Zero the sums and write the corner record (A.xyz, B.xyz, C.xyz as fp32) of every triangle.
+__global__ void k_backward_prepare(int n_tri, const float *t0, const float *t1, const float *t2,
+                                   const float *t3, const float *t4, const float *t5,
+                                   const float *t6, const float *t7, const float *t8,
+                                   double *__restrict__ g_acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tri) return;
+    double4 *row = reinterpret_cast<double4 *>(g_acc + (size_t)i * kRowDoubles);
+    row[0] = make_double4(0, 0, 0, 0);
+    row[1] = make_double4(0, 0, 0, 0);
+    float4 *rec = reinterpret_cast<float4 *>(row + 2);
+    rec[0] = make_float4(t0[i], t1[i], t2[i], t3[i]);
+    rec[1] = make_float4(t4[i], t5[i], t6[i], t7[i]);
+    rec[2] = make_float4(t8[i], 0.f, 0.f, 0.f);
+}
 
 struct BwdParams {
     int n_rays, n_iters, index_mode, n_grad_tri;
@@ -35,7 +62,6 @@ struct BwdParams {
     const uint8_t *tape_status; // K*N
     const int32_t *tape_outpos; // K*N
     const float *g_hist[4][6];
-    const float *tri[9];
     const float *norm;
     const float *src_wavelength;
     const int32_t *mat_in, *mat_out;
@@ -44,13 +70,13 @@ struct BwdParams {
     const double *n_table;      // optional tabulated indices (see TfrtTrace3DArgs)
     const int32_t *lambda_index;
     int n_lambda;
-    double *g_acc;              // T*12
+    double *g_acc;              // T rows of kRowDoubles: six sums, two spare, corner record
     float *g_src[6];            // written at k == 0 when non-null
 };
 
 // Sum `vals[12]` over the lanes of `peers` (lanes sharing one triangle) into the group's lowest
 // lane.  Groups are tiny for incoherent rays, so a rank-by-rank gather is enough.
-__device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double vals[12],
+__device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double vals[kSums],
                                                 bool &is_leader) {
     const int n = __popc(peers);
     int maxn = n;
@@ -62,7 +88,7 @@ __device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double
         const unsigned src = __fns(peers, 0, step + 1);   // lane of the peer with rank `step`
         const int src_lane = (src == 0xffffffffu) ? lane : (int)src;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
+        for (int c = 0; c < kSums; ++c) {
             const double other = __shfl_sync(0xffffffffu, vals[c], src_lane);
             if (is_leader && step < n) vals[c] += other;
         }
@@ -73,7 +99,10 @@ __device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double
 // 0 .. k_last of the iterations); the running cotangent of the ray stays in registers, the
 // tape is read slot-indexed (coalesced), and each iteration's triangle cotangents are combined
 // across the lanes that hit the same triangle before the fp64 atomics.  One launch per trace.
-__global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
+// kMinBlocks = 3 caps the kernel at 80 registers (a few spilled words) for 24 instead of 16 resident
+// warps per SM: the kernel waits on scattered L2 reads and atomics, so the extra warps pay.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBwdThreads, kMinBlocks) k_backward3d(BwdParams P) {
     const int slot = blockIdx.x * kBwdThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const size_t N = (size_t)P.n_rays;
@@ -98,9 +127,9 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
     const int active_offset = (int)active_before;
     bool contributes = false;
     int tri = -1;
-    double acc[12];
+    double acc[kSums];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) acc[c] = 0.0;
+    for (int c = 0; c < kSums; ++c) acc[c] = 0.0;
 
     if (mine && k <= k_last) {
         const int status = P.tape_status[(size_t)k * N + slot];
@@ -135,15 +164,13 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                 }
             }
         } else {
-            double A[3], B[3], C[3];
-            for (int c = 0; c < 3; ++c) {
-                A[c] = P.tri[c][tri];
-                B[c] = P.tri[3 + c][tri];
-                C[c] = P.tri[6 + c][tri];
-            }
+            const float4 *rec =
+                reinterpret_cast<const float4 *>(P.g_acc + (size_t)tri * kRowDoubles + 8);
+            const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+            const double A[3] = {r0.x, r0.y, r0.z}, B[3] = {r0.w, r1.x, r1.y};
+            const double C[3] = {r1.z, r1.w, r2.x};
             double gH[3] = {ghP[0], ghP[1], ghP[2]};
             double gSd[3] = {ghS[0], ghS[1], ghS[2]};
-            double gnA[3] = {0, 0, 0}, gnB[3] = {0, 0, 0}, gnC[3] = {0, 0, 0};   // via the normal
             if (status == TFRT_STATUS_ACTIVE) {
                 // (gSn, gEn): cotangent of the reacted ray, left by iteration k + 1 of this slot
                 // (zero when that iteration was not executed)
@@ -226,23 +253,13 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
                     for (int c = 0; c < 3; ++c)
                         g_nr[c] = (n2 > 1e-12) ? (g_nh[c] - dot * nh[c]) * ninv : g_nh[c] * ninv;
                     if (P.norm) {
-                        for (int c = 0; c < 3; ++c) acc[9 + c] = g_nr[c];
+                        for (int c = 0; c < 3; ++c) acc[3 + c] = g_nr[c];
                     } else {
-                        // through n = c/|c|, c = u x v, u = B - A, v = C - B  (K3 backward fused):
-                        //   g_c = (g_n - (g_n.n) n)/|c| ; g_u = v x g_c ; g_v = g_c x u
-                        //   g_A -= g_u ; g_B += g_u - g_v ; g_C += g_v
+                        // through n = c/|c|, c = u x v (u = B - A, v = C - B): the cotangent of
+                        // the unnormalised cross product, g_c = (g_n - (g_n.n) n)/|c|; its map
+                        // onto the corners is applied once per triangle by k_finish_tri_grads
                         const double dn = g_nr[0] * nr[0] + g_nr[1] * nr[1] + g_nr[2] * nr[2];
-                        const double gc[3] = {(g_nr[0] - dn * nr[0]) / clen, (g_nr[1] - dn * nr[1]) / clen,
-                                              (g_nr[2] - dn * nr[2]) / clen};
-                        const double gu[3] = {cv[1] * gc[2] - cv[2] * gc[1], cv[2] * gc[0] - cv[0] * gc[2],
-                                              cv[0] * gc[1] - cv[1] * gc[0]};
-                        const double gv[3] = {gc[1] * cu[2] - gc[2] * cu[1], gc[2] * cu[0] - gc[0] * cu[2],
-                                              gc[0] * cu[1] - gc[1] * cu[0]};
-                        for (int c = 0; c < 3; ++c) {
-                            gnA[c] = -gu[c];
-                            gnB[c] = gu[c] - gv[c];
-                            gnC[c] = gv[c];
-                        }
+                        for (int c = 0; c < 3; ++c) acc[3 + c] = (g_nr[c] - dn * nr[c]) / clen;
                     }
                 }
             }
@@ -256,12 +273,11 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
             const double mD = m[0] * D[0] + m[1] * D[1] + m[2] * D[2];
             const double gD = gH[0] * D[0] + gH[1] * D[1] + gH[2] * D[2];
             const double kappa = (mD != 0.0) ? gD / mD : 0.0;
-            const double b0 = 1.0 - u - v;
+            acc[0] = (1.0 - u - v) * kappa;
+            acc[1] = u * kappa;
+            acc[2] = v * kappa;
             for (int c = 0; c < 3; ++c) {
                 const double km = kappa * m[c];
-                acc[c] = b0 * km + gnA[c];
-                acc[3 + c] = u * km + gnB[c];
-                acc[6 + c] = v * km + gnC[c];
                 const double proj = gH[c] - km;
                 gS[c] = gSd[c] + (1.0 - t) * proj;
                 gE[c] = t * proj;
@@ -286,25 +302,49 @@ __global__ void __launch_bounds__(kBwdThreads) k_backward3d(BwdParams P) {
         bool is_leader = false;
         aggregate_peers(peers, lane, acc, is_leader);
         if (contributes && is_leader) {
-            double *dst = P.g_acc + (size_t)tri * 12;
+            double *dst = P.g_acc + (size_t)tri * kRowDoubles;
 #pragma unroll
-            for (int c = 0; c < 12; ++c)
+            for (int c = 0; c < kSums; ++c)
                 if (acc[c] != 0.0) atomicAdd(dst + c, acc[c]);
         }
     }
     }   // iterations, in reverse
 }
 
-__global__ void k_finish_tri_grads(const double *__restrict__ g_acc, int n_tri, float *o0,
-                                   float *o1, float *o2, float *o3, float *o4, float *o5,
-                                   float *o6, float *o7, float *o8, float *g_norm) {
+// Per-triangle maps of the six sums onto the corner cotangents (see the header):
+//   g_A = s0 m - g_u ; g_B = s1 m + g_u - g_v ; g_C = s2 m + g_v,  m = (B-A) x (C-A),
+//   g_u = (C-B) x G ; g_v = G x (B-A)  with G = sum of g_c (geometric normals), else G = 0 and
+//   g_norm = the sum itself (caller-supplied normals).
+__global__ void k_finish_tri_grads(const double *__restrict__ g_acc, int n_tri, int has_norm,
+                                   float *o0, float *o1, float *o2, float *o3, float *o4,
+                                   float *o5, float *o6, float *o7, float *o8, float *g_norm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_tri) return;
-    const double *g = g_acc + (size_t)i * 12;
-    o0[i] = (float)g[0]; o1[i] = (float)g[1]; o2[i] = (float)g[2];
-    o3[i] = (float)g[3]; o4[i] = (float)g[4]; o5[i] = (float)g[5];
-    o6[i] = (float)g[6]; o7[i] = (float)g[7]; o8[i] = (float)g[8];
-    g_norm[3 * i] = (float)g[9]; g_norm[3 * i + 1] = (float)g[10]; g_norm[3 * i + 2] = (float)g[11];
+    const double *g = g_acc + (size_t)i * kRowDoubles;
+    const float4 *rec = reinterpret_cast<const float4 *>(g + 8);
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+    const double A[3] = {r0.x, r0.y, r0.z}, B[3] = {r0.w, r1.x, r1.y}, C[3] = {r1.z, r1.w, r2.x};
+    const double e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+    const double e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+    const double cv[3] = {C[0] - B[0], C[1] - B[1], C[2] - B[2]};
+    const double m[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                         e1[0] * e2[1] - e1[1] * e2[0]};
+    double gu[3] = {0, 0, 0}, gv[3] = {0, 0, 0};
+    if (!has_norm) {
+        const double G[3] = {g[3], g[4], g[5]};
+        gu[0] = cv[1] * G[2] - cv[2] * G[1]; gu[1] = cv[2] * G[0] - cv[0] * G[2];
+        gu[2] = cv[0] * G[1] - cv[1] * G[0];
+        gv[0] = G[1] * e1[2] - G[2] * e1[1]; gv[1] = G[2] * e1[0] - G[0] * e1[2];
+        gv[2] = G[0] * e1[1] - G[1] * e1[0];
+    }
+    float *const oa[3] = {o0, o1, o2}, *const ob[3] = {o3, o4, o5}, *const oc[3] = {o6, o7, o8};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        oa[c][i] = (float)(g[0] * m[c] - gu[c]);
+        ob[c][i] = (float)(g[1] * m[c] + gu[c] - gv[c]);
+        oc[c][i] = (float)(g[2] * m[c] + gv[c]);
+        g_norm[3 * i + c] = has_norm ? (float)g[3 + c] : 0.f;
+    }
 }
 
 }  // namespace
@@ -318,7 +358,10 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         TFRT_REQUIRE(b->g_tri_out[c], "tfrt_trace3d_backward: null g_tri_out[%d]", c);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = a->n_rays, K = a->max_iterations, T = a->n_tri;
-    TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_acc, 0, sizeof(double) * 12 * (size_t)T, st));
+    k_backward_prepare<<<tfrt_div_up(T, 256), 256, 0, st>>>(
+        T, a->tri[0], a->tri[1], a->tri[2], a->tri[3], a->tri[4], a->tri[5], a->tri[6], a->tri[7],
+        a->tri[8], b->g_acc);
+    tfrt_note_launch(1);
     if (N > 0) {
         for (int c = 0; c < 6; ++c)
             if (b->g_src[c]) TFRT_CHECK_CUDA(cudaMemsetAsync(b->g_src[c], 0, sizeof(float) * N, st));
@@ -332,18 +375,24 @@ extern "C" int tfrt_trace3d_backward(const TfrtTrace3DArgs *a, const int32_t *ch
         P.tape_status = a->tape_status; P.tape_outpos = a->tape_outpos;
         for (int w = 0; w < 4; ++w)
             for (int c = 0; c < 6; ++c) P.g_hist[w][c] = b->g_hist[w][c];
-        for (int c = 0; c < 9; ++c) P.tri[c] = a->tri[c];
         P.norm = a->norm; P.src_wavelength = a->src[6];
         P.mat_in = a->mat_in; P.mat_out = a->mat_out; P.n_in = a->n_in; P.n_out = a->n_out;
         P.materials = a->materials;
         P.n_table = a->n_table; P.lambda_index = a->lambda_index; P.n_lambda = a->n_lambda;
         for (int c = 0; c < 6; ++c) P.g_src[c] = b->g_src[c];
         P.g_acc = b->g_acc;
-        k_backward3d<<<tfrt_div_up(N, kBwdThreads), kBwdThreads, 0, st>>>(P);
+        static const int min_blocks = [] {
+            const char *e = getenv("TFRT_BWD_MINBLOCKS");     // tuning switch (2 or 3)
+            return e ? atoi(e) : 3;
+        }();
+        if (min_blocks >= 3)
+            k_backward3d<3><<<tfrt_div_up(N, kBwdThreads), kBwdThreads, 0, st>>>(P);
+        else
+            k_backward3d<2><<<tfrt_div_up(N, kBwdThreads), kBwdThreads, 0, st>>>(P);
         tfrt_note_launch(1);
     }
     k_finish_tri_grads<<<tfrt_div_up(T, 256), 256, 0, st>>>(
-        b->g_acc, T, b->g_tri_out[0], b->g_tri_out[1], b->g_tri_out[2], b->g_tri_out[3],
+        b->g_acc, T, a->norm != nullptr, b->g_tri_out[0], b->g_tri_out[1], b->g_tri_out[2], b->g_tri_out[3],
         b->g_tri_out[4], b->g_tri_out[5], b->g_tri_out[6], b->g_tri_out[7], b->g_tri_out[8],
         b->g_norm_out);
     tfrt_note_launch(1);

@@ -216,13 +216,13 @@ class OpticalSystemBase(RecursivelyUpdatable):
         self._source_rows = None
 
     def source_rows(self):
-        """The amalgamated 3D source rays as one (7,N) fp32 block [x_start .. z_end, wavelength]
-        (the layout the trace kernels read), built once per update()."""
+        """The amalgamated source rays as one fp32 block [x_start .. z_end, wavelength] -- (7,N)
+        in 3D, (5,N) in 2D, the layout the trace kernels read -- built once per update()."""
         rows = getattr(self, "_source_rows", None)
         if rows is None:
             f = self._amalgamated_sources
             n = f["x_start"].shape[0]
-            cols = [f[k] for k in RAY_FIELDS_3D]
+            cols = [f[k] for k in (RAY_FIELDS_3D if self.dimension == 3 else kernels.RAY_FIELDS_2D)]
             cols.append(f["wavelength"] if "wavelength" in f
                         else torch.zeros(n, dtype=torch.float32, device=cols[0].device))
             rows = torch.stack([c.to(torch.float32) for c in cols]).contiguous()
@@ -614,7 +614,17 @@ class OpticalSystem2D(OpticalSystemBase):
                 else:
                     counts.append(0)
                 parts.append(d)
-            return counts, amalgamate(parts, sig | {"catagory"})
+            # static boundaries hand in the very same tensors at every update: the merged set
+            # (and the (4,S) / (5,A) device blocks built from it) is then reused as it is
+            full = sig | {"catagory"}
+            ids = tuple((id(d[f]), d[f]._version) for d in parts if bool(d) for f in full)
+            cache = self.__dict__.setdefault("_merge_cache", {})
+            hit = cache.get(suffix)
+            if hit is not None and hit[0] == ids:
+                return counts, hit[2]
+            merged = amalgamate(parts, full)
+            cache[suffix] = (ids, [dict(d) for d in parts], merged)   # inputs kept alive
+            return counts, merged
 
         (self._optical_seg_count, self._stop_seg_count, self._target_seg_count), \
             self._merged_segments = merge("segments", "x_start", SEGMENT_GEO_SIG)
@@ -624,13 +634,22 @@ class OpticalSystem2D(OpticalSystemBase):
     def merged_device_arrays(self):
         """(seg (4,S) f32 or None, arc (5,A) f32 or None), attached to the autograd graph of
         the boundary parameters."""
-        seg = arc = None
-        if bool(self._merged_segments):
-            seg = torch.stack([self._merged_segments[k] for k in kernels.SEG_FIELDS]).to(
-                torch.float32).contiguous()
-        if bool(self._merged_arcs):
-            arc = torch.stack([self._merged_arcs[k] for k in kernels.ARC_FIELDS]).to(
-                torch.float32).contiguous()
+        def block(merged, fields, name):
+            if not bool(merged):
+                return None
+            cols = [merged[k] for k in fields]
+            ids = tuple((id(c), c._version) for c in cols)
+            cache = self.__dict__.setdefault("_block_cache", {})
+            hit = cache.get(name)
+            if hit is not None and hit[0] == ids:
+                return hit[2]
+            out = torch.stack(cols).to(torch.float32).contiguous()
+            if not out.requires_grad:      # a block that carries a graph is rebuilt every time
+                cache[name] = (ids, cols, out)
+            return out
+
+        seg = block(self._merged_segments, kernels.SEG_FIELDS, "seg")
+        arc = block(self._merged_arcs, kernels.ARC_FIELDS, "arc")
         return seg, arc
 
     def intersect(self, rays):
@@ -1046,6 +1065,10 @@ class OpticalEngine:
         the trace's counters) and attach them to the autograd graph of the boundary parameters."""
         if self._pending is None:
             return
+        if self.dimension == 2:
+            pending, self._pending = self._pending, None
+            self._materialise_pending_2d(*pending)
+            return
         tri, norm_in, src, plan, src_fields = self._pending
         self._pending = None
         active, stopped, finished, dead = TraceFunction.apply(tri, norm_in, src, plan)
@@ -1072,12 +1095,8 @@ class OpticalEngine:
         plan.lease = None     # from here on only the autograd node (if any) holds the lease
 
     def _ray_trace_fused_2d(self, max_iterations):
-        """Whole 2D trace in one kernel launch (K4); histories are gathered from the
-        per-(iteration, source ray) tape in the reference's order: per iteration the rays that
-        hit segments, then those that hit arcs, each order-preserving
-        (tfrt/engine.py:1640-1660, :1797-1815); the next pass sees them in the same order
-        (:1950-1956)."""
-        from .autograd import Trace2DFunction
+        """Enqueue the whole 2D trace as one kernel launch (K4, asynchronous); the history sets
+        are built when first read (_materialise_pending_2d)."""
         system = self.optical_system
         src_fields = system._amalgamated_sources
         seg, arc = system.merged_device_arrays()
@@ -1085,12 +1104,7 @@ class OpticalEngine:
             return
         reaction = next(o for o in self._operations if type(o) is op.StandardReaction)
         dev = (seg if seg is not None else arc).device
-        n = src_fields["x_start"].shape[0]
-        rows = [src_fields[k] for k in kernels.RAY_FIELDS_2D]
-        rows.append(src_fields["wavelength"] if "wavelength" in src_fields
-                    else torch.zeros(n, dtype=torch.float32, device=dev))
-        src = torch.stack([r.to(torch.float32) for r in rows]).contiguous()
-
+        src = system.source_rows()
         index_mode = reaction.refractive_index_type == "index"
         keys = ("mat_in", "mat_out") if index_mode else ("n_in", "n_out")
 
@@ -1103,14 +1117,36 @@ class OpticalEngine:
                   ray_start_eps=system.ray_start_epsilion, new_ray_length=self.new_ray_length)
         if index_mode:
             kw.update(materials=system.material_table(dev), n_materials=len(system.materials))
-        plan = {"counts": dict(seg_optical=system._optical_seg_count,
-                               seg_stop=system._stop_seg_count,
-                               arc_optical=system._optical_arc_count,
-                               arc_stop=system._stop_arc_count),
-                "max_iterations": max_iterations, "kwargs": kw}
-        tape = Trace2DFunction.apply(seg, arc, src, plan)        # (K, 4, N)
-        tr = plan["trace"]
+        counts = dict(seg_optical=system._optical_seg_count, seg_stop=system._stop_seg_count,
+                      arc_optical=system._optical_arc_count, arc_stop=system._stop_arc_count)
+        # Reuse the previous trace's tape unless an autograd graph can still read it (its lease
+        # is then still alive), as the 3D path does with its workspace.
+        old = self._workspace
+        if old is not None and self._lease_ref is not None and self._lease_ref() is not None:
+            old = None
+        tr = kernels.Trace2D(src.detach(), None if seg is None else seg.detach(),
+                             None if arc is None else arc.detach(), counts, max_iterations,
+                             reuse=old, **kw)
+        tr.forward()
+        lease = WorkspaceLease(tr)
+        plan = {"trace": tr, "lease": lease}
+        self._workspace, self._lease_ref = tr, weakref.ref(lease)
         self.last_trace = tr
+        self._pending = (seg, arc, src, plan, src_fields, max_iterations)
+        self.last_projection_result = {}
+
+    def _materialise_pending_2d(self, seg, arc, src, plan, src_fields, max_iterations):
+        """Histories of the pending 2D trace, gathered from the per-(iteration, source ray) tape
+        in the reference's order: per iteration the rays that hit segments, then those that hit
+        arcs, each order-preserving (tfrt/engine.py:1640-1660, :1797-1815); the next pass sees
+        them in the same order (:1950-1956).  The gathers are plain torch indexing of the tape,
+        so the cotangents of the sets scatter back into the tape's cotangent."""
+        from .autograd import Trace2DFunction
+        tr = plan["trace"]
+        dev = src.device
+        n = tr.N
+        tape = Trace2DFunction.apply(seg, arc, src, plan)        # (K, 4, N)
+        plan["lease"] = None     # from here on only the autograd node (if any) holds the lease
 
         both = seg is not None and arc is not None
         code = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}

@@ -414,7 +414,7 @@ class Trace3D:
             keep.append(g)
             for i in range(6):
                 b.g_hist[w][i] = g[i].data_ptr()
-        g_acc = torch.empty((self.T * 12,), dtype=torch.float64, device=dev)
+        g_acc = torch.empty((self.T * 16,), dtype=torch.float64, device=dev)   # 128-byte rows
         g_tri = torch.empty((9, self.T), dtype=torch.float32, device=dev)
         g_norm = torch.empty((self.T, 3), dtype=torch.float32, device=dev)
         g_src = torch.empty((6, max(self.N, 1)), dtype=torch.float32, device=dev) if want_src_grad else None
@@ -491,11 +491,13 @@ class Trace2D:
 
     def __init__(self, src, seg, arc, counts, max_iterations, *, seg_mat=None, arc_mat=None,
                  materials=None, n_materials=0, intersect_eps=1e-10, size_eps=1e-10,
-                 ray_start_eps=1e-10, new_ray_length=1.0):
+                 ray_start_eps=1e-10, new_ray_length=1.0, reuse=None):
         """src (5,N): x_start,y_start,x_end,y_end,wavelength.  seg (4,S) / arc (5,A) merged
         optical -> stop -> target (either may be None).  counts = dict(seg_optical, seg_stop,
         arc_optical, arc_stop).  seg_mat / arc_mat: (in, out) tensors over the OPTICAL
-        boundaries -- int material indices when `materials` is given, else float n values."""
+        boundaries -- int material indices when `materials` is given, else float n values.
+        reuse: an earlier Trace2D whose tape may be overwritten (taken over when the shapes
+        agree; the caller guarantees no autograd graph still reads it)."""
         _require_cuda(src, seg, arc)
         self.src = _f32(src)
         self.seg = None if seg is None or seg.shape[1] == 0 else _f32(seg)
@@ -508,12 +510,18 @@ class Trace2D:
         self.index_mode = 1 if materials is not None else 0
         self.materials = materials
         n1 = max(N, 1)
-        # entries of slots that are not live at an iteration are never read (status 255)
-        self.tape_f = torch.empty((K, 4, n1), dtype=torch.float32, device=dev)
-        self.tape_d = torch.empty((K, 2, n1), dtype=torch.float64, device=dev)
-        self.tape_hit = torch.empty((K, n1), dtype=torch.int32, device=dev)
-        self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
-        self.live = torch.empty((K,), dtype=torch.int32, device=dev)
+        if reuse is not None and reuse.N == N and reuse.K == K and reuse.tape_f.device == dev:
+            self.tape_f, self.tape_d = reuse.tape_f, reuse.tape_d
+            self.tape_hit, self.tape_status, self.live = reuse.tape_hit, reuse.tape_status, reuse.live
+            reuse.generation += 1      # the old trace's backward would read the wrong tape
+        else:
+            # entries of slots that are not live at an iteration are never read (status 255)
+            self.tape_f = torch.empty((K, 4, n1), dtype=torch.float32, device=dev)
+            self.tape_d = torch.empty((K, 2, n1), dtype=torch.float64, device=dev)
+            self.tape_hit = torch.empty((K, n1), dtype=torch.int32, device=dev)
+            self.tape_status = torch.empty((K, n1), dtype=torch.uint8, device=dev)
+            self.live = torch.empty((K,), dtype=torch.int32, device=dev)
+        self.generation = 0
         self._live_host = None
 
         def conv(pair):
