@@ -46,7 +46,8 @@ def can_build():
 
 def _deps():
     return sources() + [os.path.join(CSRC, "common.cuh"),
-                        os.path.join(HERE, "..", "include", "tfrt_b200.h")]
+                        os.path.join(HERE, "..", "include", "tfrt_b200.h"),
+                        os.path.join(HERE, "_reuse_patch.py")]
 
 
 def source_hash():
@@ -82,6 +83,18 @@ def build(force=False, verbose=False):
         if os.path.exists(tmp):
             os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    # Post-link step: set the operand-reuse flags ptxas leaves unset in the search kernel's packed
+    # FP32 loops (_reuse_patch.py; +2 % on k_intersect3d, same bits out).  TFRT_REUSE_PATCH=0 skips
+    # it; without cuobjdump the library is used as ptxas wrote it.
+    if os.environ.get("TFRT_REUSE_PATCH", "1") != "0":
+        if shutil.which("cuobjdump"):
+            from . import _reuse_patch
+            n = _reuse_patch.patch(tmp)
+            if verbose:
+                print(f"reuse flags set: {n}")
+        else:
+            print("tensorflowraytrace_b200: cuobjdump not found, operand-reuse patch skipped",
+                  file=sys.stderr)
     os.chmod(tmp, 0o755)
     os.replace(tmp, LIB_PATH)
     if verbose:

@@ -365,9 +365,9 @@ class OpticalSystem3D(OpticalSystemBase):
         for (cat, name, items), n in zip(groups, counts):
             d = {}
             if n:
-                for i, k in enumerate(TRI_FIELDS):
-                    d[k] = tri[i, lo:lo + n]
-                d["norm"] = norm[lo:lo + n]
+                whole = n == tri.shape[1]
+                d.update(zip(TRI_FIELDS, (tri if whole else tri[:, lo:lo + n]).unbind(0)))
+                d["norm"] = norm if whole else norm[lo:lo + n]
                 live = [b for b in items if bool(b)]
                 extra = set(live[0].keys()) - set(TRI_FIELDS) - {"norm"}
                 for b in live[1:]:
@@ -377,7 +377,7 @@ class OpticalSystem3D(OpticalSystemBase):
                 d["catagory"] = self._category_tensor(cat, d["xp"])
             setattr(self, "_amalgamated_" + name, d)
             lo += n
-        merged = {k: tri[i] for i, k in enumerate(TRI_FIELDS)}
+        merged = dict(zip(TRI_FIELDS, tri.unbind(0)))
         merged["norm"] = norm
         merged["catagory"] = self._cached_cat(
             ("merged", "catagory"),
