@@ -47,7 +47,7 @@ def can_build():
 def _deps():
     return sources() + [os.path.join(CSRC, "common.cuh"),
                         os.path.join(HERE, "..", "include", "tfrt_b200.h"),
-                        os.path.join(HERE, "_reuse_patch.py")]
+                        os.path.join(HERE, "_reuse_patch.py"), os.path.join(HERE, "_sass_sched.py")]
 
 
 def source_hash():
@@ -83,12 +83,19 @@ def build(force=False, verbose=False):
         if os.path.exists(tmp):
             os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    # Post-link step: set the operand-reuse flags ptxas leaves unset in the search kernel's packed
-    # FP32 loops (_reuse_patch.py; +2 % on k_intersect3d, same bits out).  TFRT_REUSE_PATCH=0 skips
-    # it; without cuobjdump the library is used as ptxas wrote it.
+    # Post-link steps on the search kernel's packed FP32 loops (same bits out, profiles/
+    # r2_k1_tuning.md sections 5 and 6): the loop bodies of the 8-rays-per-thread kernels are
+    # re-ordered so that runs of instructions share their coefficient operand (_sass_sched.py),
+    # then the operand-reuse flags ptxas leaves unset elsewhere are set (_reuse_patch.py).
+    # TFRT_SASS_SCHED=0 / TFRT_REUSE_PATCH=0 skip them; without cuobjdump the library is used as
+    # ptxas wrote it.
     if os.environ.get("TFRT_REUSE_PATCH", "1") != "0":
         if shutil.which("cuobjdump"):
-            from . import _reuse_patch
+            from . import _reuse_patch, _sass_sched
+            if os.environ.get("TFRT_SASS_SCHED", "1") != "0":
+                rep = _sass_sched.reschedule(tmp, min_packed=100)
+                if verbose:
+                    print(f"loop bodies re-scheduled: {len(rep)}")
             n = _reuse_patch.patch(tmp)
             if verbose:
                 print(f"reuse flags set: {n}")

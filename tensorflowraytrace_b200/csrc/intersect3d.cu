@@ -255,7 +255,6 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                     const float2 s1 = f2(c1.z, c1.w), s2 = f2(c2.x, c2.y), s0 = f2(c2.z, c2.w);
                     const float2 e1 = f2(c3.x, c3.y), e2 = f2(c3.z, c3.w), e0 = f2(c4.x, c4.y);
                     float2 tt[NR], xx[NR];
-                    float xmin = __int_as_float(0x7f800000);
 #pragma unroll
                     for (int i = 0; i < NR; ++i) {
                         float2 det = k_fma2(m1, bc(D[K1][i]), bc(D[K][i]));
@@ -280,11 +279,42 @@ k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
                         const float2 ea = abs2(ev);
                         const float2 kk = k_add2(sv, neg2(ea));
                         const float2 x = k_add2(ea, abs2(kk));
-                        // x >= 0 or NaN (fminf drops a NaN operand): the smallest x decides
-                        // whether any of the thread's rays is inside one of the two triangles
-                        xmin = fminf(fminf(xmin, x.x), x.y);             // one FMNMX3
                         tt[i] = t;
                         xx[i] = x;
+                    }
+                    // x >= 0 or NaN (fminf drops a NaN operand): the smallest x decides whether
+                    // any of the thread's rays is inside one of the two triangles.  Reduced as a
+                    // tree of three-input minima (FMNMX3): depth 3 for 16 values instead of a
+                    // chain of 8 dependent instructions at the end of the loop body.
+                    float xmin;
+                    {
+                        float lvl[(2 * NR + 2) / 3 + 1];
+                        int m = 0;
+#pragma unroll
+                        for (int i = 0; i + 1 < NR; i += 3) {     // three rays = six values -> two minima
+                            if (i + 2 < NR) {
+                                lvl[m++] = fminf(fminf(xx[i].x, xx[i].y), xx[i + 1].x);
+                                lvl[m++] = fminf(fminf(xx[i + 1].y, xx[i + 2].x), xx[i + 2].y);
+                            } else {                               // two rays left: four values
+                                lvl[m++] = fminf(fminf(xx[i].x, xx[i].y), xx[i + 1].x);
+                                lvl[m++] = xx[i + 1].y;
+                            }
+                        }
+                        if (NR % 3 == 1) lvl[m++] = fminf(xx[NR - 1].x, xx[NR - 1].y);
+                        // NR = 8: six values; NR = 4: three; NR = 2: two
+#pragma unroll
+                        for (int step = 0; step < 3; ++step) {
+                            int o = 0;
+#pragma unroll
+                            for (int i = 0; i < m; i += 3) {
+                                float v = lvl[i];
+                                if (i + 1 < m) v = fminf(v, lvl[i + 1]);
+                                if (i + 2 < m) v = fminf(v, lvl[i + 2]);
+                                lvl[o++] = v;
+                            }
+                            m = o;
+                        }
+                        xmin = lvl[0];
                     }
                     // Rare path (a few inside hits per ray over the whole mesh): warp-uniform
                     // branch, so the common case pays the min chain, one compare and one vote per

@@ -95,3 +95,28 @@ def test_operand_reuse_patch_is_applied_and_idempotent(tmp_path):
         a, b = int.from_bytes(before[i:i + 8], "little"), int.from_bytes(after[i:i + 8], "little")
         assert (a ^ b) & ~mask == 0 and b & a == a
     assert _reuse_patch.patch(raw, dry=True) == 0
+
+
+def test_rescheduled_loop_bodies_respect_the_dependency_graph(tmp_path):
+    """_sass_sched.py re-orders the loop bodies of the 8-rays-per-thread search kernels: every
+    block must be a permutation of ptxas's instructions (only stall / yield / reuse bits differ),
+    in an order that respects ptxas's dependency graph, with stall counts that keep ptxas's own
+    minimum distances."""
+    import shutil
+    import subprocess
+    import pytest
+    from tensorflowraytrace_b200 import _sass_sched
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    raw = str(tmp_path / "raw.so")
+    new = str(tmp_path / "new.so")
+    subprocess.run([_build._nvcc()] + _build.NVCC_FLAGS +
+                   ["-o", raw, os.path.join(_build.CSRC, "intersect3d.cu"),
+                    os.path.join(_build.CSRC, "abi.cu")], check=True)
+    shutil.copy(raw, new)
+    report = _sass_sched.reschedule(new, min_packed=100)
+    assert len(report) == 6            # three axis loops x (queue, no queue)
+    for _, _, n, before, after, _, _ in report:
+        assert n > 100 and after < before
+    assert _sass_sched.verify(raw, new) == 6
+    assert len(open(raw, "rb").read()) == len(open(new, "rb").read())
