@@ -52,6 +52,22 @@ def functions(binary):
     return funcs
 
 
+def locate(data, words, name, binary):
+    """File offset of a function's first instruction: its leading instruction words, as many as it
+    takes to be unique in the file (template instances share their prologues)."""
+    n = 8
+    while True:
+        probe = b"".join(lo.to_bytes(8, "little") + hi.to_bytes(8, "little") for lo, hi in words[:n])
+        base = data.find(probe)
+        if base < 0:
+            raise RuntimeError(f"{name}: code not found in {binary} (compressed fatbin?)")
+        if data.find(probe, base + 1) < 0:
+            return base
+        if n >= len(words):
+            raise RuntimeError(f"{name}: code not found uniquely in {binary}")
+        n = min(2 * n, len(words))
+
+
 def sources(text):
     """(opcode, predicated, dest registers, [(register, width) or None per source slot])."""
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)\s+(.*)", text)
@@ -126,11 +142,7 @@ def patch(binary, sub="k_intersect3d", keep_warp=True, max_chain=0, across_mufu=
         todo = plan(insns, max_chain, across_mufu)
         if not todo and not no_yield_all:
             continue
-        # locate the function's code in the file by its first instructions
-        probe = b"".join(lo.to_bytes(8, "little") + hi.to_bytes(8, "little") for _, _, lo, hi in insns[:8])
-        base = data.find(probe)
-        if base < 0 or data.find(probe, base + 1) >= 0:
-            raise RuntimeError(f"{name}: code not found uniquely in {binary} (compressed fatbin?)")
+        base = locate(data, [(lo, hi) for _, _, lo, hi in insns], name, binary)
         base -= insns[0][0]
         flagged = sum(1 for _, t, _, _ in insns if ".reuse" in t)
         for i, slot in todo:

@@ -35,7 +35,7 @@ parity suite run on the re-scheduled library.
 """
 import re
 
-from ._reuse_patch import PACKED, functions
+from ._reuse_patch import PACKED, functions, locate
 
 CONTROL = ("BRA", "BSSY", "BSYNC", "VOTE", "EXIT", "WARPSYNC", "BAR", "CALL", "RET", "JMP", "BRX",
            "BREAK", "NANOSLEEP", "YIELD", "DEPBAR", "ENDCOLLECTIVE", "ELECT", "SYNCS", "UBLKCP",
@@ -44,7 +44,7 @@ MEMORY = ("LDS", "LDG", "STS", "STG", "LDC", "LDCU", "ATOMS", "ATOMG", "ATOM", "
           "ST", "LDL", "STL")
 LMAX = 16
 # tuning switches of the study in profiles/r2_k1_tuning.md section 6 (defaults = shipped)
-OPTIONS = {"yield": "never", "mufu_first": False, "share_weight": 1}
+OPTIONS = {"yield": "never", "mufu_first": False, "share_weight": 1, "mufu_gap": 0}
 
 
 def ctrl(hi):
@@ -310,6 +310,7 @@ def schedule(block, lat, gap, scoreboard=None):
     ready = [i for i in range(n) if indeg[i] == 0 and i != last]
     order, t_new = [], {}
     prev = None
+    last_mufu = -99
     while len(order) < n - 1:
         if not ready:
             raise Unschedulable("dependency cycle")
@@ -319,6 +320,8 @@ def schedule(block, lat, gap, scoreboard=None):
             for j, kind in deps[i].items():
                 earliest = max(earliest, t_new[j] + need(j, i, kind, False))
             floor = 0 if prev is None else t_new[prev] + min_gap(prev, i)
+            if block[i].base == "MUFU":      # soft: special-function instructions share one queue
+                earliest = max(earliest, last_mufu + OPTIONS["mufu_gap"])
             t_i = max(earliest, floor)
             share = 0
             if prev is not None and block[i].base in PACKED and block[prev].base in PACKED:
@@ -333,6 +336,8 @@ def schedule(block, lat, gap, scoreboard=None):
         order.append(best)
         t_new[best] = best_t
         prev = best
+        if block[best].base == "MUFU":
+            last_mufu = best_t
         for u in users[best]:
             indeg[u] -= 1
             if indeg[u] == 0 and u != last:
@@ -424,10 +429,7 @@ def reschedule(binary, sub="k_intersect3d", min_packed=24, dry=False, verbose=Fa
         blocks = split_blocks(insns)
         lat, gap = observe(insns, blocks)
         scoreboard = scoreboard_registers(insns)
-        probe = b"".join(i.lo.to_bytes(8, "little") + i.hi.to_bytes(8, "little") for i in insns[:8])
-        base = data.find(probe)
-        if base < 0 or data.find(probe, base + 1) >= 0:
-            raise RuntimeError(f"{name}: code not found uniquely in {binary}")
+        base = locate(data, [(i.lo, i.hi) for i in insns], name, binary)
         base -= insns[0].addr
         for idxs in blocks:
             block = [insns[i] for i in idxs]

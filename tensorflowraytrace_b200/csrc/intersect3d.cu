@@ -90,7 +90,7 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 __device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
 
 template <int NR, bool kQueue>
-__global__ void __launch_bounds__(kThreads, (NR >= 8 ? TFRT_K1_MINBLOCKS : 1))
+__global__ void __launch_bounds__(kThreads, ((NR >= 8 || TFRT_K1_FORCE_NR) ? TFRT_K1_MINBLOCKS : 1))
 k_intersect3d(const float *__restrict__ sx, const float *__restrict__ sy,
               const float *__restrict__ sz, const float *__restrict__ ex,
               const float *__restrict__ ey, const float *__restrict__ ez,

@@ -88,6 +88,23 @@ def rel_err(a, b, floor=ATOL_FRACTION, scale=None):
 # ----------------------------------------------------------------------------------------------
 # CUDA-vs-oracle comparison of a whole trace
 
+def near_tie_bound(ray_hits, size_eps=EPS["size_epsilion"], p=1e-6):
+    """Upper bound on the number of near-tie index mismatches among `ray_hits` ray-surface hits.
+    A near tie needs the hit inside the strip where the size_epsilion inflation makes two
+    neighbouring triangles both valid: barycentric width size_eps on either side of each of the
+    three edges, i.e. a fraction 6 * size_eps of the triangle's area (every one of them counted
+    as a mismatch, although only about half flip the winner).  The count is Poisson with that
+    mean; the bound is its (1 - p) quantile."""
+    import math
+    mean = ray_hits * 6.0 * size_eps
+    k, term, cdf = 0, math.exp(-mean), math.exp(-mean)
+    while 1.0 - cdf > p:
+        k += 1
+        term *= mean / k
+        cdf += term
+    return k
+
+
 def compare_trace(engine, oracle, near_tie_rel=1e-6):
     """Compare the fused CUDA trace held by `engine.last_trace` with a traced oracle engine,
     iteration by iteration and slot by slot.

@@ -120,7 +120,8 @@ def test_largest_mesh_with_a_ray_subsample():
     oracle.ray_trace(3)
     cmp = helpers.compare_trace(engine, oracle)
     assert cmp["max_rel"] < 1e-5
-    assert cmp["mismatches"] <= 8      # near ties only (compare_trace raises on anything else)
+    # near ties only (compare_trace raises on anything else); 2 048 rays cross two lens surfaces
+    assert cmp["mismatches"] <= helpers.near_tie_bound(2 * 2048)
     # gradients: oracle with fp64 vertices formed from the parameters (autograd needs the chain)
     oracle, oparams = helpers.oracle_from_scene(scene, requires_grad=True)
     oracle.ray_trace(3)

@@ -406,7 +406,8 @@ def test_full_size_cfg5_subsample_parity():
     cmp = helpers.compare_trace(sub, oracle)
     assert cmp["iterations"] == 3
     assert cmp["max_rel"] < POINT_TOL, cmp
-    assert cmp["mismatches"] <= 6                        # near ties only (others raise)
+    # near ties only (anything else raises); 3 072 rays cross the two lens surfaces
+    assert cmp["mismatches"] <= helpers.near_tie_bound(2 * 3072)
 
 
 def test_full_size_cfg4_subsample_parity():
