@@ -350,6 +350,17 @@ int tfrt_sample_sphere(uint32_t seed, uint32_t stream, uint32_t epoch, int32_t m
                        int32_t n, int64_t total, double angular_size, double radius, float *points,
                        float *ranks, void *stream_);
 
+/* The ray fields of a directed 3D source with paired domains (tfrt/sources.py:590-635 PointSource,
+ * :820-866 AngularSource) in one launch: dirs (n,3) unit vectors about +x, base (n,base_dim) points
+ * in the y-z plane (base_dim 2) or in space (3), or NULL (all rays start at `center`).  Both are
+ * rotated by the unit quaternion quat = (w,x,y,z), the base is offset by center,
+ * end = start + ray_length * direction; forward = 0 swaps the two ends.  rows: (7,n) fp32 block
+ * x_start, y_start, z_start, x_end, y_end, z_end, wavelength (wavelength (n,) copied, 0 if NULL) --
+ * the layout tfrt_trace3d_forward reads as src[0..6]. */
+int tfrt_rays_from_directions(int32_t n, const float *dirs, const float *base, int32_t base_dim,
+                              const double quat[4], const double center[3], double ray_length,
+                              int32_t forward, const float *wavelength, float *rows, void *stream_);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (roofline denominators): run an FFMA-only loop on every SM and return the
  * achieved fp32 FLOP/s through *flops_per_s (host).  packed=0: scalar FFMA, 1: FFMA2 (f32x2),

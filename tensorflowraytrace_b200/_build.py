@@ -16,6 +16,8 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libtfrt_b200.so")
+# the same sources as ptxas wrote them (no post-link steps): only the A/B parity test loads it
+PTXAS_LIB_PATH = os.path.join(HERE, "libtfrt_b200_ptxas.so")
 
 SOURCES = ["abi.cu", "pack.cu", "intersect3d.cu", "trace3d.cu", "backward3d.cu", "trace2d.cu",
            "sources.cu", "grid3d.cu"]
@@ -68,12 +70,15 @@ def needs_build():
     return not os.path.exists(LIB_PATH)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out_path=None, post_link=True):
     """Compile every CUDA source into libtfrt_b200.so (sm_100a).  Returns the library path.
     The library is written under a temporary name and renamed, so concurrent processes (one per
-    GPU under torchrun) never load a half-written file."""
-    if not force and not needs_build():
-        return LIB_PATH
+    GPU under torchrun) never load a half-written file.  out_path / post_link=False build the
+    comparison library of tests/test_gpu_round2.py (same sources, instruction order as ptxas
+    wrote it)."""
+    out_path = out_path or LIB_PATH
+    if not force and os.path.exists(out_path):
+        return out_path
     fd, tmp = tempfile.mkstemp(prefix=".libtfrt_b200.", suffix=".so", dir=HERE)
     os.close(fd)
     cmd = ([_nvcc()] + NVCC_FLAGS + [f'-DTFRT_SOURCE_HASH="{source_hash()}"']
@@ -89,24 +94,42 @@ def build(force=False, verbose=False):
     # then the operand-reuse flags ptxas leaves unset elsewhere are set (_reuse_patch.py).
     # TFRT_SASS_SCHED=0 / TFRT_REUSE_PATCH=0 skip them; without cuobjdump the library is used as
     # ptxas wrote it.
-    if os.environ.get("TFRT_REUSE_PATCH", "1") != "0":
+    if post_link and os.environ.get("TFRT_REUSE_PATCH", "1") != "0":
         if shutil.which("cuobjdump"):
             from . import _reuse_patch, _sass_sched
-            if os.environ.get("TFRT_SASS_SCHED", "1") != "0":
-                rep = _sass_sched.reschedule(tmp, min_packed=100)
+            # each step rewrites the file only after it has succeeded on every block; a step that
+            # fails leaves a correct library behind (as ptxas wrote it, or with the earlier step)
+            try:
+                if os.environ.get("TFRT_SASS_SCHED", "1") != "0":
+                    rep = _sass_sched.reschedule(tmp, min_packed=100)
+                    if verbose:
+                        print(f"loop bodies re-scheduled: {len(rep)}")
+                n = _reuse_patch.patch(tmp)
                 if verbose:
-                    print(f"loop bodies re-scheduled: {len(rep)}")
-            n = _reuse_patch.patch(tmp)
-            if verbose:
-                print(f"reuse flags set: {n}")
+                    print(f"reuse flags set: {n}")
+            except Exception as e:      # noqa: BLE001  (an optimisation must not break the build)
+                print(f"tensorflowraytrace_b200: post-link step skipped ({type(e).__name__}: {e})",
+                      file=sys.stderr)
         else:
             print("tensorflowraytrace_b200: cuobjdump not found, operand-reuse patch skipped",
                   file=sys.stderr)
     os.chmod(tmp, 0o755)
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, out_path)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out_path
+
+
+def build_unpatched(force=False):
+    """libtfrt_b200_ptxas.so: the library without the post-link steps, rebuilt when the sources
+    changed (its embedded source hash is compared)."""
+    if not force and os.path.exists(PTXAS_LIB_PATH):
+        with open(PTXAS_LIB_PATH, "rb") as f:
+            data = f.read()
+        at = data.find(b"TFRT_SOURCE_HASH=")
+        if at >= 0 and data[at + 17:at + 33].decode(errors="replace") == source_hash():
+            return PTXAS_LIB_PATH
+    return build(force=True, out_path=PTXAS_LIB_PATH, post_link=False)
 
 
 if __name__ == "__main__":

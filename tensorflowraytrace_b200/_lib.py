@@ -120,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "tfrt_trace3d_sync_bytes", "tfrt_trace3d_forward", "tfrt_history_count", "tfrt_materialize3d",
     "tfrt_trace3d_backward",
     "tfrt_intersect2d", "tfrt_trace2d_forward", "tfrt_trace2d_backward",
-    "tfrt_sample_uniform", "tfrt_sample_square", "tfrt_sample_sphere",
+    "tfrt_sample_uniform", "tfrt_sample_square", "tfrt_sample_sphere", "tfrt_rays_from_directions",
     "tfrt_fp32_peak", "tfrt_launch_count", "tfrt_profile_enable", "tfrt_profile_read",
 ]
 
@@ -135,13 +135,18 @@ def lib_path():
 
 
 def _stale(path):
-    """The library's embedded source hash differs from the hash of the sources on disk."""
+    """The library's embedded source hash differs from the hash of the sources on disk.  Read
+    from the file's bytes: dlopen() here would keep the old mapping alive, and loading the
+    rebuilt library under the same name would return it again."""
     try:
-        probe = ctypes.CDLL(path)
-        probe.tfrt_source_hash.restype = ctypes.c_char_p
-        return probe.tfrt_source_hash().decode() != _build.source_hash()
-    except (OSError, AttributeError):
+        with open(path, "rb") as f:
+            data = f.read()
+    except OSError:
         return True
+    at = data.find(b"TFRT_SOURCE_HASH=")
+    if at < 0:
+        return True
+    return data[at + 17:at + 33].decode(errors="replace") != _build.source_hash()
 
 
 def load():
@@ -155,10 +160,16 @@ def load():
         # the sources changed since the library was built (a kernel edit without an ABI bump):
         # never measure or test old code silently
         _build.build(force=True)
+    _lib = open_library(_build.LIB_PATH)
+    return _lib
+
+
+def open_library(path):
+    """ctypes handle of a build of the library, prototypes declared and ABI checked."""
     try:
-        lib = ctypes.CDLL(_build.LIB_PATH)
+        lib = ctypes.CDLL(path)
     except OSError as e:  # pragma: no cover
-        raise RuntimeError(f"tensorflowraytrace_b200: cannot load {_build.LIB_PATH}: {e}") from e
+        raise RuntimeError(f"tensorflowraytrace_b200: cannot load {path}: {e}") from e
     lib.tfrt_last_error.restype = ctypes.c_char_p
     lib.tfrt_abi_version.restype = ctypes.c_int
     lib.tfrt_source_hash.restype = ctypes.c_char_p
@@ -175,10 +186,12 @@ def load():
     lib.tfrt_sample_square.argtypes = [u32, u32, u32, i64, i32, f64, f64, c_void_p, c_void_p, c_void_p]
     lib.tfrt_sample_sphere.argtypes = [u32, u32, u32, i32, i64, i32, i64, f64, f64, c_void_p,
                                        c_void_p, c_void_p]
+    lib.tfrt_rays_from_directions.argtypes = [i32, c_void_p, c_void_p, i32, c_void_p, c_void_p, f64,
+                                              i32, c_void_p, c_void_p, c_void_p]
     lib.tfrt_launch_count.restype = ctypes.c_longlong
     lib.tfrt_launch_count.argtypes = [ctypes.c_int]
     if lib.tfrt_abi_version() != ABI_VERSION:
-        raise RuntimeError(f"tensorflowraytrace_b200: {_build.LIB_PATH} has ABI version "
+        raise RuntimeError(f"tensorflowraytrace_b200: {path} has ABI version "
                            f"{lib.tfrt_abi_version()}, this package needs {ABI_VERSION}; rebuild "
                            f"with `python -m tensorflowraytrace_b200._build --force`")
     for code, mirror in enumerate(STRUCT_MIRRORS):
@@ -186,7 +199,6 @@ def load():
             raise RuntimeError(f"tensorflowraytrace_b200: ctypes mirror of {mirror.__name__} is "
                                f"{ctypes.sizeof(mirror)} bytes, the library's is "
                                f"{lib.tfrt_struct_size(code)}")
-    _lib = lib
     return lib
 
 

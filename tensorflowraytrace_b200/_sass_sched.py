@@ -44,7 +44,7 @@ MEMORY = ("LDS", "LDG", "STS", "STG", "LDC", "LDCU", "ATOMS", "ATOMG", "ATOM", "
           "ST", "LDL", "STL")
 LMAX = 16
 # tuning switches of the study in profiles/r2_k1_tuning.md section 6 (defaults = shipped)
-OPTIONS = {"yield": "never", "mufu_first": False, "share_weight": 1, "mufu_gap": 0}
+OPTIONS = {"yield": "never", "mufu_first": False, "share_weight": 1, "mufu_gap": 6}
 
 
 def ctrl(hi):

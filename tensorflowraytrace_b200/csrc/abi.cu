@@ -17,7 +17,10 @@ extern "C" int tfrt_abi_version(void) { return TFRT_B200_ABI_VERSION; }
 #ifndef TFRT_SOURCE_HASH
 #define TFRT_SOURCE_HASH "unknown"
 #endif
-extern "C" const char *tfrt_source_hash(void) { return TFRT_SOURCE_HASH; }
+// The marker lets the loader read the hash out of the file without dlopen()ing it (a library
+// that is already mapped would be returned again after a rebuild under the same name).
+static const char g_source_hash[] = "TFRT_SOURCE_HASH=" TFRT_SOURCE_HASH;
+extern "C" const char *tfrt_source_hash(void) { return g_source_hash + 17; }
 extern "C" size_t tfrt_struct_size(int which) {
     switch (which) {
     case 0: return sizeof(TfrtMaterial);

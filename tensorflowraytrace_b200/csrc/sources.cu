@@ -99,6 +99,52 @@ __global__ void k_sample_sphere(SampleKey key, int mode, int n, long long total,
     ranks[2 * i + 1] = (float)theta;
 }
 
+// Directed sources (tfrt/sources.py:590-635 PointSource, :820-866 AngularSource, 3D, paired
+// domains): rotate the unit directions (and the base points, given in the y-z plane or in 3D) by
+// the unit quaternion q = (w, r) with v' = v + 2 r x (r x v + w v), offset the base by `center`,
+// end = start + ray_length * direction; `forward` = 0 swaps the two ends.  fp64 inside, one
+// rounding to fp32 on the way out.  Writes the seven rows x_start .. z_end, wavelength of the
+// (7, n) block the trace kernels read.
+struct RayFrame { double q[4], center[3], ray_length; };
+
+__device__ __forceinline__ void rotate(const double q[4], const double v[3], double out[3]) {
+    const double w = q[0], rx = q[1], ry = q[2], rz = q[3];
+    const double tx = ry * v[2] - rz * v[1] + w * v[0];
+    const double ty = rz * v[0] - rx * v[2] + w * v[1];
+    const double tz = rx * v[1] - ry * v[0] + w * v[2];
+    out[0] = v[0] + 2.0 * (ry * tz - rz * ty);
+    out[1] = v[1] + 2.0 * (rz * tx - rx * tz);
+    out[2] = v[2] + 2.0 * (rx * ty - ry * tx);
+}
+
+__global__ void k_rays_from_directions(RayFrame f, int n, const float *__restrict__ dirs,
+                                       const float *__restrict__ base, int base_dim, int forward,
+                                       const float *__restrict__ wavelength,
+                                       float *__restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d[3] = {dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]};
+    double dir[3], start[3] = {f.center[0], f.center[1], f.center[2]};
+    rotate(f.q, d, dir);
+    if (base) {
+        double b[3], rb[3];
+        if (base_dim == 2) { b[0] = 0.0; b[1] = base[2 * i]; b[2] = base[2 * i + 1]; }
+        else { b[0] = base[3 * i]; b[1] = base[3 * i + 1]; b[2] = base[3 * i + 2]; }
+        rotate(f.q, b, rb);
+        for (int c = 0; c < 3; ++c) start[c] += rb[c];
+    }
+    const size_t N = (size_t)n;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // the reference forms both ends in float32: start, then start + length * direction
+        const float s = (float)start[c];
+        const float e = (float)((double)s + f.ray_length * dir[c]);
+        rows[(forward ? c : 3 + c) * N + i] = s;
+        rows[(forward ? 3 + c : c) * N + i] = e;
+    }
+    rows[6 * N + i] = wavelength ? wavelength[i] : 0.f;
+}
+
 }  // namespace
 
 static SampleKey make_key(uint32_t seed, uint32_t stream, uint32_t epoch, long long first) {
@@ -141,6 +187,26 @@ extern "C" int tfrt_sample_sphere(uint32_t seed, uint32_t stream, uint32_t epoch
     if (n == 0) return 0;
     k_sample_sphere<<<tfrt_div_up(n, 256), 256, 0, (cudaStream_t)stream_>>>(
         make_key(seed, stream, epoch, first), mode, n, total, angular_size, radius, points, ranks);
+    tfrt_note_launch(1);
+    TFRT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tfrt_rays_from_directions(int32_t n, const float *dirs, const float *base,
+                                         int32_t base_dim, const double quat[4],
+                                         const double center[3], double ray_length,
+                                         int32_t forward, const float *wavelength, float *rows,
+                                         void *stream_) {
+    TFRT_REQUIRE(n >= 0 && quat && center && ((dirs && rows) || n == 0) &&
+                     (!base || base_dim == 2 || base_dim == 3),
+                 "tfrt_rays_from_directions: bad arguments");
+    if (n == 0) return 0;
+    RayFrame f;
+    for (int c = 0; c < 4; ++c) f.q[c] = quat[c];
+    for (int c = 0; c < 3; ++c) f.center[c] = center[c];
+    f.ray_length = ray_length;
+    k_rays_from_directions<<<tfrt_div_up(n, 256), 256, 0, (cudaStream_t)stream_>>>(
+        f, n, dirs, base, base_dim, forward, wavelength, rows);
     tfrt_note_launch(1);
     TFRT_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -219,6 +219,15 @@ class OpticalSystemBase(RecursivelyUpdatable):
         """The amalgamated source rays as one fp32 block [x_start .. z_end, wavelength] -- (7,N)
         in 3D, (5,N) in 2D, the layout the trace kernels read -- built once per update()."""
         rows = getattr(self, "_source_rows", None)
+        if rows is None and len(self._sources) == 1 and self.dimension == 3:
+            # a directed source writes its rays straight into this layout (sources._publish_fused)
+            blk = getattr(self._sources[0], "_ray_block", None)
+            f = self._amalgamated_sources
+            if blk is not None and f.get("wavelength") is not None and \
+                    f["x_start"].data_ptr() == blk.data_ptr() and \
+                    f["x_start"].shape[0] == blk.shape[1] and \
+                    f["wavelength"].data_ptr() == blk[6].data_ptr():
+                rows = self._source_rows = blk
         if rows is None:
             f = self._amalgamated_sources
             n = f["x_start"].shape[0]

@@ -218,6 +218,24 @@ def sample_sphere(seed, stream, epoch, mode, first, n, total, angular_size, radi
     return points, ranks
 
 
+def rays_from_directions(dirs, base, quat, center, ray_length, forward, wavelength):
+    """(7,N) f32 block x_start .. z_end, wavelength of a directed 3D source in one launch:
+    dirs (N,3) unit vectors about +x, base (N,2 | N,3) or None, quat (w,x,y,z), center (3,)."""
+    _require_cuda(dirs, base, wavelength)
+    dirs = _f32(dirs)
+    n = dirs.shape[0]
+    base = None if base is None else _f32(base)
+    wavelength = None if wavelength is None else _f32(wavelength)
+    rows = torch.empty((7, n), dtype=torch.float32, device=dirs.device)
+    q = (ctypes.c_double * 4)(*[float(v) for v in quat])
+    c = (ctypes.c_double * 3)(*[float(v) for v in center])
+    check(_lib.load().tfrt_rays_from_directions(
+        n, ptr(dirs), ptr(base), 0 if base is None else int(base.shape[1]), q, c,
+        float(ray_length), 1 if forward else 0, ptr(wavelength), ptr(rows), _stream()),
+        "tfrt_rays_from_directions")
+    return rows
+
+
 class TraceWorkspace:
     """Tape and scratch of a whole-loop trace for one (N rays, K iterations) shape: one device
     allocation carved into the arrays of TfrtTrace3DArgs, plus a pinned host mirror of the

@@ -327,7 +327,31 @@ class _DirectedSource(SourceBase, RotationBase):
     """Common tail of PointSource / AngularSource: write the ray fields from start points and
     unit directions (or 2D angles)."""
 
+    def _publish_fused(self, dirs, base, forward, expanded_vars):
+        """3D, device-resident, nothing to differentiate: rotation, offset and both ray ends in one
+        kernel (csrc/sources.cu), written straight into the (7,N) block the trace kernels read;
+        the ray fields are its rows (OpticalSystemBase.source_rows hands the block on as it is).
+        Returns False when the general path has to run."""
+        wl = expanded_vars.get("wavelengths")
+        tensors = [t for t in (dirs, base, wl) if t is not None]
+        if self._dimension != 3 or not all(t.is_cuda and not t.requires_grad for t in tensors):
+            return False
+        n = dirs.shape[0]
+        if dirs.shape != (n, 3) or (base is not None and (base.shape[0] != n or base.shape[1] not in (2, 3))) \
+                or (wl is not None and wl.shape != (n,)):
+            return False
+        from . import kernels
+        block = kernels.rays_from_directions(dirs, base, self._central_angle, self._center_host,
+                                             self.ray_length, forward, wl)
+        for i, name in enumerate(("x_start", "y_start", "z_start", "x_end", "y_end", "z_end")):
+            self._fields[name] = block[i]
+        if wl is not None:
+            self._fields["wavelength"] = block[6]
+        self._ray_block = block
+        return True
+
     def _publish(self, start, angles, forward, expanded_vars):
+        self._ray_block = None
         if self._dimension == 2:
             end = start + self.ray_length * torch.stack([torch.cos(angles), torch.sin(angles)], 1)
         else:
@@ -368,6 +392,8 @@ class PointSource(_DirectedSource):
         return out
 
     def _internal_update(self, expanded_vars):
+        if self._publish_fused(expanded_vars["angles"], None, self.start_on_center, expanded_vars):
+            return
         angles = self._rotate_angles(expanded_vars["angles"])
         start = torch.broadcast_to(self._center.to(angles.device).reshape(1, -1),
                                    (angles.shape[0], self._dimension))
@@ -392,6 +418,7 @@ class PointSource(_DirectedSource):
     @center.setter
     def center(self, val):
         self._center = _center(val, self.dimension, "PointSource")
+        self._center_host = np.asarray(val, dtype=np.float64).reshape(-1)
 
     @property
     def angular_distribution(self):
@@ -424,6 +451,9 @@ class AngularSource(_DirectedSource):
         return out
 
     def _internal_update(self, expanded_vars):
+        if self._publish_fused(expanded_vars["angles"], expanded_vars["base_points"],
+                               self.start_on_base, expanded_vars):
+            return
         angles = self._rotate_angles(expanded_vars["angles"])
         base = self._rotate_points(expanded_vars["base_points"])
         start = self._center.to(base.device).reshape(1, -1) + base
@@ -453,6 +483,7 @@ class AngularSource(_DirectedSource):
     @center.setter
     def center(self, val):
         self._center = _center(val, self.dimension, "AngularSource")
+        self._center_host = np.asarray(val, dtype=np.float64).reshape(-1)
 
     @property
     def angular_distribution(self):

@@ -315,3 +315,62 @@ def test_scene_in_millimetres_and_far_from_the_origin(factor, offset):
     d = check_diagnostics(engine.last_trace, f"x{factor}+{offset}")
     # nearly every ray still reaches the target
     assert engine.last_trace.history_count("finished") > 0.95 * 8192, d
+
+
+# --------------------------------------------------------------------------- post-link steps, A/B
+@pytest.mark.parametrize("case", ["soup_8rays", "soup_short_items", "cfg5_mesh", "grazing"])
+def test_rescheduled_search_kernel_is_bit_identical_to_the_ptxas_build(case, monkeypatch):
+    """The build re-orders the search kernel's loop bodies and sets operand-reuse flags after
+    ptxas (_sass_sched.py, _reuse_patch.py).  The same sources as ptxas wrote them are built
+    beside the library (libtfrt_b200_ptxas.so); every output of the b1 seam -- hit index, hit
+    point, ray_u, barycentrics, validity, re-validation counters -- must be bit-identical between
+    the two builds, on inputs that go through every kernel instance (8 / 4 / 2 rays per thread,
+    item queue or not, split triangle ranges with the atomic merge) and through the rare path
+    (near ties, grazing rays)."""
+    from tensorflowraytrace_b200 import _build, _lib
+    if not os.path.exists(_build.PTXAS_LIB_PATH):
+        if not _build.can_build():
+            pytest.skip("comparison build not present and nvcc not available")
+        _build.build_unpatched()
+    plain = _lib.open_library(_build.PTXAS_LIB_PATH)
+    shipped = _lib.load()
+    assert plain.tfrt_source_hash() == shipped.tfrt_source_hash()
+
+    rng = np.random.default_rng(7)
+    if case == "cfg5_mesh":
+        scene = scenes.config5(ray_count=300000)
+        system = scenes.build_engine(scene, eps=helpers.EPS)[0].optical_system
+        tri = system.merged_device_arrays()[0].detach()
+        rays = torch.stack([system.sources[k] for k in RAYS]).float()
+    else:
+        n_rays, n_tri = {"soup_8rays": (400000, 3000), "soup_short_items": (5000, 40000),
+                         "grazing": (200000, 2048)}[case]
+        centre = rng.uniform(-1, 1, (n_tri, 3))
+        tri_np = np.concatenate([centre + rng.normal(0, 0.08, (n_tri, 3)) for _ in range(3)], 1).T
+        start = rng.uniform(-1, 1, (n_rays, 3)) + np.array([-3.0, 0, 0])
+        end = rng.uniform(-1, 1, (n_rays, 3)) + np.array([3.0, 0, 0])
+        if case == "grazing":
+            # aim every ray at a point on an edge of some triangle: ties and edge rounding
+            pick = rng.integers(0, n_tri, n_rays)
+            a, b = tri_np[0:3, pick].T, tri_np[3:6, pick].T
+            w = rng.uniform(0, 1, (n_rays, 1))
+            end = start + 2.0 * ((1 - w) * a + w * b - start)
+        tri = dev(tri_np)
+        rays = dev(np.concatenate([start, end], 1).T)
+
+    def run(lib):
+        monkeypatch.setattr(_lib, "_lib", lib)
+        packed = kernels.pack_triangles(tri, helpers.EPS["size_epsilion"])
+        diag = torch.zeros(4, dtype=torch.int32, device=DEV)
+        out = kernels.intersect3d(rays, tri, packed, helpers.EPS["intersect_epsilion"],
+                                  helpers.EPS["size_epsilion"], helpers.EPS["ray_start_epsilion"],
+                                  diag=diag)
+        torch.cuda.synchronize()
+        return out, diag
+
+    a, da = run(shipped)
+    b, db = run(plain)
+    assert int(a["valid"].sum()) > 0.05 * rays.shape[1]
+    for k in a:
+        assert torch.equal(a[k], b[k]), (case, k)
+    assert torch.equal(da, db)

@@ -150,3 +150,40 @@ def test_system_uses_the_native_shard_of_a_single_source():
     assert sh.sources["x_start"].shape[0] == hi - lo
     assert torch.equal(sh.sources["y_start"], full.sources["y_start"][lo:hi])
     assert torch.equal(sh.sources["rank"], full.sources["rank"][lo:hi])
+
+
+@pytest.mark.parametrize("kind", ["angular_2d_base", "angular_backward", "point"])
+def test_fused_directed_source_equals_the_general_path(kind, monkeypatch):
+    """3D PointSource / AngularSource on the device write their rays with one kernel
+    (tfrt_rays_from_directions) straight into the (7,N) block the trace reads; the same source
+    built through the general torch path (rotation, offset, ends as separate fp32 operations)
+    must agree to fp32 rounding, and the system must hand the block on without a copy."""
+    from tensorflowraytrace_b200 import engine as eng
+    n = 20000
+
+    def build():
+        D.seed_all(11)
+        ang = D.RandomLambertianSphere(math.pi / 5, n)
+        if kind == "point":
+            return sources.PointSource(3, (0.5, -1.0, 2.0), (0.3, -0.2, 0.9), ang, [450.0, 650.0],
+                                       dense=True)
+        base = D.RandomUniformSquare(0.4, n, 0.3, 1)
+        return sources.AngularSource(3, (-4.0, 0.25, 1.0), (1.0, 0.5, -0.25), ang, base, [575.0],
+                                     dense=False, start_on_base=(kind != "angular_backward"),
+                                     ray_length=2.5)
+
+    fused = build()
+    assert fused._ray_block is not None and fused._ray_block.shape[0] == 7
+    monkeypatch.setattr(sources._DirectedSource, "_publish_fused", lambda *a, **k: False)
+    plain = build()
+    assert plain._ray_block is None
+    for f in ("x_start", "y_start", "z_start", "x_end", "y_end", "z_end", "wavelength"):
+        a, b = fused[f], plain[f]
+        assert a.shape == b.shape and float((a - b).abs().max()) < 2e-6, f
+    monkeypatch.undo()
+    system = eng.OpticalSystem3D(**helpers.EPS)
+    system.sources = [fused]
+    system.update()
+    rows = system.source_rows()
+    assert rows.data_ptr() == fused._ray_block.data_ptr() and rows.shape == (7, fused["x_start"].shape[0])
+    assert torch.equal(rows[3], fused["x_end"]) and torch.equal(rows[6], fused["wavelength"])
