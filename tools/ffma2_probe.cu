@@ -47,6 +47,15 @@ __global__ void __launch_bounds__(256) k_probe(int iters, const float *__restric
                 if (MODE == 5) a[i] = __ffma2_rn(bc(s[i]), b[i], a[i]);
                 if (MODE == 6) a[i] = __fmul2_rn(a[i], b[i]);
                 if (MODE == 7) { a[i].x = fmaf(s[i], a[i].x, c[i].x); a[i].y = fmaf(s[i], a[i].y, c[i].y); }
+                // MODE 8 / 9: seven FMA-bound FFMA2 (the MODE 2 form) + one / two MUFU.RCP per
+                // round: does a reciprocal take issue cycles away from the FMA pipe?
+                if (MODE == 8 || MODE == 9) {
+                    if (i < 7) a[i] = __ffma2_rn(bc(s[i]), a[i], bc(u));
+                    else {
+                        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[7].x));
+                        if (MODE == 9) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[7].y));
+                    }
+                }
             }
         }
     }
@@ -181,6 +190,8 @@ int main() {
     PROBE(5, "FFMA2 bcast32,pair,acc");
     PROBE(6, "FMUL2 pair,pair");
     PROBE(7, "scalar FFMA x2");
+    PROBE(8, "7 x FFMA2 bcast32,pair,bcast32 + 1 MUFU.RCP (per 8 slots)");
+    PROBE(9, "7 x FFMA2 bcast32,pair,bcast32 + 2 MUFU.RCP (per 8 slots)");
 #define TEST(M, what)                                                                            \
     {                                                                                            \
         const float ms = time_it([&] { k_test<M><<<sms * 4, 128>>>(iters, d_in, sink); });       \
