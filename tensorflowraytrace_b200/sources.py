@@ -541,7 +541,8 @@ class PrecompiledSource(RecursivelyUpdatable):
     jittering the end points at every update (tfrt/sources.py:1099-1358).
 
     arg : str  -> file written by `save` here or by the reference's `PrecompiledSource.save`
-                  (pickle of {"dimension", "standard_domains", "fields": {name: ndarray}});
+                  (pickle of {"dimension", "standard_domains", "fields": {name: ndarray}} --
+                  the reference's format; unpickling executes code, so load only files you trust);
           int  -> dimension of a new, empty source (fill it with `from_samples`);
           else -> an updated source object whose fields are copied.
     The stored rays live on the field device; `update()` samples `sample_count` of them with
