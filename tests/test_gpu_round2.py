@@ -374,3 +374,93 @@ def test_rescheduled_search_kernel_is_bit_identical_to_the_ptxas_build(case, mon
     for k in a:
         assert torch.equal(a[k], b[k]), (case, k)
     assert torch.equal(da, db)
+
+
+# --------------------------------------------------------------------------- tape reuse
+def _lens_engine():
+    scene = scenes.lens_optimize_config(ray_count=4096, step_count=5, name="reuse")
+    engine, params, _ = scenes.build_engine(scene, eps=helpers.EPS, compile_active_rays=False,
+                                            compile_finished_rays=True)
+    return scene, engine, params
+
+
+def test_trace_workspace_is_reused_only_when_no_graph_can_read_it():
+    """The engine keeps the tape of a trace for the next one (no allocation in steady state), but a
+    trace whose histories were read hangs on an autograd graph that will read the tape in its
+    backward pass: the next trace must then get a tape of its own, the old graph must still give
+    the right gradient, and a tape that is overwritten under a live graph must be refused."""
+    scene, engine, params = _lens_engine()
+    errf = scenes.imaging_error(scene)
+    K = scene["max_iterations"]
+
+    engine.ray_trace(K)
+    first = engine.last_trace
+    loss_a = errf(engine).sum()                      # reads finished_rays: graph A holds the tape
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    second = engine.last_trace
+    assert second.ws is not first.ws                 # A is alive: no reuse
+    loss_b = errf(engine).sum()
+    g_a = torch.autograd.grad(loss_a, params)
+    g_b = torch.autograd.grad(loss_b, params)
+    for a, b in zip(g_a, g_b):       # same system, same rays: same gradient (atomic order aside)
+        assert helpers.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
+    _, fresh_engine, fresh_params = _lens_engine()
+    fresh_engine.ray_trace(K)
+    g_ref = torch.autograd.grad(errf(fresh_engine).sum(), fresh_params)
+    for a, r in zip(g_a, g_ref):
+        assert helpers.rel_err(a.cpu().numpy(), r.cpu().numpy()) < 1e-6
+
+    # histories never read: the pending trace holds nothing, the next trace takes its tape over
+    del loss_a, loss_b, g_a, g_b
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    ws = engine.last_trace.ws
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    assert engine.last_trace.ws is ws
+    fin = engine.finished_rays
+    assert fin["x_end"].shape[0] == \
+        engine.last_trace.history_count(kernels.HISTORY["finished"]) > 0
+
+    # a tape overwritten under a live graph is detected, not differentiated
+    loss = errf(engine).sum()
+    engine.last_trace.ws.generation += 1
+    with pytest.raises(RuntimeError, match="overwritten"):
+        torch.autograd.grad(loss, params)
+
+
+def test_2d_tape_reuse_follows_the_same_rule():
+    scene = scenes.config1()
+    engine, params, _ = scenes.build_engine_2d(scene, eps=helpers.EPS, parametric=True)
+    K = scene["max_iterations"]
+
+    def loss_of(e):
+        fin = e.finished_rays
+        return ((fin["y_end"] - 0.3) ** 2).sum() + 0.1 * (fin["x_end"] * fin["y_start"]).sum()
+
+    engine.ray_trace(K)
+    first = engine.last_trace
+    loss_a = loss_of(engine)                         # graph A reads the tape in its backward
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    assert engine.last_trace.tape_f.data_ptr() != first.tape_f.data_ptr()
+    g_a = torch.autograd.grad(loss_a, params, allow_unused=True)
+    g_b = torch.autograd.grad(loss_of(engine), params, allow_unused=True)
+    for a, b in zip(g_a, g_b):
+        assert (a is None and b is None) or \
+            helpers.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
+    del loss_a, g_a, g_b
+    # unread traces hand their tape on
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    tape = engine.last_trace.tape_f.data_ptr()
+    engine.optical_system.update()
+    engine.ray_trace(K)
+    assert engine.last_trace.tape_f.data_ptr() == tape
+    assert engine.finished_rays["x_end"].shape[0] > 0
+    # overwritten under a live graph: refused
+    loss = loss_of(engine)
+    engine.last_trace.generation += 1
+    with pytest.raises(RuntimeError, match="overwritten"):
+        torch.autograd.grad(loss, params, allow_unused=True)
