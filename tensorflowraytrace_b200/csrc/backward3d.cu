@@ -75,7 +75,8 @@ struct BwdParams {
 };
 
 // Sum `vals[12]` over the lanes of `peers` (lanes sharing one triangle) into the group's lowest
-// lane.  Groups are tiny for incoherent rays, so a rank-by-rank gather is enough.
+// lane: the leader walks its peers in ascending lane order (one shuffle round per peer; groups are
+// tiny for incoherent rays, and the order makes the sum independent of the launch shape).
 __device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double vals[kSums],
                                                 bool &is_leader) {
     const int n = __popc(peers);
@@ -84,9 +85,12 @@ __device__ __forceinline__ void aggregate_peers(unsigned peers, int lane, double
     for (int off = 16; off > 0; off >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, off));
     const int leader = __ffs(peers) - 1;
     is_leader = (lane == leader);
+    unsigned rest = peers & (peers - 1);                   // the peers above the leader
+#pragma unroll 1
     for (int step = 1; step < maxn; ++step) {
-        const unsigned src = __fns(peers, 0, step + 1);   // lane of the peer with rank `step`
-        const int src_lane = (src == 0xffffffffu) ? lane : (int)src;
+        // lane of the peer with rank `step`, in ascending order (peeled off with ffs)
+        const int src_lane = rest ? __ffs(rest) - 1 : lane;
+        rest &= rest - 1;
 #pragma unroll
         for (int c = 0; c < kSums; ++c) {
             const double other = __shfl_sync(0xffffffffu, vals[c], src_lane);
@@ -184,15 +188,16 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) k_backward3d(BwdParam
                 const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
                 const double dinv = rsqrt(fmax(d2, 1e-12));
                 const double uh[3] = {d[0] * dinv, d[1] * dinv, d[2] * dinv};
-                double nr[3], cu[3], cv[3], clen = 1.0;
+                double nr[3], cu[3], cv[3], inv_clen = 1.0;
                 if (P.norm) {
                     nr[0] = P.norm[3 * tri]; nr[1] = P.norm[3 * tri + 1]; nr[2] = P.norm[3 * tri + 2];
                 } else {   // geometric normal from the corners, as in the forward kernel
                     for (int c = 0; c < 3; ++c) { cu[c] = B[c] - A[c]; cv[c] = C[c] - B[c]; }
                     const double cr[3] = {cu[1] * cv[2] - cu[2] * cv[1], cu[2] * cv[0] - cu[0] * cv[2],
                                           cu[0] * cv[1] - cu[1] * cv[0]};
-                    clen = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-                    for (int c = 0; c < 3; ++c) nr[c] = cr[c] / clen;
+                    // 1/|c| once (rsqrt) instead of a square root and six divisions
+                    inv_clen = rsqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+                    for (int c = 0; c < 3; ++c) nr[c] = cr[c] * inv_clen;
                 }
                 const double n2 = nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2];
                 const double ninv = rsqrt(fmax(n2, 1e-12));
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) k_backward3d(BwdParam
                         // the unnormalised cross product, g_c = (g_n - (g_n.n) n)/|c|; its map
                         // onto the corners is applied once per triangle by k_finish_tri_grads
                         const double dn = g_nr[0] * nr[0] + g_nr[1] * nr[1] + g_nr[2] * nr[2];
-                        for (int c = 0; c < 3; ++c) acc[3 + c] = (g_nr[c] - dn * nr[c]) / clen;
+                        for (int c = 0; c < 3; ++c) acc[3 + c] = (g_nr[c] - dn * nr[c]) * inv_clen;
                     }
                 }
             }
