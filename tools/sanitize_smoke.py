@@ -21,5 +21,13 @@ s2 = scenes.mixed_2d(ray_count=700)
 e2, p2, _ = scenes.build_engine_2d(s2, parametric=True, compile_dead_rays=True, compile_stopped_rays=True)
 e2.ray_trace(5)
 g2 = torch.autograd.grad((e2.finished_rays["y_end"] ** 2).sum(), p2, allow_unused=True)
+# rays born on the device (sampling kernels + the fused directed-source kernel) and the grid mode
+src = scenes.lens_optimize_device_source(5000, 7)
+scene5 = scenes.lens_optimize_config(ray_count=5000, step_count=5, name="san_dev", with_rays=False)
+e5, p5, _ = scenes.build_engine(scene5, source=src, compile_finished_rays=True)
+e5.optical_system.accel = "grid"
+e5.optical_system.update()
+e5.ray_trace(3)
+g5 = torch.autograd.grad(scenes.imaging_error(scene5)(e5).sum(), p5)
 torch.cuda.synchronize()
 print("ok", float(err.sum()), e4.last_trace.live_counts(), e2.last_trace.live_counts())
