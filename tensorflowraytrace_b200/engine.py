@@ -1160,7 +1160,7 @@ class OpticalEngine:
         both = seg is not None and arc is not None
         code = {"active": 0, "stopped": 1, "finished": 2, "dead": 3}
         sets = {}
-        if n * max_iterations <= (1 << 20):
+        if n * max_iterations <= (1 << 13) or (both and n * max_iterations <= (1 << 20)):
             # small traces are latency bound: ONE device->host copy of the status / hit tape,
             # the ordering on the host (NumPy), one host->device copy of the gather indices
             import numpy as np
@@ -1200,9 +1200,17 @@ class OpticalEngine:
             is_arc = tr.tape_hit[:, :n] < -1
             if not both:
                 # one geometry: the live list stays in source order, so every set is the
-                # row-major (iteration, slot) list of its status code
+                # row-major (iteration, slot) list of its status code.  One stable sort groups
+                # the (iteration, slot) positions by code and one count gives the set sizes: a
+                # single wait for the device instead of one per set
+                flat = status.reshape(-1)
+                _, where = torch.sort(flat, stable=True)
+                sizes = torch.bincount(flat, minlength=4)[:4].tolist()
+                off = 0
                 for name, c in code.items():
-                    sets[name] = torch.nonzero(status == c, as_tuple=True)
+                    idx = where[off:off + sizes[c]]
+                    sets[name] = (torch.div(idx, n, rounding_mode="floor"), idx % n)
+                    off += sizes[c]
             else:
                 acc = {name: ([], []) for name in code}
                 order = torch.arange(n, device=dev)
